@@ -1,0 +1,169 @@
+/*
+ * structured_gpu.h -- C ABI of the B200 (sm_100a) residual + Jacobian path.
+ *
+ * Drop-in boundary for the hot path of anandpratap/structured.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree).
+ * Plain pointers and sizes only; all functions return 0 (SGPU_OK) or a negative error code and
+ * leave a message retrievable with sgpu_last_error().  One context per Mesh; calls on one context
+ * are issued from one host thread (the reference is single threaded, src/main.cpp:8-44).
+ *
+ * Host array layouts are exactly the reference's rarray layouts (row-major, last index fastest):
+ *   vertices  xv, yv      [ni][nj]              Mesh::xv.data()          src/utils/mesh.cpp:354-355
+ *   state     q, rhs, dt  [nic][njc][nv]        Solution::q.data()       src/solver/solution.cpp:28,49-51
+ *   fields    per cell    [nic][njc]
+ * with nic = ni-1, njc = nj-1, nv = 4 + ntrans.  Flat index (i*njc + j)*nv + k is the row/column
+ * numbering of the Jacobian (src/solver/solver.cpp:73-88,164-166).
+ *
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels on the context's device and
+ * fails with SGPU_ERR_CUDA when that is impossible.
+ */
+#ifndef STRUCTURED_GPU_H
+#define STRUCTURED_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPU_OK            0
+#define SGPU_ERR_ARG      -1   /* bad argument / unsupported configuration */
+#define SGPU_ERR_CUDA     -2   /* CUDA runtime error (message has the CUDA string) */
+#define SGPU_ERR_STATE    -3   /* call order (e.g. residual before set_grid) */
+#define SGPU_ERR_OVERFLOW -4   /* COO export would overflow `int nnz` (src/solver/solution.h:16) */
+
+/* [[boundary]] type strings of src/model/bc.cpp:494-524 */
+enum sgpu_bc_type {
+    SGPU_BC_FREESTREAM = 0,      /* "freestream"      bc.cpp:26-60   */
+    SGPU_BC_SLIPWALL = 1,        /* "slipwall"        bc.cpp:78-128  */
+    SGPU_BC_WALL = 2,            /* "wall" adiabatic  bc.cpp:150-204 */
+    SGPU_BC_ISOTHERMALWALL = 3,  /* "isothermalwall"  bc.cpp:388-427 */
+    SGPU_BC_WAKE = 4,            /* "wake"            bc.cpp:224-263 */
+    SGPU_BC_OUTFLOW = 5,         /* "outflow"         bc.cpp:284-311 */
+    SGPU_BC_PERIODIC = 6         /* "periodic"        bc.cpp:329-365 */
+};
+/* face ids of src/model/bc.h:8-11 */
+enum sgpu_face { SGPU_FACE_BOTTOM = 0, SGPU_FACE_RIGHT = 1, SGPU_FACE_TOP = 2, SGPU_FACE_LEFT = 3 };
+/* solver.flux strings, src/model/eulerequation.cpp:123-128 */
+enum sgpu_flux { SGPU_FLUX_ROE = 0, SGPU_FLUX_AUSM = 1 };
+/* which state array a residual is evaluated on / an update writes (src/solver/solver.cpp:104,110) */
+enum sgpu_state { SGPU_STATE_Q = 0, SGPU_STATE_Q_TMP = 1 };
+
+/* One [[boundary]] table (src/model/bc.cpp:472-488). start/end index the PADDED arrays, inclusive;
+ * a negative `end` is resolved as in BoundaryContainer::get_index (bc.cpp:436-457). */
+typedef struct sgpu_bc {
+    int type;      /* sgpu_bc_type */
+    int face;      /* sgpu_face */
+    int start;
+    int end;
+    double u, v, T;
+} sgpu_bc;
+
+/* Everything EulerEquation's constructor reads from Config (src/model/eulerequation.cpp:31-133,
+ * src/utils/config.cpp:32-87).  gamma is the reference's constant 1.4 (src/common.h:40). */
+typedef struct sgpu_desc {
+    int ni, nj;                 /* geometry.ni / geometry.nj : GLOBAL vertex counts */
+    int ntrans;                 /* 0 = laminar (the reference), 1 = Spalart-Allmaras extension */
+    int order, lhs_order;       /* solver.order / solver.lhs_order : 1 or 2 */
+    int flux;                   /* sgpu_flux */
+    double rho_inf, u_inf, v_inf, p_inf, T_inf, mu_inf, pr_inf;   /* [freestream] */
+    double dpdx, dpdy;          /* [source] */
+    int n_bc;
+    const sgpu_bc* bc;          /* in config-file order (BoundaryContainer::apply, bc.cpp:430-433) */
+    int device;                 /* CUDA device ordinal */
+    /* j-slab partition for multi-GPU runs: this context owns global cell rows [j_begin, j_end).
+     * j_begin = j_end = 0 means the whole grid. */
+    int j_begin, j_end;
+} sgpu_desc;
+
+typedef struct sgpu_ctx sgpu_ctx;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* replaces Mesh::setup -> Solution / EulerEquation construction (src/utils/mesh.cpp:392-414) */
+int sgpu_create(const sgpu_desc* desc, sgpu_ctx** out);
+int sgpu_destroy(sgpu_ctx* ctx);
+const char* sgpu_last_error(const sgpu_ctx* ctx);       /* ctx may be NULL: last create() failure */
+int sgpu_set_stream(sgpu_ctx* ctx, void* cuda_stream);  /* all later work is enqueued on this stream */
+int sgpu_synchronize(sgpu_ctx* ctx);
+int sgpu_dims(const sgpu_ctx* ctx, int* nic, int* njc, int* nv, int* j_begin, int* j_end);
+
+/* ---- static inputs ------------------------------------------------------------------------- */
+/* replaces Mesh::simple_loader / plot3d_loader output + Mesh::calc_metrics (src/utils/mesh.cpp:134-279):
+ * GLOBAL vertex arrays [ni][nj]; the metrics are evaluated on the device from these. */
+int sgpu_set_grid(sgpu_ctx* ctx, const double* xv, const double* yv);
+/* SA extension inputs, GLOBAL [nic][njc]: name = "wall_distance" | "beta" (no reference counterpart) */
+int sgpu_set_field(sgpu_ctx* ctx, const char* name, const double* field);
+/* metrics as Mesh::calc_metrics leaves them, for parity checks: normal_chi [ni][njc][2],
+ * normal_eta [nic][nj][2], volume [nic][njc] (GLOBAL shapes; only owned rows are written) */
+int sgpu_get_metrics(sgpu_ctx* ctx, double* normal_chi, double* normal_eta, double* volume);
+
+/* ---- state --------------------------------------------------------------------------------- */
+/* Solution::q / q_tmp  (src/solver/solution.cpp:28,51), GLOBAL [nic][njc][nv] host arrays.
+ * set: owned rows plus the slab's ghost rows are read.  get: only owned rows are written. */
+int sgpu_set_state(sgpu_ctx* ctx, int which, const double* q);
+int sgpu_get_state(sgpu_ctx* ctx, int which, double* q);
+int sgpu_copy_state(sgpu_ctx* ctx, int dst, int src);   /* set_rarray, src/solver/solver.cpp:4-10,114 */
+int sgpu_get_rhs(sgpu_ctx* ctx, double* rhs);            /* Solution::rhs */
+int sgpu_get_dt(sgpu_ctx* ctx, double* dt);              /* Solution::dt (all nv entries of a cell equal) */
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* EulerEquation::calc_dt(cfl) on state q  (src/model/eulerequation.cpp:237-259) */
+int sgpu_calc_dt(sgpu_ctx* ctx, double cfl);
+/* EulerEquation::calc_residual(state, rhs, lhs)  (src/model/eulerequation.cpp:202-232): applies the
+ * boundary conditions to `which`, evaluates rhs on the device.  If l2sq != NULL it receives, for each
+ * of the nv equations, sum over owned cells of rhs^2 (the sums of src/solver/solver.cpp:125-134 before
+ * the sqrt, so that slabs can be added) and the call synchronizes. */
+int sgpu_residual(sgpu_ctx* ctx, int which, int lhs, double* l2sq);
+/* Same through HOST buffers: q -> device, residual, rhs -> host.  This is the call-site form of
+ * `equation->calc_residual(solution->q, solution->rhs)` (src/solver/solver.cpp:104). */
+int sgpu_residual_host(sgpu_ctx* ctx, const double* q, double* rhs, int lhs);
+/* update_rk4: q_tmp = q + rhs*dt/(4-order)   (src/solver/solver.cpp:20-26,111) */
+int sgpu_rk_stage(sgpu_ctx* ctx, int order);
+/* update_forward_euler: q = q + rhs*dt       (src/solver/solver.cpp:12-18,105) */
+int sgpu_forward_euler(sgpu_ctx* ctx);
+/* The explicit branch of Solver::step (src/solver/solver.cpp:66,103-134) entirely on the device:
+ * calc_dt, 1 (forward_euler) or 4 (rk4_jameson) residual evaluations + updates, then l2sq[nv]
+ * of the last rhs.  scheme: 0 = forward_euler, 1 = rk4_jameson. */
+int sgpu_explicit_step(sgpu_ctx* ctx, int scheme, double cfl, double* l2sq);
+
+/* ---- Jacobian ------------------------------------------------------------------------------ */
+/* Replaces trace_on .. trace_off + sparse_jac(1, nt, nt, repeat, q, &nnz, &rind, &cind, &values, options)
+ * (src/solver/solver.cpp:72-90,156): d rhs / d q of calc_residual(q, lhs = true) at state q.
+ * Output arrays are malloc()ed and owned by the caller, who free()s them exactly as after sparse_jac
+ * (src/solver/solver.cpp:181-183).  Entries are sorted by (row, col); duplicates are summed.
+ * apply_lhs_transform != 0 additionally performs the loop of src/solver/solver.cpp:162-171:
+ * values = -values, diagonal += 1/dt[row] (sgpu_calc_dt must have been called). */
+int sgpu_jacobian_coo(sgpu_ctx* ctx, int* nnz, unsigned int** rind, unsigned int** cind, double** values,
+                      int apply_lhs_transform);
+/* Device-resident block-stencil form (no size limit): evaluates the Jacobian and leaves it on the device.
+ * *slots = number of stencil slots per cell, block layout J[slot][r][c][cell]. build_ms (may be NULL)
+ * receives the device time of the build. */
+int sgpu_jacobian_device(sgpu_ctx* ctx, int* slots, float* build_ms);
+/* y = J x  and  y = J^T x with the device-resident Jacobian (adjoint building block); x, y host [nic][njc][nv] */
+int sgpu_jacobian_apply(sgpu_ctx* ctx, int transpose, const double* x, double* y);
+
+/* ---- multi-GPU j-slabs ---------------------------------------------------------------------- */
+/* Two ghost rows of q per interior slab edge.  side: 0 = low-j neighbour, 1 = high-j neighbour.
+ * pack writes this slab's two boundary rows into a contiguous DEVICE buffer of sgpu_halo_count()
+ * doubles (layout [nv][2][nic]); unpack reads the neighbour's packed rows into this slab's ghost rows. */
+int sgpu_halo_count(const sgpu_ctx* ctx);
+int sgpu_halo_pack(sgpu_ctx* ctx, int which, int side, double* dev_buf);
+int sgpu_halo_unpack(sgpu_ctx* ctx, int which, int side, const double* dev_buf);
+/* Peer-memory variant: register the neighbour's ghost-row buffer (a device pointer valid on this
+ * device, e.g. from cudaIpcOpenMemHandle) so that sgpu_halo_push stores the boundary rows straight
+ * into the neighbour's memory over NVLink. */
+int sgpu_halo_recv_buffer(sgpu_ctx* ctx, int side, double** dev_ptr);
+int sgpu_halo_set_peer(sgpu_ctx* ctx, int side, double* peer_recv_buf);
+int sgpu_halo_push(sgpu_ctx* ctx, int which);
+int sgpu_halo_pull(sgpu_ctx* ctx, int which);   /* ghost rows <- own recv buffers */
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* number of kernels this library launched on the context since creation */
+long long sgpu_launch_count(const sgpu_ctx* ctx);
+/* device time (ms, CUDA events on the context's stream) of the most recent residual kernel launches:
+ * fills at most n entries, returns how many are available */
+int sgpu_kernel_times(sgpu_ctx* ctx, float* ms, int n);
+int sgpu_enable_kernel_timing(sgpu_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
