@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on B200: Mcell residual evals/s (+ Jacobian build ms, % HBM roofline).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   the CPU implementation of the same path on the host cores
+
+A "step" is one residual evaluation (boundary conditions + the fused residual kernel + norm partials;
+with N > 1 preceded by the ghost-row exchange) over the whole synthetic grid, state resident in HBM.
+Workload (BASELINE.json configs[2] / configs[4]): bump-channel grid, SA turbulent (nv = 5), MUSCL + Roe +
+viscous, fp64.  N = 1: 4096 x 4096 cells.  N > 1: 16384 x (1024 N) cells in j-slabs of 16384 x 1024 per GPU
+(N = 8 is the named 16384 x 8192 grid) -- the same 16.8 M cells per GPU, i.e. weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_CELL = {4: 104.0, 5: 136.0}          # compulsory bytes per cell-eval
+JAC_B_PER_CELL = {4: 1736.0, 5: 2696.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nic", type=int, default=0, help="override grid (cells in i)")
+    ap.add_argument("--njc", type=int, default=0, help="override grid (cells in j, per GPU)")
+    ap.add_argument("--ntrans", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-jacobian", action="store_true")
+    return ap.parse_args()
+
+
+def workload_dims(args, n_gpus):
+    if args.nic and args.njc:
+        return args.nic, args.njc * n_gpus, args.njc
+    if n_gpus == 1:
+        return 4096, 4096, 4096
+    return 16384, 1024 * n_gpus, 1024
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(nic, njc_total, ntrans):
+    from structured_b200.cases import turbulent_channel_case
+    return turbulent_channel_case(nic, njc_total, ntrans=ntrans, order=2, flux="roe", mach=0.2, reynolds=5e6, periodic=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU baseline (the checker, timed): port of the same workload on a bounded sample + the reference itself
+# -------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, nic, njc, ntrans, reps = args
+    sys.path.insert(0, ROOT)
+    from oracle.bindings import PortOracle, RefOracle
+    case = build_case(nic, njc, ntrans)
+    q = case.perturbed_q()
+    orc = RefOracle(case) if kind == "reference" else PortOracle(case)
+    orc.time_residual(q, 1)
+    t = orc.time_residual(q, reps)
+    return t
+
+
+def cpu_throughput(kind, nic, njc, ntrans, reps, procs):
+    """procs independent evaluations run concurrently (the reference is single threaded: src/SConstruct:34-36
+    OpenMP option is broken and scales negatively); returns Mcell-evals/s over all procs."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    t0 = time.time()
+    with ctx.Pool(procs) as pool:
+        ts = pool.map(_cpu_worker, [(kind, nic, njc, ntrans, reps)] * procs)
+    wall = max(ts)
+    return procs * nic * njc * reps / wall / 1e6, wall, time.time() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.bindings import have_ref
+    nic, njc_total, _ = workload_dims(args, args.gpus)
+    cores = os.cpu_count() or 1
+    sn = 512                                        # sample: 512 x 512 cells of the same workload per core
+    reps = max(1, args.steps // 4)
+    for _ in range(max(1, min(args.warmup, 1))):
+        pass
+    val, wall, total = cpu_throughput("port", sn, sn, args.ntrans, reps, cores)
+    extra = {}
+    if have_ref() and not args.no_cpu_baseline:
+        v1, _, _ = cpu_throughput("reference", sn, sn, 0, reps, 1)
+        extra = {"reference_laminar_1core_mcells": round(v1, 4)}
+    sample = ("%d concurrent single-thread evaluations (one per host core) x %d reps of a %dx%d-cell sample of the workload "
+              "(same grid generator, state, BCs, nv=%d); CPU cost per cell is size independent") % (cores, reps, sn, sn, 4 + args.ntrans)
+    out = {"impl": "reference", "metric": "residual_mcell_evals_per_s", "value": round(val, 4), "unit": "Mcell-evals/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / reps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "SA turbulent bump channel %dx%d cells (timed on a %dx%d sample per core), MUSCL+Roe+viscous, nv=%d" % (nic, njc_total, sn, sn, 4 + args.ntrans)},
+           "cpu_baseline": {"value": round(val, 4), "unit": "Mcell-evals/s", "cores": cores, "kind": "port", "sample": sample, **extra},
+           "e2e": {"value": round(val, 4), "unit": "Mcell-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from structured_b200.api import GpuEulerEquation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    nic, njc_total, njc_per = workload_dims(args, n_gpus)
+    nv = 4 + args.ntrans
+    case = build_case(nic, njc_total, args.ntrans)
+    j0, j1 = rank * njc_per, (rank + 1) * njc_per
+    eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0)
+    # synthetic state, generated per rank for its rows only would need the global index: build rows lazily
+    q = case.perturbed_q()
+    eq.set_state(q, 0)
+    eq.synchronize()
+    cells_local = nic * njc_per
+    cells_total = nic * njc_total
+
+    halo = None
+    if world > 1:
+        n = eq.halo_count()
+        halo = {s: (torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")) for s in (0, 1)}
+
+    def exchange():
+        ops = []
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= nb < world:
+                send, recv = halo[side]
+                eq.halo_pack(0, side, send.data_ptr())
+                ops.append(dist.P2POp(dist.isend, send, nb))
+                ops.append(dist.P2POp(dist.irecv, recv, nb))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= nb < world:
+                eq.halo_unpack(0, side, halo[side][1].data_ptr())
+
+    l2 = np.zeros(nv)
+
+    def step():
+        if world > 1:
+            exchange()
+        eq.residual_device(0, lhs=False, norms=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    eq.enable_kernel_timing(True)
+    launches0 = eq.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eq.launch_count - launches0
+    ktimes = eq.kernel_times()
+    eq.enable_kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = cells_total / (ms_step * 1e-3) / 1e6
+
+    # residual norms once (outside the timed loop: the reference computes them once per step, not per evaluation)
+    l2 = eq.residual_device(0, norms=True)
+
+    # ---- e2e: the call-site form through HOST buffers (pinned), H2D + kernel + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        qh = torch.from_numpy(q).pin_memory()
+        rh = torch.empty_like(qh).pin_memory()
+        qn, rn = qh.numpy(), rh.numpy()
+        k_e2e = max(2, min(args.steps, 5))
+        eq.calc_residual(qn, out=rn)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k_e2e):
+            if world > 1:
+                pass                                    # set_state reads the neighbour rows from the host array itself
+            eq.calc_residual(qn, out=rn)
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        rows_in = njc_per + (0 if world == 1 else (2 if rank in (0, world - 1) else 4))
+        e2e = {"value": round(cells_total / (ms_e / k_e2e * 1e-3) / 1e6, 3), "unit": "Mcell-evals/s",
+               "h2d_bytes_per_step": int(nic * rows_in * nv * 8) * 1, "d2h_bytes_per_step": int(nic * njc_per * nv * 8),
+               "steps": k_e2e, "note": "per-GPU bytes; sgpu_residual_host(q_host, rhs_host) from pinned host arrays"}
+
+    # ---- Jacobian build (second half of the metric); skipped when the device form is unavailable
+    jac = None
+    if not args.no_jacobian:
+        try:
+            slots, ms = eq.jacobian_device()
+            slots, ms = eq.jacobian_device()
+            jac = {"build_ms": round(ms, 4), "slots": slots, "Mcell_per_s": round(cells_local / (ms * 1e-3) / 1e6, 2),
+                   "roofline_frac": round(cells_local * JAC_B_PER_CELL[nv] / (ms * 1e-3) / 1e9 / measured_peak()[0], 4)}
+        except Exception as ex:  # noqa: BLE001
+            jac = {"unavailable": str(ex)[:120]}
+
+    peak, peak_src = measured_peak()
+    kt = float(np.mean(ktimes)) if len(ktimes) else None
+    achieved = cells_local * B_PER_CELL[nv] / (kt * 1e-3) / 1e9 if kt else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "residual_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": round(achieved, 2) if achieved else None, "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                "kernel": "residual_kernel<nv=%d,order=2,roe,viscous>" % nv, "kernel_ms": round(kt, 4) if kt else None,
+                "bytes_per_cell": B_PER_CELL[nv], "peak_source": peak_src}
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        from oracle.bindings import have_ref
+        sn, reps = 512, 4
+        v, wall, _ = cpu_throughput("port", sn, sn, args.ntrans, reps, 1)
+        cpu = {"value": round(v, 4), "unit": "Mcell-evals/s", "cores": 1, "kind": "port",
+               "sample": "%d reps of a %dx%d-cell sample of the same workload (nv=%d), 1 thread" % (reps, sn, sn, nv)}
+        if have_ref():
+            v2, _, _ = cpu_throughput("reference", sn, sn, 0, reps, 1)
+            cpu["reference_laminar_1core"] = round(v2, 4)
+
+    if rank == 0:
+        out = {"metric": "residual_mcell_evals_per_s", "value": round(value, 2), "unit": "Mcell-evals/s", "n_gpus": n_gpus,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "SA turbulent bump channel %dx%d cells, MUSCL+Roe+viscous, nv=%d, fp64%s" % (
+                              nic, njc_total, nv, "" if n_gpus == 1 else ", j-slabs of %dx%d per GPU" % (nic, njc_per)),
+                          "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
+                          "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel"},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+               "jacobian": jac, "l2norm": [float(x) for x in np.sqrt(l2)]}
+        print(json.dumps(out), flush=True)
+    eq.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

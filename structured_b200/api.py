@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's operator interface over the C ABI (include/structured_gpu.h).
+
+`GpuEulerEquation` has the methods of `EulerEquation` (src/model/eulerequation.h:53-55: calc_residual,
+calc_dt, initialize) plus the pieces of `Solver::step` (src/solver/solver.cpp:53-196) that the GPU path
+takes over: the stage updates, the residual norms and the sparse Jacobian that replaces ADOL-C's
+`sparse_jac`.  All compute goes through libstructured_gpu.so; if the library or a CUDA device is missing
+every call raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .cases import BC_TYPES, FACES, FLUXES, Case
+
+_P = ctypes.POINTER(ctypes.c_double)
+_U = ctypes.POINTER(ctypes.c_uint)
+
+SYMBOLS = [
+    "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
+    "sgpu_set_grid", "sgpu_set_field", "sgpu_get_metrics", "sgpu_set_state", "sgpu_get_state", "sgpu_copy_state",
+    "sgpu_get_rhs", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_rk_stage",
+    "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
+    "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_set_peer",
+    "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
+]
+
+
+class SgpuBc(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("face", ctypes.c_int), ("start", ctypes.c_int), ("end", ctypes.c_int),
+                ("u", ctypes.c_double), ("v", ctypes.c_double), ("T", ctypes.c_double)]
+
+
+class SgpuDesc(ctypes.Structure):
+    _fields_ = [("ni", ctypes.c_int), ("nj", ctypes.c_int), ("ntrans", ctypes.c_int), ("order", ctypes.c_int),
+                ("lhs_order", ctypes.c_int), ("flux", ctypes.c_int),
+                ("rho_inf", ctypes.c_double), ("u_inf", ctypes.c_double), ("v_inf", ctypes.c_double),
+                ("p_inf", ctypes.c_double), ("T_inf", ctypes.c_double), ("mu_inf", ctypes.c_double),
+                ("pr_inf", ctypes.c_double), ("dpdx", ctypes.c_double), ("dpdy", ctypes.c_double),
+                ("n_bc", ctypes.c_int), ("bc", ctypes.POINTER(SgpuBc)), ("device", ctypes.c_int),
+                ("j_begin", ctypes.c_int), ("j_end", ctypes.c_int)]
+
+
+class SgpuError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstructured_gpu.so")
+
+
+def load_library():
+    """Load libstructured_gpu.so (building it if the sources are newer and nvcc is available)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        from . import build as _build
+        _build.build()
+    L = ctypes.CDLL(path)
+    L.sgpu_last_error.restype = ctypes.c_char_p
+    L.sgpu_last_error.argtypes = [ctypes.c_void_p]
+    L.sgpu_launch_count.restype = ctypes.c_longlong
+    L.sgpu_launch_count.argtypes = [ctypes.c_void_p]
+    L.sgpu_create.argtypes = [ctypes.POINTER(SgpuDesc), ctypes.POINTER(ctypes.c_void_p)]
+    _LIB = L
+    return L
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_P)
+
+
+def make_desc(case: Case, device: int = 0, j_begin: int = 0, j_end: int = 0):
+    n = len(case.boundaries)
+    arr = (SgpuBc * max(n, 1))()
+    for k, b in enumerate(case.boundaries):
+        if b.type not in BC_TYPES:
+            raise SgpuError("Wrong type of BC.")  # src/model/bc.cpp:523
+        arr[k] = SgpuBc(BC_TYPES[b.type], FACES[b.face], b.start, b.end, b.u, b.v, b.T)
+    if case.flux not in FLUXES:
+        raise SgpuError("Flux not found.")  # src/model/eulerequation.cpp:128
+    d = SgpuDesc(case.ni, case.nj, case.ntrans, case.order, case.lhs_order if case.lhs_order is not None else case.order,
+                 FLUXES[case.flux], case.rho_inf, case.u_inf, case.v_inf, case.p_inf, case.T_inf, case.mu_inf,
+                 case.pr_inf, case.dpdx, case.dpdy, n, arr, device, j_begin, j_end)
+    return d, arr
+
+
+class GpuEulerEquation:
+    """EulerEquation + the explicit/implicit pieces of Solver::step on one B200 (or one j-slab of a grid)."""
+
+    def __init__(self, case: Case, device: int = 0, j_begin: int = 0, j_end: int = 0, stream: Optional[int] = None):
+        self.L = load_library()
+        self.case = case
+        d, self._keep = make_desc(case, device, j_begin, j_end)
+        h = ctypes.c_void_p()
+        rc = self.L.sgpu_create(ctypes.byref(d), ctypes.byref(h))
+        if rc != 0:
+            raise SgpuError("sgpu_create: %s" % self.L.sgpu_last_error(None).decode())
+        self.h = h
+        self.nic, self.njc, self.nv = case.nic, case.njc, case.nv
+        self.j_begin, self.j_end = (j_begin, j_end) if (j_begin or j_end) else (0, case.njc)
+        if stream is not None:
+            self._ck(self.L.sgpu_set_stream(self.h, ctypes.c_void_p(stream)))
+        self._ck(self.L.sgpu_set_grid(self.h, _dp(np.ascontiguousarray(case.xv, dtype=np.float64)),
+                                      _dp(np.ascontiguousarray(case.yv, dtype=np.float64))))
+        if case.ntrans:
+            if case.wall_distance is not None:
+                self.set_field("wall_distance", case.wall_distance)
+            if case.beta is not None:
+                self.set_field("beta", case.beta)
+
+    # ---- plumbing
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise SgpuError("libstructured_gpu error %d: %s" % (rc, self.L.sgpu_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self.L.sgpu_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.sgpu_launch_count(self.h))
+
+    def _state_array(self):
+        return np.zeros((self.nic, self.njc, self.nv))
+
+    # ---- static inputs
+    def set_field(self, name: str, field: np.ndarray):
+        self._ck(self.L.sgpu_set_field(self.h, name.encode(), _dp(np.ascontiguousarray(field, dtype=np.float64))))
+
+    def metrics(self):
+        nchi = np.zeros((self.case.ni, self.njc, 2)); neta = np.zeros((self.nic, self.case.nj, 2)); vol = np.zeros((self.nic, self.njc))
+        self._ck(self.L.sgpu_get_metrics(self.h, _dp(nchi), _dp(neta), _dp(vol)))
+        return nchi, neta, vol
+
+    # ---- state
+    def set_state(self, q: np.ndarray, which: int = 0):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == (self.nic, self.njc, self.nv)
+        self._ck(self.L.sgpu_set_state(self.h, which, _dp(q)))
+        self.synchronize()
+
+    def get_state(self, which: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._state_array() if out is None else out
+        self._ck(self.L.sgpu_get_state(self.h, which, _dp(out)))
+        return out
+
+    def get_rhs(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._state_array() if out is None else out
+        self._ck(self.L.sgpu_get_rhs(self.h, _dp(out)))
+        return out
+
+    def get_dt(self) -> np.ndarray:
+        out = self._state_array()
+        self._ck(self.L.sgpu_get_dt(self.h, _dp(out)))
+        return out
+
+    def initialize(self):
+        """EulerEquation::initialize (src/model/eulerequation.cpp:262-291): q = q_tmp = freestream."""
+        q = self.case.freestream_q()
+        self.set_state(q, 0)
+        self.set_state(q, 1)
+        return q
+
+    # ---- hot path
+    def calc_dt(self, cfl: float):
+        self._ck(self.L.sgpu_calc_dt(self.h, ctypes.c_double(cfl)))
+
+    def residual_device(self, which: int = 0, lhs: bool = False, norms: bool = False):
+        """Residual of the device-resident state; returns sum(rhs^2) per equation if norms."""
+        if norms:
+            l2 = np.zeros(self.nv)
+            self._ck(self.L.sgpu_residual(self.h, which, int(lhs), _dp(l2)))
+            return l2
+        self._ck(self.L.sgpu_residual(self.h, which, int(lhs), None))
+        return None
+
+    def calc_residual(self, q: np.ndarray, lhs: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """equation->calc_residual(q, rhs, lhs) with HOST arrays (src/solver/solver.cpp:80,93,104,110)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        out = self._state_array() if out is None else out
+        self._ck(self.L.sgpu_residual_host(self.h, _dp(q), _dp(out), int(lhs)))
+        return out
+
+    def rk_stage(self, order: int):
+        self._ck(self.L.sgpu_rk_stage(self.h, order))
+
+    def forward_euler(self):
+        self._ck(self.L.sgpu_forward_euler(self.h))
+
+    def copy_state(self, dst: int, src: int):
+        self._ck(self.L.sgpu_copy_state(self.h, dst, src))
+
+    def explicit_step(self, cfl: float, scheme: Optional[str] = None) -> np.ndarray:
+        """One explicit Solver::step on the device; returns the L2 norms of the last rhs (solver.cpp:125-134)."""
+        scheme = self.case.scheme if scheme is None else scheme
+        if scheme not in ("forward_euler", "rk4_jameson"):
+            raise SgpuError("scheme not defined.")  # src/solver/solver.cpp:119
+        l2 = np.zeros(self.nv)
+        self._ck(self.L.sgpu_explicit_step(self.h, 0 if scheme == "forward_euler" else 1, ctypes.c_double(cfl), _dp(l2)))
+        return np.sqrt(l2)
+
+    # ---- Jacobian
+    def jacobian_coo(self, apply_lhs_transform: bool = False):
+        """Replacement of sparse_jac (src/solver/solver.cpp:156): returns (rind, cind, values) numpy copies."""
+        nnz = ctypes.c_int(); r, c, v = _U(), _U(), _P()
+        self._ck(self.L.sgpu_jacobian_coo(self.h, ctypes.byref(nnz), ctypes.byref(r), ctypes.byref(c), ctypes.byref(v), int(apply_lhs_transform)))
+        n = nnz.value
+        libc = ctypes.CDLL(None)
+        libc.free.argtypes = [ctypes.c_void_p]
+        ri = np.ctypeslib.as_array(r, (max(n, 1),))[:n].copy(); ci = np.ctypeslib.as_array(c, (max(n, 1),))[:n].copy()
+        va = np.ctypeslib.as_array(v, (max(n, 1),))[:n].copy()
+        for p in (r, c, v):
+            libc.free(ctypes.cast(p, ctypes.c_void_p))
+        return ri, ci, va
+
+    def jacobian_device(self):
+        slots = ctypes.c_int(); ms = ctypes.c_float()
+        self._ck(self.L.sgpu_jacobian_device(self.h, ctypes.byref(slots), ctypes.byref(ms)))
+        return slots.value, ms.value
+
+    def jacobian_apply(self, x: np.ndarray, transpose: bool = False) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = self._state_array()
+        self._ck(self.L.sgpu_jacobian_apply(self.h, int(transpose), _dp(x), _dp(y)))
+        return y
+
+    # ---- halos (multi-GPU j-slabs)
+    def halo_count(self) -> int:
+        return int(self.L.sgpu_halo_count(self.h))
+
+    def halo_pack(self, which: int, side: int, dev_ptr: int):
+        self._ck(self.L.sgpu_halo_pack(self.h, which, side, ctypes.c_void_p(dev_ptr)))
+
+    def halo_unpack(self, which: int, side: int, dev_ptr: int):
+        self._ck(self.L.sgpu_halo_unpack(self.h, which, side, ctypes.c_void_p(dev_ptr)))
+
+    # ---- instrumentation
+    def enable_kernel_timing(self, on: bool = True):
+        self._ck(self.L.sgpu_enable_kernel_timing(self.h, int(on)))
+
+    def kernel_times(self, n: int = 4096) -> np.ndarray:
+        buf = (ctypes.c_float * n)()
+        k = self.L.sgpu_kernel_times(self.h, buf, n)
+        return np.array(buf[:k], dtype=np.float64)

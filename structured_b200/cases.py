@@ -135,10 +135,10 @@ def write_grid_p3d(filename: str, xv: np.ndarray, yv: np.ndarray) -> None:
             np.savetxt(f, a.T.reshape(-1), fmt="%.17e")
 
 
-def load_case(config_path: str) -> Case:
-    """Parse a stock reference `.inp` (TOML) + its grid, like Config / Mesh / BoundaryContainer do."""
-    with open(config_path, "rb") as f:
-        t = tomllib.load(f)
+def case_from_toml(text: str, xv: Optional[np.ndarray] = None, yv: Optional[np.ndarray] = None, base_dir: str = ".") -> Case:
+    """Parse reference `.inp` TOML text like Config / BoundaryContainer do; the grid is read from
+    geometry.filename unless vertex arrays are passed."""
+    t = tomllib.loads(text)
     g, fs, so = t.get("geometry", {}), t.get("freestream", {}), t.get("solver", {})
     src, io = t.get("source", {}), t.get("io", {})
     ni, nj = int(g.get("ni", 0)), int(g.get("nj", 0))
@@ -161,11 +161,21 @@ def load_case(config_path: str) -> Case:
         c.boundaries.append(Boundary(type=b.get("type", ""), face=b.get("face", ""), start=int(b.get("start", 0)),
                                      end=int(b.get("end", 0)), u=float(b.get("u", 0.0)), v=float(b.get("v", 0.0)),
                                      T=float(b.get("T", 0.0))))
-    fn = g.get("filename", "grid.unf2")
-    if not os.path.isabs(fn):
-        fn = os.path.join(os.path.dirname(os.path.abspath(config_path)), fn)
-    c.xv, c.yv = read_grid(fn, ni, nj, g.get("format", "grid.unf2"))
+    if xv is not None:
+        c.xv, c.yv = np.ascontiguousarray(xv, dtype=np.float64), np.ascontiguousarray(yv, dtype=np.float64)
+    else:
+        fn = g.get("filename", "grid.unf2")
+        if not os.path.isabs(fn):
+            fn = os.path.join(base_dir, fn)
+        c.xv, c.yv = read_grid(fn, ni, nj, g.get("format", "grid.unf2"))
     return c
+
+
+def load_case(config_path: str) -> Case:
+    """Parse a stock reference `.inp` (TOML) + its grid, like Config / Mesh / BoundaryContainer do."""
+    with open(config_path, "r") as f:
+        text = f.read()
+    return case_from_toml(text, base_dir=os.path.dirname(os.path.abspath(config_path)))
 
 
 def write_case(case: Case, directory: str, name: str = "case") -> str:

@@ -1,0 +1,163 @@
+// Device-side physics of the residual path, written from the reference's formulas (cited per
+// function, paths relative to the reference tree).  Templated on the scalar type S so that the same
+// statements run on `double` (residual kernel) and on small forward-mode dual numbers (Jacobian kernel).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sg {
+
+constexpr double GAMMA = 1.4;                 // src/common.h:40
+constexpr double GM1 = GAMMA - 1.0;
+constexpr double OGM1 = 1.0/GM1;
+
+// Spalart-Allmaras constants (extension, DESIGN.md "SA extension")
+constexpr double SA_CB1 = 0.1355, SA_CB2 = 0.622, SA_SIGMA = 2.0/3.0, SA_KAPPA = 0.41;
+constexpr double SA_CW2 = 0.3, SA_CW3 = 2.0, SA_CV1 = 7.1, SA_PRT = 0.9;
+
+// ---- scalar helpers (double overloads; Dual overloads live in dual.cuh) ---------------------------
+__device__ __forceinline__ double s_rcp(double x) { return 1.0/x; }
+__device__ __forceinline__ double s_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double s_abs(double x) { return fabs(x); }
+__device__ __forceinline__ double s_val(double x) { return x; }
+// x^(2/3): FluidModel::get_laminar_viscosity uses pow(T/T_ref, 2.0/3.0) (src/model/fluid.cpp:38-40);
+// cbrt(x)^2 agrees with it to ~2 ulp, far inside the 1e-12 parity bar, at a fraction of pow's cost.
+__device__ __forceinline__ double s_pow23(double x) { double c = cbrt(x); return c*c; }
+// x^(1/6) for the SA f_w function
+__device__ __forceinline__ double s_pow16(double x) { return cbrt(sqrt(x)); }
+
+struct Gas {            // FluidModel, src/model/fluid.cpp:5-15
+    double R, cp, pr, mu_ref, T_ref;
+    double rho_inf, u_inf, v_inf, p_inf;
+    double cp_over_pr;
+};
+
+// FluidModel::primvars, src/model/fluid.cpp:50-67 (T = p/rho/R, :19-21)
+template <class S>
+__device__ __forceinline__ void cons_to_prim(const Gas& g, S q0, S q1, S q2, S q3, S& r, S& u, S& v, S& p, S& T) {
+    r = q0;
+    S ri = s_rcp(q0);
+    u = q1*ri; v = q2*ri;
+    p = (q3 - 0.5*r*(u*u + v*v))*GM1;
+    T = p*ri*(1.0/g.R);
+}
+__device__ __forceinline__ void prim_to_cons(double r, double u, double v, double p, double& q0, double& q1, double& q2, double& q3) {
+    q0 = r; q1 = r*u; q2 = r*v; q3 = p*OGM1 + 0.5*r*(u*u + v*v);
+}
+template <class S>
+__device__ __forceinline__ S laminar_viscosity(const Gas& g, S T) { return g.mu_ref*s_pow23(T*(1.0/g.T_ref)); }   // fluid.cpp:38-40
+
+// ---- reconstruction: ReconstructionSecondOrder, src/model/reconstruction.cpp:94-111,133-150 -------
+// For one interior cell with neighbours (qm, q0, qp) along a direction returns the value extrapolated to
+// its high face (becomes that face's LEFT state) and to its low face (that face's RIGHT state).
+template <class S>
+__device__ __forceinline__ void muscl_cell(S qm, S q0, S qp, double eps, S& to_high, S& to_low) {
+    const double thm = 2.0/3.0, thp = 4.0/3.0;          // reconstruction.h:55-56
+    S f2a = q0 - qm, f2b = qp - q0;
+    S a1 = 3.0*f2b*f2a;
+    S d = f2b - f2a;
+    S a2 = 2.0*d*d + a1;
+    S f3qt = 0.25*(a1 + eps)*s_rcp(a2 + eps);
+    to_high = q0 + f3qt*(thm*f2a + thp*f2b);
+    to_low = q0 - f3qt*(thp*f2a + thm*f2b);
+}
+
+// ---- ConvectiveFluxRoe::evaluate, src/model/flux.cpp:51-146 ------------------------------------------
+template <class S>
+__device__ __forceinline__ void roe_flux(double nx, double ny, S rlft, S ulft, S vlft, S plft,
+                                         S rrht, S urht, S vrht, S prht, S* f) {
+    S rlfti = s_rcp(rlft), rulft = rlft*ulft, rvlft = rlft*vlft;
+    S uvl = 0.5*(ulft*ulft + vlft*vlft), elft = plft*OGM1 + rlft*uvl, hlft = (elft + plft)*rlfti;
+    S rrhti = s_rcp(rrht), rurht = rrht*urht, rvrht = rrht*vrht;
+    S uvr = 0.5*(urht*urht + vrht*vrht), erht = prht*OGM1 + rrht*uvr, hrht = (erht + prht)*rrhti;
+    S rat = s_sqrt(rrht*rlfti), rati = s_rcp(rat + 1.0), rav = rat*rlft;
+    S uav = (rat*urht + ulft)*rati, vav = (rat*vrht + vlft)*rati, hav = (rat*hrht + hlft)*rati;
+    S uv = 0.5*(uav*uav + vav*vav), cav = s_sqrt(GM1*(hav - uv));
+    S aq1 = rrht - rlft, aq2 = urht - ulft, aq3 = vrht - vlft, aq4 = prht - plft;
+    const double dr = sqrt(nx*nx + ny*ny), dri = 1.0/dr, r1 = nx*dri, r2 = ny*dri;
+    S uu = r1*uav + r2*vav, c2 = cav*cav, c2i = s_rcp(c2);
+    S auu = s_abs(uu), aupc = s_abs(uu + cav), aumc = s_abs(uu - cav);
+    S uulft = r1*ulft + r2*vlft, uurht = r1*urht + r2*vrht, rcav = rav*cav, aquu = uurht - uulft;
+    S c2ih = 0.5*c2i, ruuav = auu*rav;
+    S b1 = auu*(aq1 - c2i*aq4), b2 = c2ih*aupc*(aq4 + rcav*aquu), b3 = c2ih*aumc*(aq4 - rcav*aquu);
+    S b4 = b1 + b2 + b3, b5 = cav*(b2 - b3), b6 = ruuav*(aq2 - r1*aquu), b7 = ruuav*(aq3 - r2*aquu);
+    aq1 = b4; aq2 = uav*b4 + r1*b5 + b6; aq3 = vav*b4 + r2*b5 + b7;
+    aq4 = hav*b4 + uu*b5 + uav*b6 + vav*b7 - c2*b1*OGM1;
+    const double aj = 0.5*dr;
+    S plar = plft + prht, eplft = elft + plft, eprht = erht + prht;
+    f[0] = aj*(rlft*uulft + rrht*uurht - aq1);
+    f[1] = aj*(rulft*uulft + rurht*uurht + r1*plar - aq2);
+    f[2] = aj*(rvlft*uulft + rvrht*uurht + r2*plar - aq3);
+    f[3] = aj*(eplft*uulft + eprht*uurht - aq4);
+}
+
+// ---- ConvectiveFluxAUSM, src/model/flux.cpp:150-224 --------------------------------------------------
+template <class S> __device__ __forceinline__ S mach_p(S M) { return s_val(s_abs(M)) <= 1.0 ? 0.25*(M + 1.0)*(M + 1.0) : 0.5*(M + s_abs(M)); }
+template <class S> __device__ __forceinline__ S mach_m(S M) { return s_val(s_abs(M)) <= 1.0 ? -0.25*(M - 1.0)*(M - 1.0) : 0.5*(M - s_abs(M)); }
+template <class S> __device__ __forceinline__ S pres_p(S M, S p) { return s_val(s_abs(M)) <= 1.0 ? 0.25*p*(M + 1.0)*(M + 1.0)*(2.0 - M) : 0.5*p*(M + s_abs(M))*s_rcp(M); }
+template <class S> __device__ __forceinline__ S pres_m(S M, S p) { return s_val(s_abs(M)) <= 1.0 ? 0.25*p*(M - 1.0)*(M - 1.0)*(2.0 + M) : 0.5*p*(M - s_abs(M))*s_rcp(M); }
+
+template <class S>
+__device__ __forceinline__ void ausm_flux(double nx, double ny, S rlft, S ulft, S vlft, S plft,
+                                          S rrht, S urht, S vrht, S prht, S* f) {
+    const double ds = sqrt(nx*nx + ny*ny), dsi = 1.0/ds;
+    S uln = (ulft*nx + vlft*ny)*dsi, urn = (urht*nx + vrht*ny)*dsi;
+    S rlfti = s_rcp(rlft), rrhti = s_rcp(rrht);
+    S alft = s_sqrt(GAMMA*plft*rlfti), arht = s_sqrt(GAMMA*prht*rrhti);
+    S machlft = uln*s_rcp(alft), machrht = urn*s_rcp(arht);
+    S uvl = 0.5*(ulft*ulft + vlft*vlft), elft = plft*OGM1 + rlft*uvl, hlft = (elft + plft)*rlfti;
+    S uvr = 0.5*(urht*urht + vrht*vrht), erht = prht*OGM1 + rrht*uvr, hrht = (erht + prht)*rrhti;
+    S mach_half = mach_p(machlft) + mach_m(machrht);
+    S p_half = pres_p(machlft, plft) + pres_m(machrht, prht);
+    if (s_val(mach_half) >= 0.0) {
+        S m = rlft*alft*mach_half*ds;
+        f[0] = m; f[1] = m*ulft + p_half*nx; f[2] = m*vlft + p_half*ny; f[3] = m*hlft;
+    } else {
+        S m = rrht*arht*mach_half*ds;
+        f[0] = m; f[1] = m*urht + p_half*nx; f[2] = m*vrht + p_half*ny; f[3] = m*hrht;
+    }
+}
+
+// ---- DiffusiveFluxGreenGauss::evaluate, src/model/flux.cpp:12-48 ----------------------------------------
+// components 1..3 (component 0 is the constant 0.0, :42)
+template <class S>
+__device__ __forceinline__ void viscous_flux(double nx, double ny, S dudx, S dudy, S dvdx, S dvdy, S dTdx, S dTdy,
+                                             S ubar, S vbar, S mu, S k, S* f) {
+    S div = dudx + dvdy;
+    S tau_xy = mu*(dudy + dvdx);
+    S tau_xx = mu*(2.0*dudx - (2.0/3.0)*div);
+    S tau_yy = mu*(2.0*dvdy - (2.0/3.0)*div);
+    S q_x = -(k*dTdx), q_y = -(k*dTdy);
+    f[1] = tau_xx*nx + tau_xy*ny;
+    f[2] = tau_xy*nx + tau_yy*ny;
+    f[3] = (ubar*tau_xx + vbar*tau_xy - q_x)*nx + (ubar*tau_xy + vbar*tau_yy - q_y)*ny;
+}
+
+// ---- SA per-cell closures (extension; normative CPU statement: oracle/port/structured_port.hpp) ------
+template <class S>
+__device__ __forceinline__ S sa_fv1(S chi) { S c3 = chi*chi*chi; return c3*s_rcp(c3 + SA_CV1*SA_CV1*SA_CV1); }
+
+template <class S>
+__device__ __forceinline__ S sa_source(S rho, S nut, S mul, S om, S dndx, S dndy, double d, double beta) {
+    const double k2 = SA_KAPPA*SA_KAPPA;
+    const double cw1 = SA_CB1/k2 + (1.0 + SA_CB2)/SA_SIGMA;
+    const double cw36 = 64.0;   // cw3^6
+    S chi = rho*nut*s_rcp(mul);
+    S fv1 = sa_fv1(chi);
+    S fv2 = 1.0 - chi*s_rcp(1.0 + chi*fv1);
+    const double k2d2 = k2*d*d;
+    S sbar = nut*fv2*(1.0/k2d2);
+    S st = om + sbar, st_min = 0.3*om;
+    if (s_val(st) < s_val(st_min)) st = st_min;
+    S den = st*k2d2;
+    if (s_val(den) < 1e-30) den = S(1e-30);
+    S r = nut*s_rcp(den);
+    if (s_val(r) > 10.0) r = S(10.0);
+    S r2 = r*r, r6 = r2*r2*r2;
+    S gg = r + SA_CW2*(r6 - r);
+    S g2 = gg*gg, g6 = g2*g2*g2;
+    S fw = gg*s_pow16((1.0 + cw36)*s_rcp(g6 + cw36));
+    S nd = nut*(1.0/d);
+    return rho*(beta*SA_CB1*st*nut - cw1*fw*nd*nd) + (SA_CB2/SA_SIGMA)*rho*(dndx*dndx + dndy*dndy);
+}
+
+} // namespace sg

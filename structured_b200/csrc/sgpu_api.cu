@@ -1,0 +1,513 @@
+// C ABI of the B200 residual + Jacobian path (include/structured_gpu.h).  Host-side glue only: every
+// compute entry point launches the CUDA kernels in this directory; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/structured_gpu.h"
+#include "common.cuh"
+#include "aux_kernels.cuh"
+#include "residual_kernel.cuh"
+#include "jacobian_kernel.cuh"
+
+using namespace sg;
+
+static thread_local std::string g_create_error;
+
+struct sgpu_ctx {
+    sgpu_desc d{};
+    std::vector<sgpu_bc> bcs;
+    View v{};
+    Gas g{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool viscous = false;
+    double eps_chi = 0, eps_eta = 0;
+    // device planes
+    double* q[2] = {nullptr, nullptr};
+    double* rhs = nullptr;
+    double* dt = nullptr;
+    double* xv = nullptr; double* yv = nullptr;
+    double* met = nullptr;                 // 5 planes: ncx ncy nex ney vol
+    double* wdist = nullptr; double* beta = nullptr;
+    double* partial = nullptr; size_t partial_cap = 0;
+    double* l2sq_dev = nullptr;
+    double* stage = nullptr; size_t stage_cap = 0;
+    double* halo_recv[2] = {nullptr, nullptr};
+    double* halo_peer[2] = {nullptr, nullptr};
+    JacStore jac{};
+    bool have_grid = false, have_dt = false;
+    std::string err;
+    long long launches = 0;
+    // kernel timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t ev_used = 0;
+};
+
+#define FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->err = _b; return (code); } while (0)
+#define CK(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
+    char _b[512]; snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    (ctx)->err = _b; return SGPU_ERR_CUDA; } } while (0)
+#define CKL(ctx) CK(ctx, cudaGetLastError())
+
+static Metrics metrics_of(const sgpu_ctx* c) {
+    Metrics m; const size_t pl = c->v.plane;
+    m.ncx = c->met; m.ncy = c->met + pl; m.nex = c->met + 2*pl; m.ney = c->met + 3*pl; m.vol = c->met + 4*pl;
+    return m;
+}
+
+static int ensure_stage(sgpu_ctx* c, size_t doubles) {
+    if (doubles <= c->stage_cap) return SGPU_OK;
+    if (c->stage) { CK(c, cudaFree(c->stage)); c->stage = nullptr; c->stage_cap = 0; }
+    CK(c, cudaMalloc(&c->stage, doubles*sizeof(double)));
+    c->stage_cap = doubles;
+    return SGPU_OK;
+}
+
+extern "C" {
+
+const char* sgpu_last_error(const sgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sgpu_create(const sgpu_desc* d, sgpu_ctx** out) {
+    if (!d || !out) { g_create_error = "null argument"; return SGPU_ERR_ARG; }
+    *out = nullptr;
+    auto fail = [&](const char* msg) { g_create_error = msg; return SGPU_ERR_ARG; };
+    if (d->ni < 3 || d->nj < 3) return fail("need at least 2x2 cells");
+    if (d->ntrans != 0 && d->ntrans != 1) return fail("ntrans must be 0 (laminar) or 1 (SA)");
+    if ((d->order != 1 && d->order != 2) || (d->lhs_order != 1 && d->lhs_order != 2)) return fail("Reconstruction not found.");   // eulerequation.cpp:108,119
+    if (d->flux != SGPU_FLUX_ROE && d->flux != SGPU_FLUX_AUSM) return fail("Flux not found.");                                      // eulerequation.cpp:128
+    if (d->ntrans == 1 && !(d->mu_inf > 1e-15)) return fail("the SA extension needs a viscous case (mu_inf > 0)");
+    const int nic = d->ni - 1, njc = d->nj - 1;
+    int j0 = d->j_begin, j1 = d->j_end;
+    if (j0 == 0 && j1 == 0) j1 = njc;
+    if (j0 < 0 || j1 > njc || j1 - j0 < 2) return fail("bad slab [j_begin, j_end): need at least 2 rows inside the grid");
+    const bool slabbed = (j0 != 0 || j1 != njc);
+    for (int n = 0; n < d->n_bc; n++) {
+        const sgpu_bc& b = d->bc[n];
+        const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
+        if (b.face < 0 || b.face > 3) return fail("boundary face must be bottom/right/top/left");
+        if (b.type < 0 || b.type > SGPU_BC_PERIODIC) return fail("Wrong type of BC.");                                             // bc.cpp:523
+        if (!horiz && (b.type == SGPU_BC_SLIPWALL || b.type == SGPU_BC_ISOTHERMALWALL || b.type == SGPU_BC_WAKE))
+            return fail("Boundary condition not implemented! (slipwall/isothermalwall/wake exist on bottom/top only, bc.cpp:116-126,251-261,415-425)");
+        if (b.type == SGPU_BC_OUTFLOW && b.face != SGPU_FACE_RIGHT)
+            return fail("Boundary not implemented! (outflow exists on the right face only, bc.cpp:286-309)");
+        if (slabbed && horiz && b.type == SGPU_BC_PERIODIC) return fail("periodic bottom/top is not supported on a j-slab partition");
+        if (slabbed && b.type == SGPU_BC_WAKE && b.face == SGPU_FACE_TOP) return fail("wake on the top face is not supported on a j-slab partition");
+    }
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e); return SGPU_ERR_CUDA; }
+
+    sgpu_ctx* c = new sgpu_ctx();
+    c->d = *d; c->bcs.assign(d->bc, d->bc + d->n_bc); c->d.bc = c->bcs.data();
+    c->device = d->device;
+    for (auto& b : c->bcs)                                         // BoundaryContainer::get_index, bc.cpp:436-457
+        if (b.end < 0) b.end = ((b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP) ? nic : njc) + 2 + b.end;
+    View& v = c->v;
+    v.nic = nic; v.njc = njc; v.ni = d->ni; v.nj = d->nj; v.j0 = j0; v.j1 = j1; v.njl = j1 - j0; v.nv = 4 + d->ntrans;
+    v.pitch = ((nic + 2*IOFF + 15)/16)*16; v.rows = v.njl + 2*JOFF; v.plane = (size_t)v.rows*v.pitch;
+    Gas& g = c->g;
+    g.R = d->p_inf/d->rho_inf/d->T_inf;                            // fluid.cpp:12
+    g.cp = GAMMA*g.R/(GAMMA - 1.0);                                // fluid.cpp:14
+    g.pr = d->pr_inf; g.mu_ref = d->mu_inf; g.T_ref = d->T_inf;
+    g.rho_inf = d->rho_inf; g.u_inf = d->u_inf; g.v_inf = d->v_inf; g.p_inf = d->p_inf;
+    g.cp_over_pr = g.cp/g.pr;
+    c->viscous = d->mu_inf > 1e-15;                                // config.cpp:41
+    c->eps_chi = std::pow(10.0/nic, 3); c->eps_eta = std::pow(10.0/njc, 3);   // reconstruction.cpp:62-63 (GLOBAL counts)
+
+    auto alloc = [&](double** p, size_t n) { return cudaMalloc(p, n*sizeof(double)); };
+    const size_t pl = v.plane, vpl = (size_t)(v.rows + 1)*v.pitch;
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = alloc(&c->q[0], pl*v.nv);
+    if (ce == cudaSuccess) ce = alloc(&c->q[1], pl*v.nv);
+    if (ce == cudaSuccess) ce = alloc(&c->rhs, pl*v.nv);
+    if (ce == cudaSuccess) ce = alloc(&c->dt, pl);
+    if (ce == cudaSuccess) ce = alloc(&c->xv, vpl);
+    if (ce == cudaSuccess) ce = alloc(&c->yv, vpl);
+    if (ce == cudaSuccess) ce = alloc(&c->met, pl*5);
+    if (ce == cudaSuccess) ce = alloc(&c->wdist, pl);
+    if (ce == cudaSuccess) ce = alloc(&c->beta, pl);
+    if (ce == cudaSuccess) ce = alloc(&c->l2sq_dev, 8);
+    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[0], (size_t)2*v.nv*nic);
+    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[1], (size_t)2*v.nv*nic);
+    if (ce != cudaSuccess) {
+        g_create_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(ce);
+        sgpu_destroy(c); return SGPU_ERR_CUDA;
+    }
+    // benign fill (freestream) so that never-written pad cells cannot produce NaNs that leak into sums
+    const double q0 = d->rho_inf, q1 = d->rho_inf*d->u_inf, q2 = d->rho_inf*d->v_inf;
+    const double q3 = d->p_inf/(GAMMA - 1.0) + 0.5*d->rho_inf*(d->u_inf*d->u_inf + d->v_inf*d->v_inf);
+    const double fillv[5] = {q0, q1, q2, q3, 3.0*d->mu_inf};
+    for (int s = 0; s < 2; s++) for (int k = 0; k < v.nv; k++) fill_kernel<<<296, 256>>>(c->q[s] + k*pl, pl, fillv[k]);
+    fill_kernel<<<296, 256>>>(c->rhs, pl*v.nv, 0.0);
+    fill_kernel<<<296, 256>>>(c->dt, pl, 0.0);
+    fill_kernel<<<296, 256>>>(c->wdist, pl, 1.0);
+    fill_kernel<<<296, 256>>>(c->beta, pl, 1.0);
+    fill_kernel<<<296, 256>>>(c->met, pl*5, 1.0);
+    fill_kernel<<<296, 256>>>(c->xv, vpl, 0.0);
+    fill_kernel<<<296, 256>>>(c->yv, vpl, 0.0);
+    c->launches += 2*v.nv + 7;
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { g_create_error = std::string("init kernels failed: ") + cudaGetErrorString(ce); sgpu_destroy(c); return SGPU_ERR_CUDA; }
+    *out = c;
+    return SGPU_OK;
+}
+
+int sgpu_destroy(sgpu_ctx* c) {
+    if (!c) return SGPU_OK;
+    cudaSetDevice(c->device);
+    for (double* p : {c->q[0], c->q[1], c->rhs, c->dt, c->xv, c->yv, c->met, c->wdist, c->beta, c->partial, c->l2sq_dev,
+                      c->stage, c->halo_recv[0], c->halo_recv[1]})
+        if (p) cudaFree(p);
+    jac_free(c->jac);
+    for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    delete c;
+    return SGPU_OK;
+}
+
+int sgpu_set_stream(sgpu_ctx* c, void* s) { if (!c) return SGPU_ERR_ARG; c->stream = (cudaStream_t)s; return SGPU_OK; }
+int sgpu_synchronize(sgpu_ctx* c) { if (!c) return SGPU_ERR_ARG; CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream)); return SGPU_OK; }
+int sgpu_dims(const sgpu_ctx* c, int* nic, int* njc, int* nv, int* j_begin, int* j_end) {
+    if (!c) return SGPU_ERR_ARG;
+    if (nic) *nic = c->v.nic; if (njc) *njc = c->v.njc; if (nv) *nv = c->v.nv; if (j_begin) *j_begin = c->v.j0; if (j_end) *j_end = c->v.j1;
+    return SGPU_OK;
+}
+long long sgpu_launch_count(const sgpu_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- grid
+int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
+    if (!c || !xv || !yv) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.nj - 1);       // vertex rows [ja, jb]
+    const int nrows = jb - ja + 1, r0 = ja - v.j0 + JOFF;
+    if (int rc = ensure_stage(c, (size_t)v.ni*nrows)) return rc;
+    const dim3 blk(32, 8), grd((nrows + 31)/32, (v.ni + 31)/32);
+    const double* src[2] = {xv, yv}; double* dst[2] = {c->xv, c->yv};
+    for (int n = 0; n < 2; n++) {
+        CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*nrows, src[n] + ja, sizeof(double)*v.nj, sizeof(double)*nrows, v.ni,
+                                cudaMemcpyHostToDevice, c->stream));
+        vertex_to_plane_kernel<<<grd, blk, 0, c->stream>>>(v, c->stage, dst[n], r0, nrows);
+        CKL(c); c->launches++;
+    }
+    Metrics m = metrics_of(c);
+    metrics_kernel<<<dim3((v.pitch + 127)/128, v.rows), 128, 0, c->stream>>>(v, c->xv, c->yv, (double*)m.ncx, (double*)m.ncy,
+                                                                            (double*)m.nex, (double*)m.ney, (double*)m.vol);
+    CKL(c); c->launches++;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->have_grid = true;
+    return SGPU_OK;
+}
+
+int sgpu_set_field(sgpu_ctx* c, const char* name, const double* f) {
+    if (!c || !name || !f) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    double* dst = !strcmp(name, "wall_distance") ? c->wdist : (!strcmp(name, "beta") ? c->beta : nullptr);
+    if (!dst) FAIL(c, SGPU_ERR_ARG, "unknown field '%s' (wall_distance | beta)", name);
+    const View& v = c->v;
+    if (int rc = ensure_stage(c, (size_t)v.nic*v.njl)) return rc;
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*v.njl, f + v.j0, sizeof(double)*v.njc, sizeof(double)*v.njl, v.nic,
+                            cudaMemcpyHostToDevice, c->stream));
+    field_to_plane_kernel<<<dim3((v.njl + 31)/32, (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, dst, JOFF, v.njl);
+    CKL(c); c->launches++;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+
+// download a cell plane group to a GLOBAL host AoS array (owned rows only)
+static int download_planes(sgpu_ctx* c, const double* planes, int nvp, double* host) {
+    const View& v = c->v;
+    const size_t M = (size_t)v.njl*v.nv;
+    if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
+    planes_to_aos_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, planes, JOFF, v.njl, nvp);
+    CKL(c); c->launches++;
+    CK(c, cudaMemcpy2DAsync(host + (size_t)v.j0*v.nv, sizeof(double)*v.njc*v.nv, c->stage, sizeof(double)*M, sizeof(double)*M, v.nic,
+                            cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+
+int sgpu_get_metrics(sgpu_ctx* c, double* normal_chi, double* normal_eta, double* volume) {
+    if (!c) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    // small, cold path: copy the planes to the host and scatter
+    const View& v = c->v;
+    std::vector<double> h(v.plane*5);
+    CK(c, cudaMemcpy(h.data(), c->met, sizeof(double)*v.plane*5, cudaMemcpyDeviceToHost));
+    const size_t pl = v.plane;
+    for (int j = v.j0; j <= v.j1; j++) {
+        const int r = j - v.j0 + JOFF;
+        for (int i = 0; i < v.ni; i++) {
+            const size_t o = v.at(r, i + IOFF);
+            if (normal_chi && j < v.j1) { normal_chi[((size_t)i*v.njc + j)*2] = h[o]; normal_chi[((size_t)i*v.njc + j)*2 + 1] = h[pl + o]; }
+            if (normal_eta && i < v.nic) { normal_eta[((size_t)i*v.nj + j)*2] = h[2*pl + o]; normal_eta[((size_t)i*v.nj + j)*2 + 1] = h[3*pl + o]; }
+            if (volume && i < v.nic && j < v.j1) volume[(size_t)i*v.njc + j] = h[4*pl + o];
+        }
+    }
+    return SGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- state
+int sgpu_set_state(sgpu_ctx* c, int which, const double* q) {
+    if (!c || !q || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.njc);        // cell rows [ja, jb)
+    const int nrows = jb - ja, r0 = ja - v.j0 + JOFF;
+    const size_t M = (size_t)nrows*v.nv;
+    if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, q + (size_t)ja*v.nv, sizeof(double)*v.njc*v.nv, sizeof(double)*M, v.nic,
+                            cudaMemcpyHostToDevice, c->stream));
+    aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, c->q[which], r0, nrows);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_get_state(sgpu_ctx* c, int which, double* q) {
+    if (!c || !q || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    return download_planes(c, c->q[which], c->v.nv, q);
+}
+int sgpu_get_rhs(sgpu_ctx* c, double* rhs) {
+    if (!c || !rhs) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    return download_planes(c, c->rhs, c->v.nv, rhs);
+}
+int sgpu_get_dt(sgpu_ctx* c, double* dt) {
+    if (!c || !dt) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    return download_planes(c, c->dt, 1, dt);
+}
+int sgpu_copy_state(sgpu_ctx* c, int dst, int src) {
+    if (!c || dst < 0 || dst > 1 || src < 0 || src > 1) return SGPU_ERR_ARG;
+    if (dst == src) return SGPU_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(c->q[dst], c->q[src], sizeof(double)*c->v.plane*c->v.nv, cudaMemcpyDeviceToDevice, c->stream));
+    return SGPU_OK;
+}
+
+} // extern "C"
+// ---------------------------------------------------------------------------------------------- hot path
+static int apply_bcs(sgpu_ctx* c, int which) {
+    const View& v = c->v;
+    Metrics m = metrics_of(c);
+    for (const sgpu_bc& b : c->bcs) {
+        BcArgs a; a.type = b.type; a.face = b.face; a.u = b.u; a.v = b.v; a.T = b.T;
+        const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
+        if (horiz) {
+            if (b.face == SGPU_FACE_BOTTOM && v.j0 != 0) continue;
+            if (b.face == SGPU_FACE_TOP && v.j1 != v.njc) continue;
+            a.lo = b.start; a.hi = b.end;
+        } else {                                                   // rows this slab holds: padded j in [j0, j1+1]
+            a.lo = std::max(b.start, v.j0); a.hi = std::min(b.end, v.j1 + 1);
+        }
+        if (a.hi < a.lo) continue;
+        const int n = a.hi - a.lo + 1;
+        bc_kernel<<<(n + 127)/128, 128, 0, c->stream>>>(v, c->g, m, c->q[which], a);
+        CKL(c); c->launches++;
+    }
+    return SGPU_OK;
+}
+
+template <int NV, int ORDER, int FLUX, bool VISC>
+static int launch_residual_t(sgpu_ctx* c, const ResParams& p, int grid) {
+    using Cfg = ResCfg<NV, VISC>;
+    static bool attr_set = false;
+    auto kern = residual_kernel<NV, ORDER, FLUX, VISC>;
+    if (!attr_set) { CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes)); attr_set = true; }
+    kern<<<grid, RW, Cfg::smem_bytes, c->stream>>>(p);
+    CKL(c);
+    return SGPU_OK;
+}
+
+static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms) {
+    const View& v = c->v;
+    ResParams p;
+    p.v = v; p.g = c->g; p.m = metrics_of(c);
+    p.q = c->q[which]; p.rhs = c->rhs; p.wdist = c->wdist; p.beta = c->beta;
+    p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.dpdx = c->d.dpdx; p.dpdy = c->d.dpdy;
+    p.nstrips = (v.nic + RW - 2)/(RW - 1);
+    // chunk rows so that the grid is a few waves of (148 SMs x resident CTAs), but chunks stay tall enough to
+    // amortise the 4-row prologue
+    const int target_items = 148*4*3;
+    int nchunks = std::max(1, std::min((target_items + p.nstrips - 1)/p.nstrips, (v.njl + 15)/16));
+    p.rpc = (v.njl + nchunks - 1)/nchunks;
+    p.nchunks = (v.njl + p.rpc - 1)/p.rpc;
+    const int grid = p.nstrips*p.nchunks;
+    if (want_norms) {
+        const size_t need = (size_t)grid*v.nv;
+        if (need > c->partial_cap) {
+            if (c->partial) CK(c, cudaFree(c->partial));
+            CK(c, cudaMalloc(&c->partial, need*sizeof(double))); c->partial_cap = need;
+        }
+        p.partial = c->partial;
+    } else p.partial = nullptr;
+    const int order = lhs ? c->d.lhs_order : c->d.order;           // eulerequation.cpp:203-208
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        if (c->ev_used == c->ev.size()) {
+            cudaEvent_t a, b; CK(c, cudaEventCreate(&a)); CK(c, cudaEventCreate(&b)); c->ev.emplace_back(a, b);
+        }
+        e0 = c->ev[c->ev_used].first; e1 = c->ev[c->ev_used].second; c->ev_used++;
+        CK(c, cudaEventRecord(e0, c->stream));
+    }
+    int rc = SGPU_ERR_ARG;
+    const bool roe = c->d.flux == SGPU_FLUX_ROE;
+#define RES_CASE(NV_, ORD_, FL_, VI_) rc = launch_residual_t<NV_, ORD_, FL_, VI_>(c, p, grid)
+    if (v.nv == 5) {
+        if (order == 2) { if (roe) RES_CASE(5, 2, SGPU_FLUX_ROE, true); else RES_CASE(5, 2, SGPU_FLUX_AUSM, true); }
+        else            { if (roe) RES_CASE(5, 1, SGPU_FLUX_ROE, true); else RES_CASE(5, 1, SGPU_FLUX_AUSM, true); }
+    } else if (c->viscous) {
+        if (order == 2) { if (roe) RES_CASE(4, 2, SGPU_FLUX_ROE, true); else RES_CASE(4, 2, SGPU_FLUX_AUSM, true); }
+        else            { if (roe) RES_CASE(4, 1, SGPU_FLUX_ROE, true); else RES_CASE(4, 1, SGPU_FLUX_AUSM, true); }
+    } else {
+        if (order == 2) { if (roe) RES_CASE(4, 2, SGPU_FLUX_ROE, false); else RES_CASE(4, 2, SGPU_FLUX_AUSM, false); }
+        else            { if (roe) RES_CASE(4, 1, SGPU_FLUX_ROE, false); else RES_CASE(4, 1, SGPU_FLUX_AUSM, false); }
+    }
+#undef RES_CASE
+    if (rc) return rc;
+    c->launches++;
+    if (c->timing) CK(c, cudaEventRecord(e1, c->stream));
+    if (want_norms) {
+        reduce_partials_kernel<<<v.nv, 256, 0, c->stream>>>(c->partial, grid, v.nv, c->l2sq_dev);
+        CKL(c); c->launches++;
+    }
+    return SGPU_OK;
+}
+
+extern "C" {
+int sgpu_residual(sgpu_ctx* c, int which, int lhs, double* l2sq) {
+    if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = apply_bcs(c, which)) return rc;
+    if (int rc = launch_residual(c, which, lhs, l2sq != nullptr)) return rc;
+    if (l2sq) {
+        CK(c, cudaMemcpyAsync(l2sq, c->l2sq_dev, sizeof(double)*c->v.nv, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    return SGPU_OK;
+}
+
+int sgpu_residual_host(sgpu_ctx* c, const double* q, double* rhs, int lhs) {
+    if (!c || !q || !rhs) return SGPU_ERR_ARG;
+    if (int rc = sgpu_set_state(c, SGPU_STATE_Q, q)) return rc;
+    if (int rc = sgpu_residual(c, SGPU_STATE_Q, lhs, nullptr)) return rc;
+    return sgpu_get_rhs(c, rhs);
+}
+
+int sgpu_calc_dt(sgpu_ctx* c, double cfl) {
+    if (!c) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    dt_kernel<<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, metrics_of(c), c->q[0], c->dt, cfl, c->d.mu_inf);
+    CKL(c); c->launches++;
+    c->have_dt = true;
+    return SGPU_OK;
+}
+
+int sgpu_rk_stage(sgpu_ctx* c, int order) {
+    if (!c || order < 0 || order > 3) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    axpy_dt_div_kernel<<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->q[1], c->q[0], c->rhs, c->dt, 4.0 - order);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_forward_euler(sgpu_ctx* c) {
+    if (!c) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    axpy_dt_div_kernel<<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->q[0], c->q[0], c->rhs, c->dt, 1.0);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+
+int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
+    if (!c || (scheme != 0 && scheme != 1)) { if (c) c->err = "scheme not defined."; return SGPU_ERR_ARG; }   // solver.cpp:119
+    if (c->v.j0 != 0 || c->v.j1 != c->v.njc) FAIL(c, SGPU_ERR_STATE, "sgpu_explicit_step drives a whole grid; on a slab partition the caller interleaves halo exchanges");
+    if (int rc = sgpu_calc_dt(c, cfl)) return rc;                  // solver.cpp:66
+    if (scheme == 0) {                                             // solver.cpp:103-106
+        if (int rc = sgpu_residual(c, SGPU_STATE_Q, 0, l2sq)) return rc;
+        return sgpu_forward_euler(c);
+    }
+    for (int order = 0; order < 4; order++) {                      // solver.cpp:109-112
+        if (int rc = sgpu_residual(c, SGPU_STATE_Q_TMP, 0, order == 3 ? l2sq : nullptr)) return rc;
+        if (int rc = sgpu_rk_stage(c, order)) return rc;
+    }
+    return sgpu_copy_state(c, SGPU_STATE_Q, SGPU_STATE_Q_TMP);     // solver.cpp:114
+}
+
+// ---------------------------------------------------------------------------------------------- halos
+int sgpu_halo_count(const sgpu_ctx* c) { return c ? 2*c->v.nv*c->v.nic : 0; }
+static int halo_rows(const sgpu_ctx* c, int side, bool ghost) {
+    // first of the two rows: own boundary rows (pack) or ghost rows (unpack)
+    if (side == 0) return ghost ? 0 : JOFF;
+    return ghost ? c->v.njl + JOFF : c->v.njl + JOFF - 2;
+}
+int sgpu_halo_pack(sgpu_ctx* c, int which, int side, double* buf) {
+    if (!c || !buf || side < 0 || side > 1 || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_pack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], buf, halo_rows(c, side, false));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_halo_unpack(sgpu_ctx* c, int which, int side, const double* buf) {
+    if (!c || !buf || side < 0 || side > 1 || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_unpack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], buf, halo_rows(c, side, true));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_halo_recv_buffer(sgpu_ctx* c, int side, double** p) {
+    if (!c || !p || side < 0 || side > 1) return SGPU_ERR_ARG;
+    *p = c->halo_recv[side];
+    return SGPU_OK;
+}
+int sgpu_halo_set_peer(sgpu_ctx* c, int side, double* peer) {
+    if (!c || side < 0 || side > 1) return SGPU_ERR_ARG;
+    c->halo_peer[side] = peer;
+    return SGPU_OK;
+}
+int sgpu_halo_push(sgpu_ctx* c, int which) {
+    if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
+    for (int side = 0; side < 2; side++)
+        if (c->halo_peer[side]) if (int rc = sgpu_halo_pack(c, which, side, c->halo_peer[side])) return rc;   // stores go over NVLink
+    return SGPU_OK;
+}
+int sgpu_halo_pull(sgpu_ctx* c, int which) {
+    if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
+    for (int side = 0; side < 2; side++) {
+        const bool has_nb = side == 0 ? c->v.j0 > 0 : c->v.j1 < c->v.njc;
+        if (has_nb) if (int rc = sgpu_halo_unpack(c, which, side, c->halo_recv[side])) return rc;
+    }
+    return SGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- timing
+int sgpu_enable_kernel_timing(sgpu_ctx* c, int on) { if (!c) return SGPU_ERR_ARG; c->timing = on != 0; c->ev_used = 0; return SGPU_OK; }
+int sgpu_kernel_times(sgpu_ctx* c, float* ms, int n) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    int cnt = 0;
+    for (size_t k = 0; k < c->ev_used && cnt < n; k++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->ev[k].first, c->ev[k].second) == cudaSuccess) ms[cnt++] = t;
+    }
+    c->ev_used = 0;
+    return cnt;
+}
+
+// ---------------------------------------------------------------------------------------------- Jacobian
+#include "jacobian_api.inl"
+
+} // extern "C"
