@@ -190,8 +190,10 @@ def run_ours(args):
     j0, j1 = rank * njc_per, (rank + 1) * njc_per
     eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0)
     # synthetic state, generated per rank for its rows only would need the global index: build rows lazily
-    q = case.perturbed_q()
-    eq.set_state(q, 0)
+    # each rank generates only its own rows (+2 ghost rows each side) of the synthetic state
+    jw0, jw1 = (max(j0 - 2, 0), min(j1 + 2, njc_total)) if world > 1 else (0, njc_total)
+    q = case.perturbed_q(j_first=jw0, j_count=jw1 - jw0)
+    eq.set_state_window(q, jw0, 0)
     eq.synchronize()
     cells_local = nic * njc_per
     cells_total = nic * njc_total
@@ -266,17 +268,25 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         qh = torch.from_numpy(q).pin_memory()
-        rh = torch.empty_like(qh).pin_memory()
-        qn, rn = qh.numpy(), rh.numpy()
+        qn = qh.numpy()
+        rh = torch.empty((nic, njc_per, nv), dtype=torch.float64).pin_memory()
+        rn = rh.numpy()
         k_e2e = max(2, min(args.steps, 5))
-        eq.calc_residual(qn, out=rn)
+
+        def e2e_step():
+            # host q window -> device, residual, owned rhs rows -> host (what sgpu_residual_host does on a whole grid)
+            eq.set_state_window(qn, jw0, 0)
+            eq.residual_device(0)
+            if world > 1:
+                eq.get_rhs_window(rn)
+            else:
+                eq.get_rhs(out=rn)
+
+        e2e_step()
         barrier()
-        t0 = time.perf_counter()
         e0.record()
         for _ in range(k_e2e):
-            if world > 1:
-                pass                                    # set_state reads the neighbour rows from the host array itself
-            eq.calc_residual(qn, out=rn)
+            e2e_step()
         e1.record()
         barrier()
         ms_e = e0.elapsed_time(e1)

@@ -100,8 +100,13 @@ int sgpu_get_metrics(sgpu_ctx* ctx, double* normal_chi, double* normal_eta, doub
  * set: owned rows plus the slab's ghost rows are read.  get: only owned rows are written. */
 int sgpu_set_state(sgpu_ctx* ctx, int which, const double* q);
 int sgpu_get_state(sgpu_ctx* ctx, int which, double* q);
+/* Same for a host array that only holds a WINDOW of rows: q is [nic][j_count][nv] = global rows
+ * [j_first, j_first + j_count), which must cover the owned rows (ghost rows outside the window are left
+ * to the halo exchange).  Lets each rank of a slab run keep only its own rows on the host. */
+int sgpu_set_state_window(sgpu_ctx* ctx, int which, const double* q, int j_first, int j_count);
 int sgpu_copy_state(sgpu_ctx* ctx, int dst, int src);   /* set_rarray, src/solver/solver.cpp:4-10,114 */
 int sgpu_get_rhs(sgpu_ctx* ctx, double* rhs);            /* Solution::rhs */
+int sgpu_get_rhs_window(sgpu_ctx* ctx, double* rhs);     /* rhs is [nic][j_end - j_begin][nv]: the owned rows only */
 int sgpu_get_dt(sgpu_ctx* ctx, double* dt);              /* Solution::dt (all nv entries of a cell equal) */
 
 /* ---- the hot path -------------------------------------------------------------------------- */

@@ -21,8 +21,8 @@ _U = ctypes.POINTER(ctypes.c_uint)
 
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
-    "sgpu_set_grid", "sgpu_set_field", "sgpu_get_metrics", "sgpu_set_state", "sgpu_get_state", "sgpu_copy_state",
-    "sgpu_get_rhs", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_rk_stage",
+    "sgpu_set_grid", "sgpu_set_field", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
+    "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_set_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
@@ -159,6 +159,13 @@ class GpuEulerEquation:
         self._ck(self.L.sgpu_set_state(self.h, which, _dp(q)))
         self.synchronize()
 
+    def set_state_window(self, q: np.ndarray, j_first: int, which: int = 0):
+        """q holds only global rows [j_first, j_first + q.shape[1]) (must cover the owned rows)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape[0] == self.nic and q.shape[2] == self.nv
+        self._ck(self.L.sgpu_set_state_window(self.h, which, _dp(q), j_first, q.shape[1]))
+        self.synchronize()
+
     def get_state(self, which: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         out = self._state_array() if out is None else out
         self._ck(self.L.sgpu_get_state(self.h, which, _dp(out)))
@@ -167,6 +174,12 @@ class GpuEulerEquation:
     def get_rhs(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         out = self._state_array() if out is None else out
         self._ck(self.L.sgpu_get_rhs(self.h, _dp(out)))
+        return out
+
+    def get_rhs_window(self, out: np.ndarray) -> np.ndarray:
+        """owned rows only: out is [nic][j_end - j_begin][nv]"""
+        assert out.shape == (self.nic, self.j_end - self.j_begin, self.nv) and out.flags.c_contiguous
+        self._ck(self.L.sgpu_get_rhs_window(self.h, _dp(out)))
         return out
 
     def get_dt(self) -> np.ndarray:

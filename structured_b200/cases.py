@@ -87,7 +87,9 @@ class Case:
 
     def freestream_q(self) -> np.ndarray:
         """EulerEquation::initialize (src/model/eulerequation.cpp:262-276); SA slot = 3 nu_inf * rho."""
-        q = np.empty((self.nic, self.njc, self.nv))
+        q = np.empty((self.nic, self.njc, self.nv)) if self.nic * self.njc < (1 << 26) else None
+        if q is None:  # huge grids: callers only need the (uniform) cell value, see perturbed_q
+            q = np.empty((1, 1, self.nv))
         q[..., 0] = self.rho_inf
         q[..., 1] = self.rho_inf * self.u_inf
         q[..., 2] = self.rho_inf * self.v_inf
@@ -96,17 +98,20 @@ class Case:
             q[..., 4] = 3.0 * self.mu_inf
         return q
 
-    def perturbed_q(self, amp: float = 0.01) -> np.ndarray:
-        """freestream x (1 + amp sin(1 + 0.7 i + 0.3 j + k)): SURVEY.md section 8(d) synthetic state."""
-        q = self.freestream_q()
-        i, j, k = np.meshgrid(np.arange(self.nic), np.arange(self.njc), np.arange(self.nv), indexing="ij")
-        pert = 1.0 + amp * np.sin(1.0 + 0.7 * i + 0.3 * j + k)
+    def perturbed_q(self, amp: float = 0.01, j_first: int = 0, j_count: Optional[int] = None) -> np.ndarray:
+        """freestream x (1 + amp sin(1 + 0.7 i + 0.3 j + k)): SURVEY.md section 8(d) synthetic state.
+        With j_first/j_count only the window of global rows [j_first, j_first + j_count) is generated."""
+        j_count = self.njc - j_first if j_count is None else j_count
+        fs = self.freestream_q()[0, 0]
+        i = np.arange(self.nic, dtype=np.float64)[:, None, None]
+        j = (j_first + np.arange(j_count, dtype=np.float64))[None, :, None]
+        k = np.arange(self.nv, dtype=np.float64)[None, None, :]
+        q = fs[None, None, :] * (1.0 + amp * np.sin(1.0 + 0.7 * i + 0.3 * j + k))
         # momentum components that are exactly zero at freestream get an additive perturbation so that
         # every Jacobian column is exercised
-        q = q * pert
         for kk in (1, 2):
-            if np.all(q[..., kk] == 0.0):
-                q[..., kk] = amp * self.rho_inf * 0.1 * np.sin(2.0 + 0.5 * i[..., kk] + 0.9 * j[..., kk])
+            if fs[kk] == 0.0:
+                q[..., kk] = amp * self.rho_inf * 0.1 * np.sin(2.0 + 0.5 * i[..., 0] + 0.9 * j[..., 0])
         return np.ascontiguousarray(q)
 
 

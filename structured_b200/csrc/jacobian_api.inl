@@ -1,15 +1,198 @@
-int sgpu_jacobian_coo(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int** cind, double** values, int apply_lhs_transform) {
-    (void)nnz; (void)rind; (void)cind; (void)values; (void)apply_lhs_transform;
-    if (!c) return SGPU_ERR_ARG;
-    FAIL(c, SGPU_ERR_STATE, "Jacobian kernels not built yet");
+// Host side of the Jacobian entry points (included inside extern "C" of sgpu_api.cu).
+
+} // extern "C"
+#include <cub/device/device_scan.cuh>
+
+// Replay the [[boundary]] tables in file order and record, for every ghost cell, the LAST condition that
+// writes it together with its source cells (BoundaryContainer::apply, src/model/bc.cpp:430-433).
+static int build_ghost_table(sgpu_ctx* c) {
+    const int nic = c->v.nic, njc = c->v.njc;
+    const size_t n = (size_t)2*(nic + 2) + 2*(njc + 2);
+    std::vector<GhostDesc> tab(n);
+    for (auto& g : tab) { g.type = -1; g.a_ip = g.a_jp = g.b_ip = g.b_jp = 0; g.face = 0; g.u = g.v = g.T = 0; }
+    auto id = [&](int ip, int jp) -> size_t {
+        if (jp <= 0) return ip; if (jp >= njc + 1) return (size_t)(nic + 2) + ip;
+        if (ip <= 0) return (size_t)2*(nic + 2) + jp; return (size_t)2*(nic + 2) + (njc + 2) + jp;
+    };
+    auto set = [&](int ip, int jp, const sgpu_bc& b, int aip, int ajp, int bip, int bjp) {
+        if (ip < 0 || ip > nic + 1 || jp < 0 || jp > njc + 1) return;
+        GhostDesc& g = tab[id(ip, jp)];
+        g.type = b.type; g.face = b.face; g.u = b.u; g.v = b.v; g.T = b.T;
+        g.a_ip = aip; g.a_jp = ajp; g.b_ip = bip; g.b_jp = bjp;
+    };
+    for (const sgpu_bc& b : c->bcs) {
+        const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
+        const bool bot = b.face == SGPU_FACE_BOTTOM, left = b.face == SGPU_FACE_LEFT;
+        for (int s = b.start; s <= b.end; s++) {
+            if (horiz) {
+                const int jg = bot ? 0 : njc + 1, j1 = bot ? 1 : njc, j2 = bot ? 2 : njc - 1;
+                switch (b.type) {
+                case SGPU_BC_WAKE: set(s, jg, b, nic + 1 - s, 1, 0, 0); set(nic + 1 - s, jg, b, s, 1, 0, 0); break;
+                case SGPU_BC_PERIODIC: set(s, 0, b, s, njc, 0, 0); set(s, njc + 1, b, s, 1, 0, 0); break;
+                default: set(s, jg, b, s, j1, s, j2); break;
+                }
+            } else {
+                const int ig = left ? 0 : nic + 1, i1 = left ? 1 : nic, i2 = left ? 2 : nic - 1;
+                switch (b.type) {
+                case SGPU_BC_PERIODIC: set(0, s, b, nic, s, 0, 0); set(nic + 1, s, b, 1, s, 0, 0); break;
+                case SGPU_BC_OUTFLOW: set(ig, s, b, ig - 1, s, 0, 0); break;
+                default: set(ig, s, b, i1, s, i2, s); break;
+                }
+            }
+        }
+    }
+    if (!c->ghost_tab) CK(c, cudaMalloc(&c->ghost_tab, n*sizeof(GhostDesc)));
+    CK(c, cudaMemcpy(c->ghost_tab, tab.data(), n*sizeof(GhostDesc), cudaMemcpyHostToDevice));
+    if (!c->jac_err) CK(c, cudaMalloc(&c->jac_err, sizeof(int)));
+    return SGPU_OK;
 }
+
+static GhostTable ghost_table_of(const sgpu_ctx* c) {
+    GhostTable gt; gt.d = (const GhostDesc*)c->ghost_tab; gt.nic = c->v.nic; gt.njc = c->v.njc; return gt;
+}
+
+template <int NV, int ORDER, int FLUX, bool VISC>
+static int launch_jacobian_t(sgpu_ctx* c, const JacParams& p) {
+    const View& v = c->v;
+    jacobian_kernel<NV, ORDER, FLUX, VISC><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(p);
+    CKL(c);
+    return SGPU_OK;
+}
+
+static int jacobian_build(sgpu_ctx* c, float* build_ms) {
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    if (!c->ghost_tab) if (int rc = build_ghost_table(c)) return rc;
+    const int nslots = c->d.lhs_order == 2 ? 13 : 9;
+    const size_t need = (size_t)nslots*v.nv*v.nv*v.plane;
+    if (need > c->jac.cap) {
+        if (c->jac.blocks) CK(c, cudaFree(c->jac.blocks));
+        c->jac.blocks = nullptr; c->jac.cap = 0;
+        CK(c, cudaMalloc(&c->jac.blocks, need*sizeof(double)));
+        c->jac.cap = need;
+    }
+    c->jac.slots = nslots; c->jac.valid = false;
+    if (int rc = apply_bcs(c, SGPU_STATE_Q)) return rc;          // ghost values of the state the tape would have seen
+    CK(c, cudaMemsetAsync(c->jac_err, 0, sizeof(int), c->stream));
+    JacParams p;
+    p.v = v; p.g = c->g; p.m = metrics_of(c); p.gt = ghost_table_of(c);
+    p.q = c->q[0]; p.J = c->jac.blocks; p.wdist = c->wdist; p.beta = c->beta;
+    p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.nslots = nslots; p.err = c->jac_err;
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    CK(c, cudaEventRecord(e0, c->stream));
+    int rc = SGPU_ERR_ARG;
+    const bool roe = c->d.flux == SGPU_FLUX_ROE;
+    const int order = c->d.lhs_order;                              // calc_residual(..., lhs = true), src/solver/solver.cpp:80
+#define JAC_CASE(NV_, ORD_, FL_, VI_) rc = launch_jacobian_t<NV_, ORD_, FL_, VI_>(c, p)
+    if (v.nv == 5) {
+        if (order == 2) { if (roe) JAC_CASE(5, 2, SGPU_FLUX_ROE, true); else JAC_CASE(5, 2, SGPU_FLUX_AUSM, true); }
+        else            { if (roe) JAC_CASE(5, 1, SGPU_FLUX_ROE, true); else JAC_CASE(5, 1, SGPU_FLUX_AUSM, true); }
+    } else if (c->viscous) {
+        if (order == 2) { if (roe) JAC_CASE(4, 2, SGPU_FLUX_ROE, true); else JAC_CASE(4, 2, SGPU_FLUX_AUSM, true); }
+        else            { if (roe) JAC_CASE(4, 1, SGPU_FLUX_ROE, true); else JAC_CASE(4, 1, SGPU_FLUX_AUSM, true); }
+    } else {
+        if (order == 2) { if (roe) JAC_CASE(4, 2, SGPU_FLUX_ROE, false); else JAC_CASE(4, 2, SGPU_FLUX_AUSM, false); }
+        else            { if (roe) JAC_CASE(4, 1, SGPU_FLUX_ROE, false); else JAC_CASE(4, 1, SGPU_FLUX_AUSM, false); }
+    }
+#undef JAC_CASE
+    if (rc) return rc;
+    c->launches++;
+    CK(c, cudaEventRecord(e1, c->stream));
+    int herr = 0;
+    CK(c, cudaMemcpyAsync(&herr, c->jac_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f; CK(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (build_ms) *build_ms = ms;
+    if (herr) FAIL(c, SGPU_ERR_ARG, "%d boundary couplings could not be represented in the block-stencil Jacobian", herr);
+    c->jac.valid = true;
+    return SGPU_OK;
+}
+
+template <int NV>
+static int jacobian_export_t(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int** cind, double** values, int lhs_transform) {
+    const View& v = c->v;
+    const size_t nrows = (size_t)v.nic*v.njl*NV;
+    const GhostTable gt = ghost_table_of(c);
+    const bool order2 = c->d.lhs_order == 2;
+    int* counts = nullptr; long long* offs = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+    CK(c, cudaMalloc(&counts, (nrows + 1)*sizeof(int)));
+    CK(c, cudaMalloc(&offs, (nrows + 1)*sizeof(long long)));
+    CK(c, cudaMemsetAsync(counts, 0, (nrows + 1)*sizeof(int), c->stream));
+    const dim3 grd((v.nic + 127)/128, v.njl);
+    jac_count_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, counts);
+    CKL(c); c->launches++;
+    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offs, (int)(nrows + 1), c->stream));
+    CK(c, cudaMalloc(&tmp, tmp_bytes));
+    CK(c, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offs, (int)(nrows + 1), c->stream));
+    c->launches++;
+    long long total = 0;
+    CK(c, cudaMemcpyAsync(&total, offs + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+    if (total > 2147483647LL) { cudaFree(counts); cudaFree(offs); FAIL(c, SGPU_ERR_OVERFLOW, "nnz = %lld does not fit the reference's `int nnz` (src/solver/solution.h:16); use sgpu_jacobian_device", total); }
+    unsigned int *dr = nullptr, *dc = nullptr; double* dv = nullptr;
+    const size_t n = (size_t)std::max<long long>(total, 1);
+    CK(c, cudaMalloc(&dr, n*sizeof(unsigned int))); CK(c, cudaMalloc(&dc, n*sizeof(unsigned int))); CK(c, cudaMalloc(&dv, n*sizeof(double)));
+    jac_fill_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, offs, c->dt, lhs_transform, dr, dc, dv);
+    CKL(c); c->launches++;
+    // malloc: ownership passes to the caller, who free()s the three arrays as after sparse_jac (src/solver/solver.cpp:181-183)
+    *rind = (unsigned int*)malloc(n*sizeof(unsigned int)); *cind = (unsigned int*)malloc(n*sizeof(unsigned int)); *values = (double*)malloc(n*sizeof(double));
+    if (!*rind || !*cind || !*values) { cudaFree(counts); cudaFree(offs); cudaFree(dr); cudaFree(dc); cudaFree(dv); FAIL(c, SGPU_ERR_ARG, "malloc of the COO arrays failed"); }
+    CK(c, cudaMemcpyAsync(*rind, dr, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(*cind, dc, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(*values, dv, (size_t)total*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(counts); cudaFree(offs); cudaFree(dr); cudaFree(dc); cudaFree(dv);
+    *nnz = (int)total;
+    return SGPU_OK;
+}
+
+extern "C" {
+
 int sgpu_jacobian_device(sgpu_ctx* c, int* slots, float* build_ms) {
-    (void)slots; (void)build_ms;
     if (!c) return SGPU_ERR_ARG;
-    FAIL(c, SGPU_ERR_STATE, "Jacobian kernels not built yet");
+    if (int rc = jacobian_build(c, build_ms)) return rc;
+    if (slots) *slots = c->jac.slots;
+    return SGPU_OK;
 }
+
+int sgpu_jacobian_coo(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int** cind, double** values, int apply_lhs_transform) {
+    if (!c || !nnz || !rind || !cind || !values) return SGPU_ERR_ARG;
+    if (apply_lhs_transform && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS transform needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
+    if (int rc = jacobian_build(c, nullptr)) return rc;
+    return c->v.nv == 5 ? jacobian_export_t<5>(c, nnz, rind, cind, values, apply_lhs_transform)
+                        : jacobian_export_t<4>(c, nnz, rind, cind, values, apply_lhs_transform);
+}
+
 int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) {
-    (void)transpose; (void)x; (void)y;
-    if (!c) return SGPU_ERR_ARG;
-    FAIL(c, SGPU_ERR_STATE, "Jacobian kernels not built yet");
+    if (!c || !x || !y) return SGPU_ERR_ARG;
+    if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    double *xp = nullptr, *yp = nullptr;
+    CK(c, cudaMalloc(&xp, v.plane*v.nv*sizeof(double))); CK(c, cudaMalloc(&yp, v.plane*v.nv*sizeof(double)));
+    CK(c, cudaMemsetAsync(xp, 0, v.plane*v.nv*sizeof(double), c->stream));
+    CK(c, cudaMemsetAsync(yp, 0, v.plane*v.nv*sizeof(double), c->stream));
+    // x: GLOBAL host AoS -> planes (owned rows + the slab's ghost rows)
+    {
+        const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.njc);
+        const int nrows = jb - ja, r0 = ja - v.j0 + JOFF;
+        const size_t M = (size_t)nrows*v.nv;
+        if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
+        CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, x + (size_t)ja*v.nv, sizeof(double)*v.njc*v.nv, sizeof(double)*M, v.nic, cudaMemcpyHostToDevice, c->stream));
+        aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, xp, r0, nrows);
+        CKL(c); c->launches++;
+    }
+    const dim3 grd((v.nic + 127)/128, v.njl);
+    const GhostTable gt = ghost_table_of(c);
+    const bool order2 = c->d.lhs_order == 2;
+    if (v.nv == 5) jac_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, xp, yp, transpose);
+    else jac_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, xp, yp, transpose);
+    CKL(c); c->launches++;
+    int rc = download_planes(c, yp, v.nv, y);
+    cudaFree(xp); cudaFree(yp);
+    return rc;
 }

@@ -41,6 +41,8 @@ struct sgpu_ctx {
     double* halo_recv[2] = {nullptr, nullptr};
     double* halo_peer[2] = {nullptr, nullptr};
     JacStore jac{};
+    void* ghost_tab = nullptr;
+    int* jac_err = nullptr;
     bool have_grid = false, have_dt = false;
     std::string err;
     long long launches = 0;
@@ -165,6 +167,8 @@ int sgpu_destroy(sgpu_ctx* c) {
                       c->stage, c->halo_recv[0], c->halo_recv[1]})
         if (p) cudaFree(p);
     jac_free(c->jac);
+    if (c->ghost_tab) cudaFree(c->ghost_tab);
+    if (c->jac_err) cudaFree(c->jac_err);
     for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
     return SGPU_OK;
@@ -219,15 +223,16 @@ int sgpu_set_field(sgpu_ctx* c, const char* name, const double* f) {
     return SGPU_OK;
 }
 
-// download a cell plane group to a GLOBAL host AoS array (owned rows only)
-static int download_planes(sgpu_ctx* c, const double* planes, int nvp, double* host) {
+// download a cell plane group to a GLOBAL host AoS array (owned rows only); window = host holds owned rows only
+static int download_planes(sgpu_ctx* c, const double* planes, int nvp, double* host, bool window = false) {
     const View& v = c->v;
     const size_t M = (size_t)v.njl*v.nv;
     if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
     planes_to_aos_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, planes, JOFF, v.njl, nvp);
     CKL(c); c->launches++;
-    CK(c, cudaMemcpy2DAsync(host + (size_t)v.j0*v.nv, sizeof(double)*v.njc*v.nv, c->stage, sizeof(double)*M, sizeof(double)*M, v.nic,
-                            cudaMemcpyDeviceToHost, c->stream));
+    if (window) CK(c, cudaMemcpyAsync(host, c->stage, sizeof(double)*M*v.nic, cudaMemcpyDeviceToHost, c->stream));
+    else CK(c, cudaMemcpy2DAsync(host + (size_t)v.j0*v.nv, sizeof(double)*v.njc*v.nv, c->stage, sizeof(double)*M, sizeof(double)*M, v.nic,
+                                 cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return SGPU_OK;
 }
@@ -254,19 +259,24 @@ int sgpu_get_metrics(sgpu_ctx* c, double* normal_chi, double* normal_eta, double
 }
 
 // ---------------------------------------------------------------------------------------------- state
-int sgpu_set_state(sgpu_ctx* c, int which, const double* q) {
+int sgpu_set_state_window(sgpu_ctx* c, int which, const double* q, int j_first, int j_count) {
     if (!c || !q || which < 0 || which > 1) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
-    const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.njc);        // cell rows [ja, jb)
+    if (j_first > v.j0 || j_first + j_count < v.j1) FAIL(c, SGPU_ERR_ARG, "state window [%d,%d) does not cover the owned rows [%d,%d)", j_first, j_first + j_count, v.j0, v.j1);
+    const int ja = std::max(std::max(v.j0 - 2, 0), j_first), jb = std::min(std::min(v.j1 + 2, v.njc), j_first + j_count);   // cell rows [ja, jb)
     const int nrows = jb - ja, r0 = ja - v.j0 + JOFF;
     const size_t M = (size_t)nrows*v.nv;
     if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
-    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, q + (size_t)ja*v.nv, sizeof(double)*v.njc*v.nv, sizeof(double)*M, v.nic,
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, q + (size_t)(ja - j_first)*v.nv, sizeof(double)*j_count*v.nv, sizeof(double)*M, v.nic,
                             cudaMemcpyHostToDevice, c->stream));
     aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, c->q[which], r0, nrows);
     CKL(c); c->launches++;
     return SGPU_OK;
+}
+int sgpu_set_state(sgpu_ctx* c, int which, const double* q) {
+    if (!c) return SGPU_ERR_ARG;
+    return sgpu_set_state_window(c, which, q, 0, c->v.njc);
 }
 int sgpu_get_state(sgpu_ctx* c, int which, double* q) {
     if (!c || !q || which < 0 || which > 1) return SGPU_ERR_ARG;
@@ -277,6 +287,11 @@ int sgpu_get_rhs(sgpu_ctx* c, double* rhs) {
     if (!c || !rhs) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     return download_planes(c, c->rhs, c->v.nv, rhs);
+}
+int sgpu_get_rhs_window(sgpu_ctx* c, double* rhs) {
+    if (!c || !rhs) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    return download_planes(c, c->rhs, c->v.nv, rhs, true);
 }
 int sgpu_get_dt(sgpu_ctx* c, double* dt) {
     if (!c || !dt) return SGPU_ERR_ARG;

@@ -1,0 +1,116 @@
+"""GPU parity tests of the Jacobian path: device block-stencil Jacobian -> COO export (the sparse_jac
+replacement) against the reference-derived golden Jacobians and the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import TOL, coo_to_dict_arrays, golden, golden_state, jac_rel_err
+from structured_b200.cases import ZOO, turbulent_channel_case, zoo_case
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_eq(case, **kw):
+    from structured_b200.api import GpuEulerEquation
+    return GpuEulerEquation(case, **kw)
+
+
+def check_pattern(n, ours, ref):
+    """every structural entry of the reference pattern must be present in ours (ours may carry a few explicit
+    zeros more); returns (nnz_ours, nnz_ref)"""
+    ko, _ = coo_to_dict_arrays(n, *ours)
+    kr, _ = coo_to_dict_arrays(n, *ref)
+    missing = np.setdiff1d(kr, ko)
+    assert len(missing) == 0, "entries of the reference pattern missing: %d, first (row, col) = %s" % (len(missing), divmod(int(missing[0]), n))
+    assert len(ko) == len(ours[2]), "COO export must not contain duplicate (row, col)"
+    assert np.all(np.diff(ours[0].astype(np.int64) * n + ours[1].astype(np.int64)) > 0), "COO export must be sorted by (row, col)"
+    return len(ko), len(kr)
+
+
+@pytest.mark.parametrize("name", ["channel"] + ["zoo_" + z for z in ZOO])
+def test_jacobian_matches_reference_golden(name):
+    case, z = golden(name)
+    eq = gpu_eq(case)
+    q = golden_state(case, z)
+    eq.set_state(q)
+    ours = eq.jacobian_coo()
+    ref = (z["jac_rind"], z["jac_cind"], z["jac_values"])
+    n = q.size
+    err = jac_rel_err(n, ours, ref)
+    assert err <= TOL, (name, err)
+    no, nr = check_pattern(n, ours, ref)
+    assert no <= 1.10 * nr, (no, nr)
+    eq.close()
+
+
+def test_jacobian_matches_reference_golden_naca_sample():
+    case, z = golden("naca0012")
+    eq = gpu_eq(case)
+    q = case.perturbed_q()
+    eq.set_state(q)
+    ri, ci, va = eq.jacobian_coo()
+    n = q.size
+    keep = np.isin(ri, z["jac_rows"])
+    ours = (ri[keep], ci[keep], va[keep])
+    ref = (z["jac_rind"], z["jac_cind"], z["jac_values"])
+    assert jac_rel_err(n, ours, ref) <= TOL
+    check_pattern(n, ours, ref)
+    assert abs(np.sqrt((va * va).sum()) - float(z["jac_fro"])) <= 1e-12 * float(z["jac_fro"])
+    assert abs(va[ri == ci].sum() - float(z["jac_trace"])) <= 1e-12 * abs(float(z["jac_trace"]))
+    eq.close()
+
+
+@pytest.mark.parametrize("nic,njc,order,lhs_order,flux,periodic", [(33, 21, 2, 2, "roe", True), (40, 18, 2, 1, "roe", False), (26, 30, 1, 1, "ausm", True), (21, 17, 2, 2, "ausm", False)])
+def test_sa_jacobian_matches_oracle(nic, njc, order, lhs_order, flux, periodic):
+    from oracle.bindings import PortOracle
+    case = turbulent_channel_case(nic, njc, ntrans=1, order=order, lhs_order=lhs_order, flux=flux, reynolds=2e4, periodic=periodic)
+    port = PortOracle(case); eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q)
+    ours = eq.jacobian_coo(); ref = port.jacobian(q, True)
+    err = jac_rel_err(q.size, ours, ref)
+    assert err <= TOL, err
+    check_pattern(q.size, ours, ref)
+    eq.close(); port.close()
+
+
+def test_lhs_transform_and_ownership():
+    """values = -values, diagonal += 1/dt (src/solver/solver.cpp:162-171)"""
+    case, z = golden("channel")
+    eq = gpu_eq(case)
+    q = golden_state(case, z)
+    eq.set_state(q)
+    eq.calc_dt(3.0)
+    ri, ci, va = eq.jacobian_coo()
+    ri2, ci2, va2 = eq.jacobian_coo(apply_lhs_transform=True)
+    assert np.array_equal(ri, ri2) and np.array_equal(ci, ci2)
+    dt = eq.get_dt().reshape(-1)
+    want = -va
+    d = ri == ci
+    want[d] += 1.0 / dt[ri[d]]
+    assert np.abs(va2 - want).max() <= 1e-13 * np.abs(want).max()
+    eq.close()
+
+
+@pytest.mark.parametrize("ntrans", [0, 1])
+def test_device_jacobian_products_and_adjoint_identity(ntrans):
+    """y = J x agrees with the COO matrix and with a directional derivative of the residual; (J^T psi).v = psi.(J v)"""
+    case = turbulent_channel_case(48, 40, ntrans=ntrans, reynolds=2e4)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q)
+    ri, ci, va = eq.jacobian_coo()
+    slots, ms = eq.jacobian_device()
+    assert slots == 13 and ms > 0
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(q.shape) * np.abs(q).mean(axis=(0, 1))
+    psi = rng.standard_normal(q.shape)
+    Jv = eq.jacobian_apply(v)
+    want = np.zeros(q.size); np.add.at(want, ri, va * v.reshape(-1)[ci])
+    assert np.abs(Jv.reshape(-1) - want).max() <= 1e-12 * np.abs(want).max()
+    h = 1e-6
+    fd = (eq.calc_residual(q + h * v) - eq.calc_residual(q - h * v)) / (2 * h)
+    assert np.abs(Jv - fd).max() <= 2e-6 * np.abs(fd).max()
+    JTpsi = eq.jacobian_apply(psi, transpose=True)
+    lhs, rhs = float((JTpsi * v).sum()), float((psi * Jv).sum())
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
+    eq.close()
