@@ -31,9 +31,12 @@ template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N>& a, 
 template <int N> __device__ __forceinline__ Dual<N> operator*(double b, const Dual<N>& a) { Dual<N> r; r.v = a.v*b; SG_DUAL_LOOP r.d[k] = a.d[k]*b; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N>& a) { Dual<N> r; r.v = -a.v; SG_DUAL_LOOP r.d[k] = -a.d[k]; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, double b) { return a*(1.0/b); }
-template <int N> __device__ __forceinline__ Dual<N> s_rcp(const Dual<N>& a) { Dual<N> r; r.v = 1.0/a.v; const double s = -r.v*r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
+__device__ __forceinline__ double rcp_fast(double x);
+__device__ __forceinline__ double rsqrt_fast(double x);
+template <int N> __device__ __forceinline__ Dual<N> s_rcp(const Dual<N>& a) { Dual<N> r; r.v = rcp_fast(a.v); const double s = -r.v*r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
+template <int N> __device__ __forceinline__ Dual<N> s_rsqrt(const Dual<N>& a) { Dual<N> r; r.v = rsqrt_fast(a.v); const double s = -0.5*r.v*r.v*r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) { return a*s_rcp(b); }
-template <int N> __device__ __forceinline__ Dual<N> s_sqrt(const Dual<N>& a) { Dual<N> r; r.v = sqrt(a.v); const double s = 0.5/r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
+template <int N> __device__ __forceinline__ Dual<N> s_sqrt(const Dual<N>& a) { Dual<N> r; const double y = rsqrt_fast(a.v); r.v = a.v*y; const double s = 0.5*y; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
 // derivative of the taken branch (a.v < 0 ? -a : a), the same convention as oracle/adtypes.hpp
 template <int N> __device__ __forceinline__ Dual<N> s_abs(const Dual<N>& a) { return a.v < 0.0 ? -a : a; }
 template <int N> __device__ __forceinline__ double s_val(const Dual<N>& a) { return a.v; }

@@ -2,20 +2,27 @@
 // sm_100a kernel -- primitives, MUSCL/first-order reconstruction, Roe/AUSM flux, Green-Gauss viscous
 // flux, SA transport + source, accumulation, /V and the partial sums of the residual norms.
 //
-// Decomposition ("j-marching strips"): a CTA of RW threads owns a strip of RW-1 cell
-// columns and walks a chunk of rows upward.  Thread t owns column i0+t: it converts that column's q to
-// primitives once per row (shared-memory ring of 5 rows), computes the chi face on the LEFT of its cell
-// and the eta face on TOP of it, keeps the bottom eta flux of the next row in registers, and gets its
-// right chi flux from thread t+1 through shared memory.  Every face flux is therefore evaluated exactly
-// once (plus one face column per strip seam and one face row per chunk seam), and q is read from HBM
-// once (plus 3 halo columns per strip and 4 halo rows per chunk).
+// Decomposition ("j-marching strips"): a CTA of RW = 128 threads owns a strip of 128 plane
+// columns (124 cells + 2 halo columns each side) and walks a chunk of rows upward.  Thread t owns column
+// i0-2+t.  Per row it
+//   phase 1  converts the prefetched q of row jl+2 to primitives and stores them and the row's metrics into
+//            shared-memory rings (every HBM byte is loaded once, coalesced, one iteration ahead of its use);
+//            evaluates the MUSCL limiter of its own cell along i ONCE (both face values) and the vertex
+//            average of its lower-left... upper-left vertex ONCE, publishing what the right neighbour needs;
+//   phase 2  evaluates the limiter of cell (i, jl+1) along j once (one value used now, one carried in
+//            registers), the eta face on top of its cell and the chi face on its left -- each face flux is
+//            computed exactly once; the bottom eta flux, the lower vertex average and the left state of the
+//            next eta face are carried in registers, the right chi flux comes from thread t+1 via smem;
+//   phase 3  accumulates, adds sources, divides by V, stores rhs (coalesced) and accumulates rhs^2.
+// Two __syncthreads per row.  Arithmetic per cell is independent of the strip/chunk/slab decomposition, so
+// one GPU and N slabs agree bit for bit.
 #pragma once
 #include "common.cuh"
 
 namespace sg {
 
-constexpr int RW = 128;                 // threads per CTA = chi faces per strip; cells per strip = RW-1
-constexpr int PW = RW + 3;              // primitive columns held per row: i0-2 .. i0+RW
+constexpr int RW = 128;                 // threads per CTA = plane columns per strip
+constexpr int RCELLS = RW - 4;          // cells per strip (threads 2 .. RW-3)
 
 struct ResParams {
     View v; Gas g; Metrics m;
@@ -26,16 +33,23 @@ struct ResParams {
     int nstrips, nchunks, rpc;
 };
 
-// primitive ring variables / vertex-average variables
-enum { PR = 0, PU = 1, PV = 2, PP = 3, PT = 4, PM = 5, PN = 6, PMT = 7, PRN = 8 };
+// vertex-average / dual-cell variable set
 enum { VU = 0, VV = 1, VT = 2, VM = 3, VN = 4, VMT = 5, VRN = 6 };
+// metric ring planes
+enum { MCX = 0, MCY = 1, MEX = 2, MEY = 3, MVOL = 4 };
 
 template <int NV, bool VISC> struct ResCfg {
     static constexpr bool SA = NV > 4;
-    static constexpr int NPV = VISC ? (SA ? 9 : 6) : (SA ? 7 : 4);
+    static constexpr int NB = VISC ? (SA ? 5 : 2) : (SA ? 1 : 0);      // ring B: T, mu [, nut, mut, rn]  (inviscid SA: nut)
     static constexpr int NVA = VISC ? (SA ? 7 : 4) : 0;
     static constexpr int NFC = NV + (SA ? 3 : 0);
-    static constexpr size_t smem_bytes = sizeof(double)*((size_t)5*NPV*PW + (size_t)2*(NVA ? NVA : 1)*RW + (size_t)NFC*RW);
+    static constexpr int A_DBL = 4*4*RW;                               // ring A: 4 rows x (rho,u,v,p)
+    static constexpr int B_DBL = 3*(NB ? NB : 1)*RW;                   // ring B: 3 rows
+    static constexpr int M_DBL = 4*5*RW;                               // metric ring: 4 rows x (ncx,ncy,nex,ney,vol)
+    static constexpr int VX_DBL = (NVA ? NVA : 1)*RW;
+    static constexpr int FC_DBL = NFC*RW;
+    static constexpr int MX_DBL = 4*RW;
+    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(A_DBL + B_DBL + M_DBL + VX_DBL + FC_DBL + MX_DBL);
 };
 
 struct FaceGeom {
@@ -63,14 +77,15 @@ __device__ __forceinline__ void face_net_flux(const Gas& g, const FaceGeom& fg, 
         auto grady = [&](int k) { return (fg.ty*qt[k] - fg.by*qb[k] + fg.ry*qrr[k] - fg.ly*qll[k])*fg.ivol2; };   // mesh.cpp:84,128
         auto bar = [&](int k) { return 0.25*(qll[k] + qrr[k] + qt[k] + qb[k]); };                                 // mesh.cpp:18,29
         const double ubar = bar(VU), vbar = bar(VV);
-        double mu = bar(VM), kk;
-        if (SA) { const double mut = bar(VMT); kk = g.cp*(mu/g.pr + mut/SA_PRT); mu = mu + mut; }
-        else kk = mu*g.cp_over_pr;
+        const double mub = bar(VM);
+        double mu = mub, kk;
+        if (SA) { const double mut = bar(VMT); kk = mub*g.cp_over_pr + mut*g.cp_over_prt; mu = mub + mut; }
+        else kk = mub*g.cp_over_pr;
         double G[4];
         viscous_flux<double>(fg.nx, fg.ny, gradx(VU), grady(VU), gradx(VV), grady(VV), gradx(VT), grady(VT), ubar, vbar, mu, kk, G);
         D[1] += G[1]; D[2] += G[2]; D[3] += G[3];
         if (SA) {
-            const double musa = bar(VM) + bar(VRN);
+            const double musa = mub + bar(VRN);
             D[4] += musa*(1.0/SA_SIGMA)*(gradx(VN)*fg.nx + grady(VN)*fg.ny);
             bars[0] = ubar; bars[1] = vbar; bars[2] = bar(VN);
         }
@@ -78,178 +93,199 @@ __device__ __forceinline__ void face_net_flux(const Gas& g, const FaceGeom& fg, 
 }
 
 template <int NV, int ORDER, int FLUX, bool VISC>
-__global__ void __launch_bounds__(RW) residual_kernel(const ResParams prm) {
+__global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
     using Cfg = ResCfg<NV, VISC>;
     constexpr bool SA = Cfg::SA;
-    constexpr int NPV = Cfg::NPV, NVA = Cfg::NVA, NFC = Cfg::NFC;
+    constexpr int NB = Cfg::NB, NVA = Cfg::NVA;
+    constexpr int BT = 0, BM = 1, BN = VISC ? 2 : 0, BMT = 3, BRN = 4;   // ring B variable indices
     extern __shared__ double smem[];
-    double* sP = smem;                                  // [5][NPV][PW]
-    double* sVA = sP + 5*NPV*PW;                        // [2][NVA][RW]
-    double* sFC = sVA + 2*(NVA ? NVA : 1)*RW;           // [NFC][RW]
+    double* sA = smem;                                  // [4][4][RW]   rho,u,v,p      rows jl..jl+2 live
+    double* sB = sA + Cfg::A_DBL;                       // [3][NB][RW]  T,mu,...       rows jl..jl+1 live
+    double* sM = sB + Cfg::B_DBL;                       // [4][5][RW]   metrics        rows jl..jl+2 live
+    double* sVX = sM + Cfg::M_DBL;                      // [NVA][RW]    vertex averages of vertex row jl+1
+    double* sFC = sVX + Cfg::VX_DBL;                    // [NFC][RW]    chi net flux (+ SA face averages)
+    double* sMX = sFC + Cfg::FC_DBL;                    // [4][RW]      MUSCL value at the cell's high-i face
 
-    const View& v = prm.v; const Gas& g = prm.g; const Metrics& m = prm.m;
+    const View& v = prm.v; const Gas& g = prm.g;
     const int t = threadIdx.x;
     const int strip = blockIdx.x % prm.nstrips, chunk = blockIdx.x / prm.nstrips;
-    const int i0 = strip*(RW - 1);
+    const int i0 = strip*RCELLS;
     const int ra = chunk*prm.rpc, rb = imin(ra + prm.rpc, v.njl);
-    const int i = i0 + t;                                // global index of own cell column / own chi face
-    const int cc = t + 2;                                // own column inside the primitive ring
-    const bool face_ok = i <= v.nic;
-    const bool cell_ok = (t < RW - 1) && (i < v.nic);
-    const int c = i + IOFF;                              // plane column of own cell / face
+    const int i = i0 - 2 + t;                            // global index of own cell column / own chi face
+    const bool face_ok = t >= 2 && t <= RW - 2 && i <= v.nic;
+    const bool cell_ok = t >= 2 && t <= RW - 3 && i < v.nic;
+    const int c = imin(i + IOFF, v.pitch - 1);           // plane column (clamped: the last strip may overhang the pitch)
     const size_t pl = v.plane;
+    const bool col_int = i >= 0 && i <= v.nic - 1;       // own column is an interior cell column
 
-    auto slot = [&](int jl) { return sP + ((jl + 10) % 5)*NPV*PW; };
-    auto vaslot = [&](int vr) { return sVA + ((vr + 2) & 1)*NVA*RW; };
+    auto Arow = [&](int jl) { return sA + ((jl + 4) & 3)*4*RW; };
+    auto Brow = [&](int jl) { return sB + ((jl + 3) % 3)*(NB ? NB : 1)*RW; };
+    auto Mrow = [&](int jl) { return sM + ((jl + 4) & 3)*5*RW; };
 
-    // ---- R1: q row -> primitive ring (FluidModel::primvars + mu loop, eulerequation.cpp:158,183-188)
-    auto load_row = [&](int jl) {
-        double* S = slot(jl);
-        const int r = jl + JOFF;
-        for (int k = t; k < PW; k += RW) {
-            const int col = i0 + k;                      // plane column = (i0 - 2 + k) + IOFF
-            if (col < v.pitch) {
-                const size_t o = v.at(r, col);
-                double rho, u, vv, p, T;
-                cons_to_prim<double>(g, prm.q[o], prm.q[pl + o], prm.q[2*pl + o], prm.q[3*pl + o], rho, u, vv, p, T);
-                S[PR*PW + k] = rho; S[PU*PW + k] = u; S[PV*PW + k] = vv; S[PP*PW + k] = p;
-                double mul = 0.0;
-                if (VISC) { S[PT*PW + k] = T; mul = laminar_viscosity<double>(g, T); S[PM*PW + k] = mul; }
-                if (SA) {
-                    const double rn = prm.q[4*pl + o];
-                    const double nut = rn/rho;
-                    S[(VISC ? PN : 4)*PW + k] = nut;
-                    if (VISC) { S[PMT*PW + k] = rn*sa_fv1<double>(rn/mul); S[PRN*PW + k] = rn; }
-                }
-            }
-        }
+    // ---- HBM -> registers (issued one iteration ahead), registers -> shared-memory rings
+    double pq[NV], pm[5];
+    auto fetch_row = [&](int jl) {
+        const size_t o = v.at(jl + JOFF, c);
+#pragma unroll
+        for (int k = 0; k < NV; k++) pq[k] = __ldg(prm.q + k*pl + o);
+        pm[MCX] = __ldg(prm.m.ncx + o); pm[MCY] = __ldg(prm.m.ncy + o);
+        pm[MEX] = __ldg(prm.m.nex + o); pm[MEY] = __ldg(prm.m.ney + o); pm[MVOL] = __ldg(prm.m.vol + o);
     };
-    constexpr int PNI = VISC ? PN : 4;                   // ring index of nu~
-
-    // ---- R2: vertex averages of row vr: vertex (i, vr) = 1/4 of the four cells around it
-    auto vertex_row = [&](int vr) {
+    auto store_row = [&](int jl) {                       // FluidModel::primvars + mu loop (eulerequation.cpp:158,183-188)
+        double* A = Arow(jl); double* B = Brow(jl); double* M = Mrow(jl);
+        double rho, u, vv, p, T;
+        cons_to_prim<double>(g, pq[0], pq[1], pq[2], pq[3], rho, u, vv, p, T);
+        A[0*RW + t] = rho; A[1*RW + t] = u; A[2*RW + t] = vv; A[3*RW + t] = p;
+        double mul = 0.0;
+        if (VISC) { B[BT*RW + t] = T; mul = laminar_viscosity<double>(g, T); B[BM*RW + t] = mul; }
+        if (SA) {
+            const double rn = pq[NV - 1];
+            B[BN*RW + t] = rn*rcp_fast(rho);
+            if (VISC) { B[BMT*RW + t] = rn*sa_fv1<double>(rn*rcp_fast(mul)); B[BRN*RW + t] = rn; }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) M[k*RW + t] = pm[k];
+    };
+    // the dual-cell variable set of a cell (row jl, ring column k)
+    auto cell_vars = [&](int jl, int k, double* out) {
+        const double* A = Arow(jl); const double* B = Brow(jl);
+        out[VU] = A[1*RW + k]; out[VV] = A[2*RW + k]; out[VT] = B[BT*RW + k]; out[VM] = B[BM*RW + k];
+        if (SA) { out[VN] = B[BN*RW + k]; out[VMT] = B[BMT*RW + k]; out[VRN] = B[BRN*RW + k]; }
+    };
+    // vertex (i, vr) = 1/4 of the four cells around it (mesh.cpp:16-17,27-28,49-52,96-97)
+    auto vertex_avg = [&](int vr, double* out) {
         if (!VISC) return;
-        const double* A = slot(vr - 1); const double* B = slot(vr);
-        double* V = vaslot(vr);
-        auto avg = [&](int pv) { return 0.25*(A[pv*PW + cc - 1] + A[pv*PW + cc] + B[pv*PW + cc - 1] + B[pv*PW + cc]); };
-        V[VU*RW + t] = avg(PU); V[VV*RW + t] = avg(PV); V[VT*RW + t] = avg(PT); V[VM*RW + t] = avg(PM);
-        if (SA) { V[VN*RW + t] = avg(PN); V[VMT*RW + t] = avg(PMT); V[VRN*RW + t] = avg(PRN); }
-    };
-    // gather the vertex-average variable set of a cell / of a vertex into a small register array
-    auto cell_vars = [&](const double* S, int k, double* out) {
-        out[VU] = S[PU*PW + k]; out[VV] = S[PV*PW + k]; out[VT] = S[PT*PW + k]; out[VM] = S[PM*PW + k];
-        if (SA) { out[VN] = S[PN*PW + k]; out[VMT] = S[PMT*PW + k]; out[VRN] = S[PRN*PW + k]; }
-    };
-    auto vert_vars = [&](const double* V, int k, double* out) {
+        const int tm = imax(t - 1, 0);
+        double a[NVA ? NVA : 1], b[NVA ? NVA : 1], cc_[NVA ? NVA : 1], d[NVA ? NVA : 1];
+        cell_vars(vr - 1, tm, a); cell_vars(vr - 1, t, b); cell_vars(vr, tm, cc_); cell_vars(vr, t, d);
 #pragma unroll
-        for (int n = 0; n < NVA; n++) out[n] = V[n*RW + k];
+        for (int n = 0; n < NVA; n++) out[n] = 0.25*(a[n] + b[n] + cc_[n] + d[n]);
+    };
+    // MUSCL limiter of the own cell along i at row jl: value at its low face (kept) and high face (published)
+    auto chi_limiter = [&](int jl, double* to_low) {
+        const double* A = Arow(jl);
+        const int tm = imax(t - 1, 0), tp = imin(t + 1, RW - 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double q0 = A[k*RW + t];
+            double hi = q0, lo = q0;                     // ghost / first order: the cell value (reconstruction.cpp:29-35)
+            if (ORDER == 2 && col_int) muscl_cell<double>(A[k*RW + tm], q0, A[k*RW + tp], prm.eps_chi, hi, lo);
+            to_low[k] = lo;
+            sMX[k*RW + t] = hi;
+        }
+    };
+    // MUSCL limiter of cell (i, jl) along j: to_high (left state of face jl+1), to_low (right state of face jl)
+    auto eta_limiter = [&](int jl, double* to_high, double* to_low) {
+        const double* Am = Arow(jl - 1); const double* A0 = Arow(jl); const double* Ap = Arow(jl + 1);
+        const int gjc = v.j0 + jl;
+        const bool row_int = gjc >= 0 && gjc <= v.njc - 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double q0 = A0[k*RW + t];
+            double hi = q0, lo = q0;
+            if (ORDER == 2 && row_int) muscl_cell<double>(Am[k*RW + t], q0, Ap[k*RW + t], prm.eps_eta, hi, lo);
+            to_high[k] = hi; to_low[k] = lo;
+        }
     };
 
-    // ---- eta face between local cell rows jl (left state) and jl+1 (right state), column i
-    auto eta_face = [&](int jl, double* D, double* bars) {
-        const double* LL = slot(jl - 1); const double* L = slot(jl); const double* R = slot(jl + 1); const double* RR = slot(jl + 2);
-        const int gj = v.j0 + jl + 1;                    // global eta-face index (face row gj lies below cell row gj)
-        double ql[4], qr[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { ql[k] = L[k*PW + cc]; qr[k] = R[k*PW + cc]; }
-        if (ORDER == 2) {                                // reconstruction.cpp:133-150; ghost side stays first order
-            const bool Lint = gj - 1 >= 0, Rint = gj <= v.njc - 1;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                double hi, lo;
-                if (Lint) { muscl_cell<double>(LL[k*PW + cc], L[k*PW + cc], R[k*PW + cc], prm.eps_eta, hi, lo); ql[k] = hi; }
-                if (Rint) { muscl_cell<double>(L[k*PW + cc], R[k*PW + cc], RR[k*PW + cc], prm.eps_eta, hi, lo); qr[k] = lo; }
-            }
-        }
+    // ---- eta face between local cell rows jl and jl+1 (global face row gj = j0+jl+1), column i
+    auto eta_face = [&](int jl, const double* ql, const double* qr, const double* vown, double* D, double* bars) {
+        const int gj = v.j0 + jl + 1;
         FaceGeom fg;
-        const int rf = gj - v.j0 + JOFF;
-        fg.nx = m.nex[v.at(rf, c)]; fg.ny = m.ney[v.at(rf, c)];
-        double qt[NVA ? NVA : 1], qb[NVA ? NVA : 1], qrr[NVA ? NVA : 1], qll[NVA ? NVA : 1];
-        if (VISC) {                                      // mesh.cpp:99-126 with clamped indices (DESIGN.md)
-            const int a = imax(gj - 1, 0), b = imin(gj, v.njc - 1);
-            const int rA = a - v.j0 + JOFF, rB = b - v.j0 + JOFF;
-            const int rT = imin(gj + 1, v.nj - 1) - v.j0 + JOFF, rBo = imax(gj - 1, 0) - v.j0 + JOFF;
-            fg.tx = fg.nx + m.nex[v.at(rT, c)]; fg.ty = fg.ny + m.ney[v.at(rT, c)];
-            fg.bx = fg.nx + m.nex[v.at(rBo, c)]; fg.by = fg.ny + m.ney[v.at(rBo, c)];
-            fg.lx = m.ncx[v.at(rA, c)] + m.ncx[v.at(rB, c)]; fg.ly = m.ncy[v.at(rA, c)] + m.ncy[v.at(rB, c)];
-            fg.rx = m.ncx[v.at(rA, c + 1)] + m.ncx[v.at(rB, c + 1)]; fg.ry = m.ncy[v.at(rA, c + 1)] + m.ncy[v.at(rB, c + 1)];
-            fg.ivol2 = 1.0/(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
-            const double* V = vaslot(jl + 1);
-            cell_vars(R, cc, qt); cell_vars(L, cc, qb);
-            vert_vars(V, t + 1, qrr); vert_vars(V, t, qll);
+        const double* Mf = Mrow(jl + 1);
+        fg.nx = Mf[MEX*RW + t]; fg.ny = Mf[MEY*RW + t];
+        double qt[NVA ? NVA : 1], qb[NVA ? NVA : 1], qrr[NVA ? NVA : 1];
+        if (VISC) {                                      // mesh.cpp:99-126 with clamped indices (DESIGN.md 3.1)
+            const int la = imax(gj - 1, 0) - v.j0, lb = imin(gj, v.njc - 1) - v.j0;     // local rows of the two cells
+            const int lT = imin(gj + 1, v.nj - 1) - v.j0, lBo = imax(gj - 1, 0) - v.j0;
+            const double* MA = Mrow(la); const double* MB = Mrow(lb); const double* MT = Mrow(lT); const double* MBo = Mrow(lBo);
+            fg.tx = fg.nx + MT[MEX*RW + t]; fg.ty = fg.ny + MT[MEY*RW + t];
+            fg.bx = fg.nx + MBo[MEX*RW + t]; fg.by = fg.ny + MBo[MEY*RW + t];
+            fg.lx = MA[MCX*RW + t] + MB[MCX*RW + t]; fg.ly = MA[MCY*RW + t] + MB[MCY*RW + t];
+            fg.rx = MA[MCX*RW + t + 1] + MB[MCX*RW + t + 1]; fg.ry = MA[MCY*RW + t + 1] + MB[MCY*RW + t + 1];
+            fg.ivol2 = rcp_fast(MA[MVOL*RW + t] + MB[MVOL*RW + t]);
+            cell_vars(jl + 1, t, qt); cell_vars(jl, t, qb);
+#pragma unroll
+            for (int n = 0; n < NVA; n++) qrr[n] = sVX[n*RW + t + 1];
         }
-        const double nutL = SA ? L[PNI*PW + cc] : 0.0, nutR = SA ? R[PNI*PW + cc] : 0.0;
-        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, qt, qb, qrr, qll, D, bars);
+        const double nutL = SA ? Brow(jl)[BN*RW + t] : 0.0, nutR = SA ? Brow(jl + 1)[BN*RW + t] : 0.0;
+        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, qt, qb, qrr, vown, D, bars);
     };
-
     // ---- chi face between cells (i-1, jl) and (i, jl)
-    auto chi_face = [&](int jl, double* D, double* bars) {
-        const double* S = slot(jl);
-        const int gj = v.j0 + jl;
-        double ql[4], qr[4];
+    auto chi_face = [&](int jl, const double* qr, const double* vtop, const double* vbot, double* D, double* bars) {
+        double ql[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { ql[k] = S[k*PW + cc - 1]; qr[k] = S[k*PW + cc]; }
-        if (ORDER == 2) {                                // reconstruction.cpp:94-111
-            const bool Lint = i - 1 >= 0, Rint = i <= v.nic - 1;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                double hi, lo;
-                if (Lint) { muscl_cell<double>(S[k*PW + cc - 2], S[k*PW + cc - 1], S[k*PW + cc], prm.eps_chi, hi, lo); ql[k] = hi; }
-                if (Rint) { muscl_cell<double>(S[k*PW + cc - 1], S[k*PW + cc], S[k*PW + cc + 1], prm.eps_chi, hi, lo); qr[k] = lo; }
-            }
-        }
+        for (int k = 0; k < 4; k++) ql[k] = sMX[k*RW + t - 1];
         FaceGeom fg;
-        const int r = jl + JOFF;
-        fg.nx = m.ncx[v.at(r, c)]; fg.ny = m.ncy[v.at(r, c)];
-        double qt[NVA ? NVA : 1], qb[NVA ? NVA : 1], qrr[NVA ? NVA : 1], qll[NVA ? NVA : 1];
+        const double* M0 = Mrow(jl); const double* M1 = Mrow(jl + 1);
+        fg.nx = M0[MCX*RW + t]; fg.ny = M0[MCY*RW + t];
+        double qrr[NVA ? NVA : 1], qll[NVA ? NVA : 1];
         if (VISC) {                                      // mesh.cpp:54-82 with clamped indices
-            const int ca = imax(i - 1, 0) + IOFF, cb = imin(i, v.nic - 1) + IOFF;
-            const int cR = imin(i + 1, v.ni - 1) + IOFF, cL = imax(i - 1, 0) + IOFF;
-            fg.tx = m.nex[v.at(r + 1, ca)] + m.nex[v.at(r + 1, cb)]; fg.ty = m.ney[v.at(r + 1, ca)] + m.ney[v.at(r + 1, cb)];
-            fg.bx = m.nex[v.at(r, ca)] + m.nex[v.at(r, cb)]; fg.by = m.ney[v.at(r, ca)] + m.ney[v.at(r, cb)];
-            fg.rx = fg.nx + m.ncx[v.at(r, cR)]; fg.ry = fg.ny + m.ncy[v.at(r, cR)];
-            fg.lx = fg.nx + m.ncx[v.at(r, cL)]; fg.ly = fg.ny + m.ncy[v.at(r, cL)];
-            fg.ivol2 = 1.0/(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
-            vert_vars(vaslot(jl + 1), t, qt); vert_vars(vaslot(jl), t, qb);
-            cell_vars(S, cc, qrr); cell_vars(S, cc - 1, qll);
+            const int ta = t - 1 + (i == 0 ? 1 : 0), tb = t - (i == v.nic ? 1 : 0);
+            const int tR = t + (i + 1 <= v.ni - 1 ? 1 : 0), tL = t - (i - 1 >= 0 ? 1 : 0);
+            fg.tx = M1[MEX*RW + ta] + M1[MEX*RW + tb]; fg.ty = M1[MEY*RW + ta] + M1[MEY*RW + tb];
+            fg.bx = M0[MEX*RW + ta] + M0[MEX*RW + tb]; fg.by = M0[MEY*RW + ta] + M0[MEY*RW + tb];
+            fg.rx = fg.nx + M0[MCX*RW + tR]; fg.ry = fg.ny + M0[MCY*RW + tR];
+            fg.lx = fg.nx + M0[MCX*RW + tL]; fg.ly = fg.ny + M0[MCY*RW + tL];
+            fg.ivol2 = rcp_fast(M0[MVOL*RW + ta] + M0[MVOL*RW + tb]);
+            cell_vars(jl, t, qrr); cell_vars(jl, t - 1, qll);
         }
-        (void)gj;
-        const double nutL = SA ? S[PNI*PW + cc - 1] : 0.0, nutR = SA ? S[PNI*PW + cc] : 0.0;
-        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, qt, qb, qrr, qll, D, bars);
+        const double nutL = SA ? Brow(jl)[BN*RW + t - 1] : 0.0, nutR = SA ? Brow(jl)[BN*RW + t] : 0.0;
+        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, vtop, vbot, qrr, qll, D, bars);
     };
 
-    // ---- prologue: rows ra-2 .. ra+1, vertex row ra, bottom eta face of row ra
-    load_row(ra - 2); load_row(ra - 1); load_row(ra); load_row(ra + 1);
+    // ---- prologue: rows ra-2 .. ra+1 into the rings; limiter of cells ra-1 and ra along j; vertex row ra;
+    //      bottom eta face of row ra
+    for (int jl = ra - 2; jl <= ra + 1; jl++) { fetch_row(jl); store_row(jl); }
+    fetch_row(imin(ra + 2, v.njl + 1));                  // prefetch for the first iteration
     __syncthreads();
-    vertex_row(ra);
-    __syncthreads();
+    double vbot[NVA ? NVA : 1], ehi[4];
     double Dbot[NV], bbot[3] = {0, 0, 0};
-    if (cell_ok) eta_face(ra - 1, Dbot, bbot);
-    else {
+    {
+        double qlo[4], elo[4], dummy[4];
+        vertex_avg(ra, vbot);
 #pragma unroll
-        for (int k = 0; k < NV; k++) Dbot[k] = 0.0;
+        for (int n = 0; n < NVA; n++) sVX[n*RW + t] = vbot[n];
+        eta_limiter(ra - 1, qlo /*to_high of cell ra-1*/, dummy);
+        eta_limiter(ra, ehi, elo);
+        __syncthreads();
+        if (cell_ok) eta_face(ra - 1, qlo, elo, vbot, Dbot, bbot);
+        else {
+#pragma unroll
+            for (int k = 0; k < NV; k++) Dbot[k] = 0.0;
+        }
     }
+    __syncthreads();                                     // all prologue reads of ring rows / sVX done before they are overwritten
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
     for (int jl = ra; jl < rb; jl++) {
-        load_row(jl + 2);
-        vertex_row(jl + 1);
+        // ---- phase 1
+        store_row(jl + 2);
+        if (jl + 1 < rb) fetch_row(jl + 3);
+        double cqr[4], vtop[NVA ? NVA : 1];
+        chi_limiter(jl, cqr);
+        vertex_avg(jl + 1, vtop);
+#pragma unroll
+        for (int n = 0; n < NVA; n++) sVX[n*RW + t] = vtop[n];
         __syncthreads();
-        double Dtop[NV], btop[3] = {0, 0, 0}, Dchi[NV], bchi[3] = {0, 0, 0};
-        if (cell_ok) eta_face(jl, Dtop, btop);
+        // ---- phase 2
+        double Dtop[NV], btop[3] = {0, 0, 0}, Dchi[NV], bchi[3] = {0, 0, 0}, ehi_next[4], elo[4];
+        eta_limiter(jl + 1, ehi_next, elo);
+        if (cell_ok) eta_face(jl, ehi, elo, vtop, Dtop, btop);
         if (face_ok) {
-            chi_face(jl, Dchi, bchi);
+            chi_face(jl, cqr, vtop, vbot, Dchi, bchi);
 #pragma unroll
             for (int k = 0; k < NV; k++) sFC[k*RW + t] = Dchi[k];
             if (SA) { sFC[(NV + 0)*RW + t] = bchi[0]; sFC[(NV + 1)*RW + t] = bchi[1]; sFC[(NV + 2)*RW + t] = bchi[2]; }
         }
         __syncthreads();
+        // ---- phase 3
         if (cell_ok) {
-            const int r = jl + JOFF;
-            const size_t o = v.at(r, c);
-            const double V = m.vol[o], Vi = 1.0/V;
+            const size_t o = v.at(jl + JOFF, c);
+            const double* M0 = Mrow(jl); const double* M1 = Mrow(jl + 1);
+            const double V = M0[MVOL*RW + t], Vi = rcp_fast(V);
             double res[NV];
 #pragma unroll
             for (int k = 0; k < NV; k++) res[k] = (Dtop[k] - Dbot[k]) + (sFC[k*RW + t + 1] - Dchi[k]);
@@ -258,8 +294,8 @@ __global__ void __launch_bounds__(RW) residual_kernel(const ResParams prm) {
             if (SA) {
                 double om = 0.0, dndx = 0.0, dndy = 0.0;
                 if (VISC) {                              // Green-Gauss over the cell's own four faces
-                    const double cxr = m.ncx[v.at(r, c + 1)], cyr = m.ncy[v.at(r, c + 1)], cxl = m.ncx[o], cyl = m.ncy[o];
-                    const double ext = m.nex[v.at(r + 1, c)], eyt = m.ney[v.at(r + 1, c)], exb = m.nex[o], eyb = m.ney[o];
+                    const double cxr = M0[MCX*RW + t + 1], cyr = M0[MCY*RW + t + 1], cxl = M0[MCX*RW + t], cyl = M0[MCY*RW + t];
+                    const double ext = M1[MEX*RW + t], eyt = M1[MEY*RW + t], exb = M0[MEX*RW + t], eyb = M0[MEY*RW + t];
                     const double ur = sFC[(NV + 0)*RW + t + 1], vr = sFC[(NV + 1)*RW + t + 1], nr = sFC[(NV + 2)*RW + t + 1];
                     const double dvdx = (vr*cxr - bchi[1]*cxl + btop[1]*ext - bbot[1]*exb)*Vi;
                     const double dudy = (ur*cyr - bchi[0]*cyl + btop[0]*eyt - bbot[0]*eyb)*Vi;
@@ -267,10 +303,9 @@ __global__ void __launch_bounds__(RW) residual_kernel(const ResParams prm) {
                     dndy = (nr*cyr - bchi[2]*cyl + btop[2]*eyt - bbot[2]*eyb)*Vi;
                     om = fabs(dvdx - dudy);
                 }
-                const double* S = slot(jl);
-                const double mul = VISC ? S[PM*PW + cc] : g.mu_ref;
-                const double src = sa_source<double>(S[PR*PW + cc], S[PNI*PW + cc], mul, om, dndx, dndy, prm.wdist[o], prm.beta[o]);
-                res[4] += src*V;
+                const double mul = VISC ? Brow(jl)[BM*RW + t] : g.mu_ref;
+                const double src = sa_source<double>(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, om, dndx, dndy, __ldg(prm.wdist + o), __ldg(prm.beta + o));
+                res[NV - 1] += src*V;
             }
 #pragma unroll
             for (int k = 0; k < NV; k++) {
@@ -282,6 +317,10 @@ __global__ void __launch_bounds__(RW) residual_kernel(const ResParams prm) {
             for (int k = 0; k < NV; k++) Dbot[k] = Dtop[k];
             if (SA) { bbot[0] = btop[0]; bbot[1] = btop[1]; bbot[2] = btop[2]; }
         }
+#pragma unroll
+        for (int n = 0; n < NVA; n++) vbot[n] = vtop[n];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ehi[k] = ehi_next[k];
     }
 
     // ---- partial sums of rhs^2 for the L2 norms (src/solver/solver.cpp:125-134): warp shuffle + smem

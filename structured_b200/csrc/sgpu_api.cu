@@ -118,7 +118,7 @@ int sgpu_create(const sgpu_desc* d, sgpu_ctx** out) {
     g.cp = GAMMA*g.R/(GAMMA - 1.0);                                // fluid.cpp:14
     g.pr = d->pr_inf; g.mu_ref = d->mu_inf; g.T_ref = d->T_inf;
     g.rho_inf = d->rho_inf; g.u_inf = d->u_inf; g.v_inf = d->v_inf; g.p_inf = d->p_inf;
-    g.cp_over_pr = g.cp/g.pr;
+    g.cp_over_pr = g.cp/g.pr; g.iR = 1.0/g.R; g.iT_ref = 1.0/g.T_ref; g.cp_over_prt = g.cp/SA_PRT;
     c->viscous = d->mu_inf > 1e-15;                                // config.cpp:41
     c->eps_chi = std::pow(10.0/nic, 3); c->eps_eta = std::pow(10.0/njc, 3);   // reconstruction.cpp:62-63 (GLOBAL counts)
 
@@ -329,14 +329,59 @@ static int apply_bcs(sgpu_ctx* c, int which) {
     return SGPU_OK;
 }
 
+// Grid shape: strips of RCELLS columns x chunks of rows.  The chunk count is chosen so that the grid is an
+// integer number of full waves of (SM count x resident CTAs per SM) -- a partial last wave would idle most
+// SMs for a whole chunk -- while chunks stay tall enough to amortise the 4-row prologue.
+static void shape_grid(const View& v, int ctas_per_sm, int sms, ResParams& p) {
+    p.nstrips = (v.nic + RCELLS - 1)/RCELLS;
+    const int wave = std::max(1, ctas_per_sm*sms);
+    int best = 1; double best_cost = 1e300;
+    const int max_chunks = std::max(1, v.njl/8);
+    for (int nch = 1; nch <= max_chunks; nch++) {
+        const int rpc = (v.njl + nch - 1)/nch;
+        const int nchunks = (v.njl + rpc - 1)/rpc;
+        const long long ctas = (long long)p.nstrips*nchunks;
+        const long long waves = (ctas + wave - 1)/wave;
+        const double cost = (double)waves*(rpc + 5.0);          // time ~ waves x (rows + prologue) per CTA
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = nchunks; }
+    }
+    p.rpc = (v.njl + best - 1)/best;
+    p.nchunks = (v.njl + p.rpc - 1)/p.rpc;
+}
+
 template <int NV, int ORDER, int FLUX, bool VISC>
-static int launch_residual_t(sgpu_ctx* c, const ResParams& p, int grid) {
+static int launch_residual_t(sgpu_ctx* c, ResParams& p, int* grid_out) {
     using Cfg = ResCfg<NV, VISC>;
-    static bool attr_set = false;
+    static int occ = 0, sms = 0;
     auto kern = residual_kernel<NV, ORDER, FLUX, VISC>;
-    if (!attr_set) { CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes)); attr_set = true; }
+    if (!occ) {
+        CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+        CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RW, Cfg::smem_bytes));
+        CK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (occ < 1) occ = 1;
+    }
+    shape_grid(c->v, occ, sms, p);
+    const int grid = p.nstrips*p.nchunks;
+    if (p.partial) {
+        const size_t need = (size_t)grid*NV;
+        if (need > c->partial_cap) {
+            if (c->partial) CK(c, cudaFree(c->partial));
+            CK(c, cudaMalloc(&c->partial, need*sizeof(double))); c->partial_cap = need;
+        }
+        p.partial = c->partial;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        if (c->ev_used == c->ev.size()) {
+            cudaEvent_t a, b; CK(c, cudaEventCreate(&a)); CK(c, cudaEventCreate(&b)); c->ev.emplace_back(a, b);
+        }
+        e0 = c->ev[c->ev_used].first; e1 = c->ev[c->ev_used].second; c->ev_used++;
+        CK(c, cudaEventRecord(e0, c->stream));
+    }
     kern<<<grid, RW, Cfg::smem_bytes, c->stream>>>(p);
     CKL(c);
+    if (c->timing) CK(c, cudaEventRecord(e1, c->stream));
+    *grid_out = grid;
     return SGPU_OK;
 }
 
@@ -346,34 +391,12 @@ static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms) {
     p.v = v; p.g = c->g; p.m = metrics_of(c);
     p.q = c->q[which]; p.rhs = c->rhs; p.wdist = c->wdist; p.beta = c->beta;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.dpdx = c->d.dpdx; p.dpdy = c->d.dpdy;
-    p.nstrips = (v.nic + RW - 2)/(RW - 1);
-    // chunk rows so that the grid is a few waves of (148 SMs x resident CTAs), but chunks stay tall enough to
-    // amortise the 4-row prologue
-    const int target_items = 148*4*3;
-    int nchunks = std::max(1, std::min((target_items + p.nstrips - 1)/p.nstrips, (v.njl + 15)/16));
-    p.rpc = (v.njl + nchunks - 1)/nchunks;
-    p.nchunks = (v.njl + p.rpc - 1)/p.rpc;
-    const int grid = p.nstrips*p.nchunks;
-    if (want_norms) {
-        const size_t need = (size_t)grid*v.nv;
-        if (need > c->partial_cap) {
-            if (c->partial) CK(c, cudaFree(c->partial));
-            CK(c, cudaMalloc(&c->partial, need*sizeof(double))); c->partial_cap = need;
-        }
-        p.partial = c->partial;
-    } else p.partial = nullptr;
+    p.partial = want_norms ? (double*)1 : nullptr;              // placeholder: sized once the grid is known
+    int grid = 0;
     const int order = lhs ? c->d.lhs_order : c->d.order;           // eulerequation.cpp:203-208
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->timing) {
-        if (c->ev_used == c->ev.size()) {
-            cudaEvent_t a, b; CK(c, cudaEventCreate(&a)); CK(c, cudaEventCreate(&b)); c->ev.emplace_back(a, b);
-        }
-        e0 = c->ev[c->ev_used].first; e1 = c->ev[c->ev_used].second; c->ev_used++;
-        CK(c, cudaEventRecord(e0, c->stream));
-    }
     int rc = SGPU_ERR_ARG;
     const bool roe = c->d.flux == SGPU_FLUX_ROE;
-#define RES_CASE(NV_, ORD_, FL_, VI_) rc = launch_residual_t<NV_, ORD_, FL_, VI_>(c, p, grid)
+#define RES_CASE(NV_, ORD_, FL_, VI_) rc = launch_residual_t<NV_, ORD_, FL_, VI_>(c, p, &grid)
     if (v.nv == 5) {
         if (order == 2) { if (roe) RES_CASE(5, 2, SGPU_FLUX_ROE, true); else RES_CASE(5, 2, SGPU_FLUX_AUSM, true); }
         else            { if (roe) RES_CASE(5, 1, SGPU_FLUX_ROE, true); else RES_CASE(5, 1, SGPU_FLUX_AUSM, true); }
@@ -387,7 +410,6 @@ static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms) {
 #undef RES_CASE
     if (rc) return rc;
     c->launches++;
-    if (c->timing) CK(c, cudaEventRecord(e1, c->stream));
     if (want_norms) {
         reduce_partials_kernel<<<v.nv, 256, 0, c->stream>>>(c->partial, grid, v.nv, c->l2sq_dev);
         CKL(c); c->launches++;
