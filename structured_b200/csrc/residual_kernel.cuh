@@ -40,7 +40,7 @@ enum { MCX = 0, MCY = 1, MEX = 2, MEY = 3, MVOL = 4 };
 
 template <int NV, bool VISC> struct ResCfg {
     static constexpr bool SA = NV > 4;
-    static constexpr int NB = VISC ? (SA ? 5 : 2) : (SA ? 1 : 0);      // ring B: T, mu [, nut, mut, rn]  (inviscid SA: nut)
+    static constexpr int NB = VISC ? (SA ? 4 : 2) : (SA ? 1 : 0);      // ring B: T, mu [, nut, mut]  (inviscid SA: nut)
     static constexpr int NVA = VISC ? (SA ? 7 : 4) : 0;
     static constexpr int NFC = NV + (SA ? 3 : 0);
     static constexpr int A_DBL = 4*4*RW;                               // ring A: 4 rows x (rho,u,v,p)
@@ -49,7 +49,8 @@ template <int NV, bool VISC> struct ResCfg {
     static constexpr int VX_DBL = (NVA ? NVA : 1)*RW;
     static constexpr int FC_DBL = NFC*RW;
     static constexpr int MX_DBL = 4*RW;
-    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(A_DBL + B_DBL + M_DBL + VX_DBL + FC_DBL + MX_DBL);
+    static constexpr int Q_DBL = (NV + (SA ? 2 : 0))*RW;                // cp.async staging: raw q row (+ wall distance, beta)
+    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(A_DBL + B_DBL + M_DBL + VX_DBL + FC_DBL + MX_DBL + Q_DBL);
 };
 
 struct FaceGeom {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
     using Cfg = ResCfg<NV, VISC>;
     constexpr bool SA = Cfg::SA;
     constexpr int NB = Cfg::NB, NVA = Cfg::NVA;
-    constexpr int BT = 0, BM = 1, BN = VISC ? 2 : 0, BMT = 3, BRN = 4;   // ring B variable indices
+    constexpr int BT = 0, BM = 1, BN = VISC ? 2 : 0, BMT = 3;   // ring B variable indices
     extern __shared__ double smem[];
     double* sA = smem;                                  // [4][4][RW]   rho,u,v,p      rows jl..jl+2 live
     double* sB = sA + Cfg::A_DBL;                       // [3][NB][RW]  T,mu,...       rows jl..jl+1 live
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
     double* sVX = sM + Cfg::M_DBL;                      // [NVA][RW]    vertex averages of vertex row jl+1
     double* sFC = sVX + Cfg::VX_DBL;                    // [NFC][RW]    chi net flux (+ SA face averages)
     double* sMX = sFC + Cfg::FC_DBL;                    // [4][RW]      MUSCL value at the cell's high-i face
+    double* sQ = sMX + Cfg::MX_DBL;                     // [NV(+2)][RW] cp.async staging of the next raw q row (+ SA fields)
 
     const View& v = prm.v; const Gas& g = prm.g;
     const int t = threadIdx.x;
@@ -122,17 +124,25 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
     auto Brow = [&](int jl) { return sB + ((jl + 3) % 3)*(NB ? NB : 1)*RW; };
     auto Mrow = [&](int jl) { return sM + ((jl + 4) & 3)*5*RW; };
 
-    // ---- HBM -> registers (issued one iteration ahead), registers -> shared-memory rings
-    double pq[NV], pm[5];
-    auto fetch_row = [&](int jl) {
+    // ---- HBM -> on-chip, one iteration ahead of use.  q (+ wall distance, beta) goes through registers because it
+    //      is transformed (primitives) on the way into the ring; the metric planes are copied untransformed,
+    //      so they go global -> shared directly with cp.async (no registers, no LDS/STS issue slots).
+    auto cp8 = [&](unsigned dst, const double* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src)); };
+    // one commit group per row: raw q of row jl -> staging, metrics of row jl -> their ring row, SA fields of row jf
+    auto fetch_async = [&](int jl, int jf) {
         const size_t o = v.at(jl + JOFF, c);
+        const unsigned dq = (unsigned)__cvta_generic_to_shared(sQ + t);
 #pragma unroll
-        for (int k = 0; k < NV; k++) pq[k] = __ldg(prm.q + k*pl + o);
-        pm[MCX] = __ldg(prm.m.ncx + o); pm[MCY] = __ldg(prm.m.ncy + o);
-        pm[MEX] = __ldg(prm.m.nex + o); pm[MEY] = __ldg(prm.m.ney + o); pm[MVOL] = __ldg(prm.m.vol + o);
+        for (int k = 0; k < NV; k++) cp8(dq + k*RW*8, prm.q + k*pl + o);
+        if (SA) { const size_t of = v.at(jf + JOFF, c); cp8(dq + NV*RW*8, prm.wdist + of); cp8(dq + (NV + 1)*RW*8, prm.beta + of); }
+        const unsigned dm = (unsigned)__cvta_generic_to_shared(Mrow(jl) + t);
+        cp8(dm + MCX*RW*8, prm.m.ncx + o); cp8(dm + MCY*RW*8, prm.m.ncy + o);
+        cp8(dm + MEX*RW*8, prm.m.nex + o); cp8(dm + MEY*RW*8, prm.m.ney + o); cp8(dm + MVOL*RW*8, prm.m.vol + o);
+        asm volatile("cp.async.commit_group;");
     };
-    auto store_row = [&](int jl) {                       // FluidModel::primvars + mu loop (eulerequation.cpp:158,183-188)
-        double* A = Arow(jl); double* B = Brow(jl); double* M = Mrow(jl);
+    auto wait_async = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+    auto store_prims = [&](int jl, const double* pq) {   // FluidModel::primvars + mu loop (eulerequation.cpp:158,183-188)
+        double* A = Arow(jl); double* B = Brow(jl);
         double rho, u, vv, p, T;
         cons_to_prim<double>(g, pq[0], pq[1], pq[2], pq[3], rho, u, vv, p, T);
         A[0*RW + t] = rho; A[1*RW + t] = u; A[2*RW + t] = vv; A[3*RW + t] = p;
@@ -141,16 +151,27 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
         if (SA) {
             const double rn = pq[NV - 1];
             B[BN*RW + t] = rn*rcp_fast(rho);
-            if (VISC) { B[BMT*RW + t] = rn*sa_fv1<double>(rn*rcp_fast(mul)); B[BRN*RW + t] = rn; }
+            if (VISC) B[BMT*RW + t] = rn*sa_fv1<double>(rn*rcp_fast(mul));
         }
+    };
+    auto store_row_direct = [&](int jl) {                // prologue: straight from HBM
+        double pq[NV];
+        const size_t o = v.at(jl + JOFF, c);
 #pragma unroll
-        for (int k = 0; k < 5; k++) M[k*RW + t] = pm[k];
+        for (int k = 0; k < NV; k++) pq[k] = __ldg(prm.q + k*pl + o);
+        store_prims(jl, pq);
+    };
+    auto store_row_staged = [&](int jl) {                // main loop: from the cp.async staging row (own column only)
+        double pq[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) pq[k] = sQ[k*RW + t];
+        store_prims(jl, pq);
     };
     // the dual-cell variable set of a cell (row jl, ring column k)
     auto cell_vars = [&](int jl, int k, double* out) {
         const double* A = Arow(jl); const double* B = Brow(jl);
         out[VU] = A[1*RW + k]; out[VV] = A[2*RW + k]; out[VT] = B[BT*RW + k]; out[VM] = B[BM*RW + k];
-        if (SA) { out[VN] = B[BN*RW + k]; out[VMT] = B[BMT*RW + k]; out[VRN] = B[BRN*RW + k]; }
+        if (SA) { out[VN] = B[BN*RW + k]; out[VMT] = B[BMT*RW + k]; out[VRN] = A[0*RW + k]*out[VN]; }
     };
     // vertex (i, vr) = 1/4 of the four cells around it (mesh.cpp:16-17,27-28,49-52,96-97)
     auto vertex_avg = [&](int vr, double* out) {
@@ -236,8 +257,13 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
 
     // ---- prologue: rows ra-2 .. ra+1 into the rings; limiter of cells ra-1 and ra along j; vertex row ra;
     //      bottom eta face of row ra
-    for (int jl = ra - 2; jl <= ra + 1; jl++) { fetch_row(jl); store_row(jl); }
-    fetch_row(imin(ra + 2, v.njl + 1));                  // prefetch for the first iteration
+    for (int jl = ra - 1; jl <= ra + 1; jl++) {          // metric rows ra-1 .. ra+1 straight into their ring rows
+        const size_t o = v.at(jl + JOFF, c);
+        double* M = Mrow(jl);
+        M[MCX*RW + t] = __ldg(prm.m.ncx + o); M[MCY*RW + t] = __ldg(prm.m.ncy + o);
+        M[MEX*RW + t] = __ldg(prm.m.nex + o); M[MEY*RW + t] = __ldg(prm.m.ney + o); M[MVOL*RW + t] = __ldg(prm.m.vol + o);
+    }
+    for (int jl = ra - 2; jl <= ra + 1; jl++) store_row_direct(jl);
     __syncthreads();
     double vbot[NVA ? NVA : 1], ehi[4];
     double Dbot[NV], bbot[3] = {0, 0, 0};
@@ -256,21 +282,26 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
         }
     }
     __syncthreads();                                     // all prologue reads of ring rows / sVX done before they are overwritten
+    fetch_async(ra + 2, ra);                             // consumed in phase 1 of the first iteration
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
     for (int jl = ra; jl < rb; jl++) {
         // ---- phase 1
-        store_row(jl + 2);
-        if (jl + 1 < rb) fetch_row(jl + 3);
+        wait_async();                                    // own cp.async of row jl+2 (issued one iteration ago) has landed
+        store_row_staged(jl + 2);
+        const double wd = SA ? sQ[NV*RW + t] : 1.0, beta = SA ? sQ[(NV + 1)*RW + t] : 1.0;   // SA inputs of row jl
         double cqr[4], vtop[NVA ? NVA : 1];
         chi_limiter(jl, cqr);
         vertex_avg(jl + 1, vtop);
 #pragma unroll
         for (int n = 0; n < NVA; n++) sVX[n*RW + t] = vtop[n];
-        __syncthreads();
+        __syncthreads();                                 // ring rows jl+2 (and everybody's metric copies) are visible
         // ---- phase 2
+        // next row's HBM traffic overlaps this row's flux arithmetic; the metric ring slot is that of row jl-1
+        // and the staging row was consumed above: no reader is left after the barrier
+        if (jl + 1 < rb) fetch_async(jl + 3, jl + 1);
         double Dtop[NV], btop[3] = {0, 0, 0}, Dchi[NV], bchi[3] = {0, 0, 0}, ehi_next[4], elo[4];
         eta_limiter(jl + 1, ehi_next, elo);
         if (cell_ok) eta_face(jl, ehi, elo, vtop, Dtop, btop);
@@ -304,7 +335,7 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
                     om = fabs(dvdx - dudy);
                 }
                 const double mul = VISC ? Brow(jl)[BM*RW + t] : g.mu_ref;
-                const double src = sa_source<double>(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, om, dndx, dndy, __ldg(prm.wdist + o), __ldg(prm.beta + o));
+                const double src = sa_source<double>(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, om, dndx, dndy, wd, beta);
                 res[NV - 1] += src*V;
             }
 #pragma unroll
