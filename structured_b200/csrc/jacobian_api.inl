@@ -54,8 +54,15 @@ static GhostTable ghost_table_of(const sgpu_ctx* c) {
 template <int NV, int ORDER, int FLUX, bool VISC>
 static int launch_jacobian_t(sgpu_ctx* c, const JacParams& p) {
     const View& v = c->v;
-    jacobian_kernel<NV, ORDER, FLUX, VISC><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(p);
+    // stage 1: every face differentiated once (chi faces i = 0..nic of the owned rows; eta faces j0..j1)
+    jac_face_kernel<NV, ORDER, FLUX, VISC, 0><<<dim3((v.nic + 1 + 127)/128, v.njl), 128, 0, c->stream>>>(p);
     CKL(c);
+    jac_face_kernel<NV, ORDER, FLUX, VISC, 1><<<dim3((v.nic + 127)/128, v.njl + 1), 128, 0, c->stream>>>(p);
+    CKL(c);
+    // stage 2: gather per row cell, SA source row, ghost fold
+    jac_gather_kernel<NV, ORDER, VISC><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(p);
+    CKL(c);
+    c->launches += 2;
     return SGPU_OK;
 }
 
@@ -72,12 +79,20 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
         CK(c, cudaMalloc(&c->jac.blocks, need*sizeof(double)));
         c->jac.cap = need;
     }
+    const size_t need_s = (size_t)2*8*v.nv*v.nv*v.plane;           // per-face scratch: chi and eta, 8 stencil cells each
+    if (need_s > c->jac_scratch_cap) {
+        if (c->jac_scratch) CK(c, cudaFree(c->jac_scratch));
+        c->jac_scratch = nullptr; c->jac_scratch_cap = 0;
+        CK(c, cudaMalloc(&c->jac_scratch, need_s*sizeof(double)));
+        c->jac_scratch_cap = need_s;
+    }
     c->jac.slots = nslots; c->jac.valid = false;
     if (int rc = apply_bcs(c, SGPU_STATE_Q)) return rc;          // ghost values of the state the tape would have seen
     CK(c, cudaMemsetAsync(c->jac_err, 0, sizeof(int), c->stream));
     JacParams p;
     p.v = v; p.g = c->g; p.m = metrics_of(c); p.gt = ghost_table_of(c);
     p.q = c->q[0]; p.J = c->jac.blocks; p.wdist = c->wdist; p.beta = c->beta;
+    p.Schi = c->jac_scratch; p.Seta = c->jac_scratch + (size_t)8*v.nv*v.nv*v.plane;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.nslots = nslots; p.err = c->jac_err;
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));

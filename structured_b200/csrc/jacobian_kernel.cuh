@@ -138,72 +138,63 @@ __device__ __forceinline__ void chain_Z(const CellD<NV>& w, double cu, double cv
 struct JacParams {
     View v; Gas g; Metrics m; GhostTable gt;
     const double* q; double* J;
+    double* Schi; double* Seta;          // per-face scratch: S[cellidx(8)][r][c][face plane]
     const double* wdist; const double* beta;
     double eps_chi, eps_eta;
     int nslots;
     int* err;
 };
 
-// accumulate a block into slot storage; first touch stores, later touches read-modify-write
-template <int NV>
-struct SlotAcc {
-    double* J; size_t stride; size_t cell; unsigned touched;
-    __device__ __forceinline__ void add(int slot, const double* blk /*[NV*NV]*/) {
-        double* p = J + ((size_t)slot*NV*NV)*stride + cell;
-        if (touched & (1u << slot)) {
-#pragma unroll
-            for (int e = 0; e < NV*NV; e++) p[e*stride] += blk[e];
-        } else {
-#pragma unroll
-            for (int e = 0; e < NV*NV; e++) p[e*stride] = blk[e];
-            touched |= (1u << slot);
-        }
-    }
-};
+// Stage 1 of the build: ONE thread per FACE computes d(net face flux D = G - F)/dq of the face's eight stencil
+// cells -- every face is differentiated exactly once -- and streams the eight nv x nv blocks to scratch planes.
+//   line cells   0:LL 1:L | 2:R 3:RR   (reconstruction, src/model/reconstruction.cpp)
+//   dual cell    D0 = L, D1 = R (direct), 4:P0 5:P1 / 6:M0 7:M1 the cells completing the "plus" / "minus"
+//                vertex averages                          (src/utils/mesh.cpp:44-53, 93-98)
+// fg.t*/b* are the doubled normals of the plus/minus sides, fg.r*/l* those of D1/D0.
+struct CellRef { int r, c; };
 
-// d(net face flux D = G - F)/dq of every stencil cell of ONE face, scaled by `scale` (= +-1/V), accumulated
-// into the row cell's slots.  Generic over chi / eta faces:
-//   line cells   LL, L | R, RR     (reconstruction, src/model/reconstruction.cpp)
-//   dual cell    D0 = L, D1 = R (direct), vertex averages over {D0, D1, P0, P1} ("plus" side) and
-//                {D0, D1, M0, M1} ("minus" side)          (src/utils/mesh.cpp:44-53, 93-98)
 template <int NV, int ORDER, int FLUX, bool VISC, int NL>
-__device__ __forceinline__ void face_jacobian(const Gas& g, const FaceGeom& fg, double scale, double eps,
-                                              const CellD<NV>* LL, const CellD<NV>& L, const CellD<NV>& R, const CellD<NV>* RR,
-                                              bool Lint, bool Rint,
-                                              const CellD<NV>* P0, const CellD<NV>* P1, const CellD<NV>* M0, const CellD<NV>* M1,
-                                              int sLL, int sL, int sR, int sRR, int sP0, int sP1, int sM0, int sM1,
-                                              SlotAcc<NV>& acc) {
+__device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const double* __restrict__ q, const FaceGeom& fg, double eps,
+                                            const CellRef* cr, bool Lint, bool Rint, double* __restrict__ S, size_t fo) {
     constexpr bool SA = NV > 4;
-    // ---- 1. reconstruction and its derivative scalars
-    double ql[4], qr[4], dl[4][3], dr[4][3];     // dl[k] = d ql_k / d(LL_k, L_k, R_k); dr[k] = d qr_k / d(L_k, R_k, RR_k)
-    const double Lw[4] = {L.r, L.u, L.v, L.p}, Rw[4] = {R.r, R.u, R.v, R.p};
+    const size_t stride = v.plane;
+    // ---- 1. primitives of the line cells, reconstruction and its derivative scalars
+    double W[4][4];                               // [LL,L,R,RR][rho,u,v,p]
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        const bool need = (n == 1 || n == 2) || (ORDER == 2 && ((n == 0 && Lint) || (n == 3 && Rint)));
+        if (need) {
+            const size_t o = v.at(cr[n].r, cr[n].c);
+            double T;
+            cons_to_prim<double>(g, q[o], q[stride + o], q[2*stride + o], q[3*stride + o], W[n][0], W[n][1], W[n][2], W[n][3], T);
+        } else { W[n][0] = W[n][1] = W[n][2] = W[n][3] = 1.0; }
+    }
+    double ql[4], qr[4], dl[4][3], dr[4][3];      // dl[k] = d ql_k / d(LL_k, L_k, R_k); dr[k] = d qr_k / d(L_k, R_k, RR_k)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        ql[k] = Lw[k]; qr[k] = Rw[k];
+        ql[k] = W[1][k]; qr[k] = W[2][k];
         dl[k][0] = 0; dl[k][1] = 1; dl[k][2] = 0; dr[k][0] = 0; dr[k][1] = 1; dr[k][2] = 0;
     }
     if (ORDER == 2) {
         typedef Dual<3> D3;
         if (Lint) {
-            const double LLw[4] = {LL->r, LL->u, LL->v, LL->p};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                D3 a(LLw[k]), b(Lw[k]), c(Rw[k]), hi, lo; a.d[0] = 1; b.d[1] = 1; c.d[2] = 1;
+                D3 a(W[0][k]), b(W[1][k]), c(W[2][k]), hi, lo; a.d[0] = 1; b.d[1] = 1; c.d[2] = 1;
                 muscl_cell<D3>(a, b, c, eps, hi, lo);
                 ql[k] = hi.v; dl[k][0] = hi.d[0]; dl[k][1] = hi.d[1]; dl[k][2] = hi.d[2];
             }
         }
         if (Rint) {
-            const double RRw[4] = {RR->r, RR->u, RR->v, RR->p};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                D3 a(Lw[k]), b(Rw[k]), c(RRw[k]), hi, lo; a.d[0] = 1; b.d[1] = 1; c.d[2] = 1;
+                D3 a(W[1][k]), b(W[2][k]), c(W[3][k]), hi, lo; a.d[0] = 1; b.d[1] = 1; c.d[2] = 1;
                 muscl_cell<D3>(a, b, c, eps, hi, lo);
                 qr[k] = lo.v; dr[k][0] = lo.d[0]; dr[k][1] = lo.d[1]; dr[k][2] = lo.d[2];
             }
         }
     }
-    // ---- 2. dF/d(ql, qr) by forward-mode passes of NL lanes through the flux function itself
+    // ---- 2. dF/d(ql, qr): forward-mode passes of NL lanes through the flux function the residual kernel runs
     double Fd[4][8], F0 = 0.0;
     typedef Dual<NL> DN;
 #pragma unroll
@@ -222,118 +213,171 @@ __device__ __forceinline__ void face_jacobian(const Gas& g, const FaceGeom& fg, 
             for (int l = 0; l < NL; l++) Fd[r][pass*NL + l] = F[r].d[l];
         F0 = F[0].v;
     }
-    // ---- 3. inviscid blocks of the four line cells: -scale * (FdL diag(dl_s) + FdR diag(dr_s)) dW_s/dq_s
+    // ---- 3. viscous: the 13 face aggregates (linear in the six cells) and dG/d(aggregate)
+    const double iv = VISC ? fg.ivol2 : 0.0;
+    double G_ux[4], G_uy[4], G_vx[4], G_vy[4], G_mu[4];           // rows 1..3
+    double G_Tx3 = 0, G_Ty3 = 0, G_ub3 = 0, G_vb3 = 0, G_k3 = 0, gn = 0, musa_s = 0;
+    const double nxf = fg.nx, nyf = fg.ny;
+    double nutL = 0.0, nutR = 0.0;
+    if (VISC || SA) {
+        double sD0[7], sD1[7], sP[7], sM[7];
+#pragma unroll
+        for (int n = 0; n < 7; n++) { sD0[n] = sD1[n] = sP[n] = sM[n] = 0.0; }
+#pragma unroll 1
+        for (int n = 1; n < 8; n++) {
+            if (n == 3) continue;
+            if (!VISC && n > 2) break;
+            CellD<NV> w; load_cell<NV, VISC>(v, g, q, cr[n].r, cr[n].c, w);
+            const double z[7] = {w.u, w.v, w.T, w.mu, w.mut, w.nut, w.rn};
+            double* dst = n == 1 ? sD0 : (n == 2 ? sD1 : (n < 6 ? sP : sM));
+#pragma unroll
+            for (int k = 0; k < 7; k++) dst[k] += z[k];
+        }
+        nutL = sD0[5]; nutR = sD1[5];
+        if (VISC) {
+            auto agg = [&](int k, double& gx, double& gy, double& bar) {
+                const double qp = 0.25*(sD0[k] + sD1[k] + sP[k]), qm = 0.25*(sD0[k] + sD1[k] + sM[k]);
+                gx = (fg.tx*qp - fg.bx*qm + fg.rx*sD1[k] - fg.lx*sD0[k])*iv;
+                gy = (fg.ty*qp - fg.by*qm + fg.ry*sD1[k] - fg.ly*sD0[k])*iv;
+                bar = 0.25*(sD0[k] + sD1[k] + qp + qm);
+            };
+            double ux, uy, ub, vx, vy, vb, Tx, Ty, Tb, mub, d1, d2;
+            agg(0, ux, uy, ub); agg(1, vx, vy, vb); agg(2, Tx, Ty, Tb); agg(3, d1, d2, mub);
+            double mutb = 0, rnb = 0, nx_ = 0, ny_ = 0, nb_ = 0;
+            if (SA) { agg(4, d1, d2, mutb); agg(6, d1, d2, rnb); agg(5, nx_, ny_, nb_); }
+            (void)Tb; (void)nb_;
+            const double mu = mub + mutb;
+            const double kk = SA ? (mub*g.cp_over_pr + mutb*g.cp_over_prt) : mub*g.cp_over_pr;
+            const double div = ux + vy;
+            const double txx_h = 2.0*ux - (2.0/3.0)*div, tyy_h = 2.0*vy - (2.0/3.0)*div, txy_h = uy + vx;   // tau / mu
+            const double txx = mu*txx_h, tyy = mu*tyy_h, txy = mu*txy_h;
+            const double c43 = 4.0/3.0*mu, c23 = 2.0/3.0*mu;       // flux.cpp:36-45
+            G_ux[1] = c43*nxf;  G_uy[1] = mu*nyf; G_vx[1] = mu*nyf; G_vy[1] = -c23*nxf; G_mu[1] = txx_h*nxf + txy_h*nyf;
+            G_ux[2] = -c23*nyf; G_uy[2] = mu*nxf; G_vx[2] = mu*nxf; G_vy[2] = c43*nyf;  G_mu[2] = txy_h*nxf + tyy_h*nyf;
+            G_ux[3] = nxf*ub*c43 - nyf*vb*c23; G_vy[3] = -nxf*ub*c23 + nyf*vb*c43;
+            G_uy[3] = mu*(nxf*vb + nyf*ub); G_vx[3] = G_uy[3];
+            G_Tx3 = kk*nxf; G_Ty3 = kk*nyf;
+            G_ub3 = nxf*txx + nyf*txy; G_vb3 = nxf*txy + nyf*tyy;
+            G_mu[3] = nxf*(ub*txx_h + vb*txy_h) + nyf*(ub*txy_h + vb*tyy_h);
+            G_k3 = nxf*Tx + nyf*Ty;
+            gn = (nx_*nxf + ny_*nyf)*(1.0/SA_SIGMA); musa_s = (mub + rnb)*(1.0/SA_SIGMA);
+        }
+    }
+    const double dk_dmu = g.cp_over_pr, dk_dmut = g.cp_over_prt;
     const bool upL = F0 >= 0.0;
-    const double nut_up = SA ? (upL ? L.nut : R.nut) : 0.0;
-    auto line_cell = [&](const CellD<NV>& cs, int slot, int il, int ir, bool isL, bool isR) {
-        // il / ir: which of dl[k][.] / dr[k][.] belongs to this cell (-1: none)
+    const double nut_up = SA ? (upL ? nutL : nutR) : 0.0;
+    // ---- 4. one block per stencil cell: inviscid part (line cells) + viscous part (dual-cell cells)
+    const double qx = 0.25*(fg.tx - fg.bx), qy = 0.25*(fg.ty - fg.by);
+#pragma unroll 1
+    for (int n = 0; n < 8; n++) {
+        const bool line = n < 4, dual = VISC && (n == 1 || n == 2 || n >= 4);
+        const bool used = (line && ((n == 1 || n == 2) || (ORDER == 2 && ((n == 0 && Lint) || (n == 3 && Rint))))) || dual;
         double blk[NV*NV];
 #pragma unroll
-        for (int r = 0; r < NV; r++) {
-            double cw[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const double fr_l = (r < 4) ? Fd[r][k] : nut_up*Fd[0][k];
-                const double fr_r = (r < 4) ? Fd[r][4 + k] : nut_up*Fd[0][4 + k];
-                cw[k] = (il >= 0 ? fr_l*dl[k][il] : 0.0) + (ir >= 0 ? fr_r*dr[k][ir] : 0.0);
-                cw[k] *= -scale;
-            }
-            double out[NV];
-#pragma unroll
-            for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
-            chain_W<NV>(cs, cw, out);
-            if (SA && r == 4 && ((isL && upL) || (isR && !upL))) {       // d(F0 nut_up)/d nut_up
-                out[0] += -scale*F0*(-cs.nut*cs.ri);
-                out[4] += -scale*F0*cs.ri;
+        for (int e = 0; e < NV*NV; e++) blk[e] = 0.0;
+        if (used) {
+            CellD<NV> cs; load_cell<NV, VISC>(v, g, q, cr[n].r, cr[n].c, cs);
+            const int il = n == 0 ? 0 : (n == 1 ? 1 : (n == 2 ? 2 : -1));      // which dl[k][.] belongs to this cell
+            const int ir = n == 1 ? 0 : (n == 2 ? 1 : (n == 3 ? 2 : -1));      // which dr[k][.]
+            double wx = 0, wy = 0, wb = 0;
+            if (dual) {
+                if (n == 2) { wx = (qx + fg.rx)*iv; wy = (qy + fg.ry)*iv; wb = 0.375; }
+                else if (n == 1) { wx = (qx - fg.lx)*iv; wy = (qy - fg.ly)*iv; wb = 0.375; }
+                else if (n < 6) { wx = 0.25*fg.tx*iv; wy = 0.25*fg.ty*iv; wb = 0.0625; }
+                else { wx = -0.25*fg.bx*iv; wy = -0.25*fg.by*iv; wb = 0.0625; }
             }
 #pragma unroll
-            for (int c2 = 0; c2 < NV; c2++) blk[r*NV + c2] = out[c2];
-        }
-        acc.add(slot, blk);
-    };
-    if (ORDER == 2 && Lint) line_cell(*LL, sLL, 0, -1, false, false);
-    line_cell(L, sL, 1, 0, true, false);
-    line_cell(R, sR, 2, 1, false, true);
-    if (ORDER == 2 && Rint) line_cell(*RR, sRR, -1, 2, false, false);
-
-    // ---- 4. viscous blocks of the six dual-cell cells
-    if (VISC) {
-        const double iv = fg.ivol2;
-        // aggregates
-        auto agg = [&](double d0, double d1, double p0, double p1, double m0, double m1, double& gx, double& gy, double& bar) {
-            const double qp = 0.25*(d0 + d1 + p0 + p1), qm = 0.25*(d0 + d1 + m0 + m1);
-            gx = (fg.tx*qp - fg.bx*qm + fg.rx*d1 - fg.lx*d0)*iv;
-            gy = (fg.ty*qp - fg.by*qm + fg.ry*d1 - fg.ly*d0)*iv;
-            bar = 0.25*(d0 + d1 + qp + qm);
-        };
-        // NOTE on naming: fg.t* / fg.b* are the normals of the "plus" / "minus" vertex-average sides and
-        // fg.r* / fg.l* those of the direct cells D1 / D0 (the caller fills them accordingly for eta faces).
-        double ux, uy, ub, vx, vy, vb, Tx, Ty, Tb, mub, dum1, dum2;
-        agg(L.u, R.u, P0->u, P1->u, M0->u, M1->u, ux, uy, ub);
-        agg(L.v, R.v, P0->v, P1->v, M0->v, M1->v, vx, vy, vb);
-        agg(L.T, R.T, P0->T, P1->T, M0->T, M1->T, Tx, Ty, Tb);
-        agg(L.mu, R.mu, P0->mu, P1->mu, M0->mu, M1->mu, dum1, dum2, mub);
-        double mutb = 0, rnb = 0, nx_ = 0, ny_ = 0, nb_ = 0;
-        if (SA) {
-            agg(L.mut, R.mut, P0->mut, P1->mut, M0->mut, M1->mut, dum1, dum2, mutb);
-            agg(L.rn, R.rn, P0->rn, P1->rn, M0->rn, M1->rn, dum1, dum2, rnb);
-            agg(L.nut, R.nut, P0->nut, P1->nut, M0->nut, M1->nut, nx_, ny_, nb_);
-        }
-        (void)Tb; (void)nb_;
-        const double mu = mub + mutb;
-        const double kk = SA ? g.cp*(mub/g.pr + mutb/SA_PRT) : mub*g.cp_over_pr;
-        const double nxf = fg.nx, nyf = fg.ny;
-        const double div = ux + vy;
-        const double txx_h = 2.0*ux - (2.0/3.0)*div, tyy_h = 2.0*vy - (2.0/3.0)*div, txy_h = uy + vx;   // tau / mu
-        const double txx = mu*txx_h, tyy = mu*tyy_h, txy = mu*txy_h;
-        // dG_r / d aggregate, r = 1..3 (flux.cpp:36-45)
-        double G_ux[4], G_uy[4], G_vx[4], G_vy[4], G_Tx[4], G_Ty[4], G_ub[4], G_vb[4], G_mu[4], G_k[4];
-        const double c43 = 4.0/3.0*mu, c23 = 2.0/3.0*mu;
-        G_ux[1] = c43*nxf;  G_uy[1] = mu*nyf; G_vx[1] = mu*nyf; G_vy[1] = -c23*nxf; G_mu[1] = txx_h*nxf + txy_h*nyf;
-        G_ux[2] = -c23*nyf; G_uy[2] = mu*nxf; G_vx[2] = mu*nxf; G_vy[2] = c43*nyf;  G_mu[2] = txy_h*nxf + tyy_h*nyf;
-        G_ux[3] = nxf*ub*c43 - nyf*vb*c23; G_vy[3] = -nxf*ub*c23 + nyf*vb*c43;
-        G_uy[3] = mu*(nxf*vb + nyf*ub); G_vx[3] = G_uy[3];
-        G_Tx[3] = kk*nxf; G_Ty[3] = kk*nyf; G_Tx[1] = G_Tx[2] = G_Ty[1] = G_Ty[2] = 0;
-        G_ub[3] = nxf*txx + nyf*txy; G_vb[3] = nxf*txy + nyf*tyy; G_ub[1] = G_ub[2] = G_vb[1] = G_vb[2] = 0;
-        G_mu[3] = nxf*(ub*txx_h + vb*txy_h) + nyf*(ub*txy_h + vb*tyy_h);
-        G_k[3] = nxf*Tx + nyf*Ty; G_k[1] = G_k[2] = 0;
-        const double dk_dmu = SA ? g.cp/g.pr : g.cp_over_pr, dk_dmut = g.cp/SA_PRT;
-        const double gn = (nx_*nxf + ny_*nyf)*(1.0/SA_SIGMA), musa_s = (mub + rnb)*(1.0/SA_SIGMA);
-        auto visc_cell = [&](const CellD<NV>& cs, int slot, double wx, double wy, double wb) {
-            double blk[NV*NV];
-#pragma unroll
-            for (int c2 = 0; c2 < NV; c2++) blk[c2] = 0.0;                 // mass row: viscous flux[0] is the constant 0 (flux.cpp:42)
-#pragma unroll
-            for (int r = 1; r < 4; r++) {
-                const double cu = G_ux[r]*wx + G_uy[r]*wy + G_ub[r]*wb;
-                const double cv = G_vx[r]*wx + G_vy[r]*wy + G_vb[r]*wb;
-                const double cT = G_Tx[r]*wx + G_Ty[r]*wy;
-                const double cmu = (G_mu[r] + G_k[r]*dk_dmu)*wb;
-                const double cmut = SA ? (G_mu[r] + G_k[r]*dk_dmut)*wb : 0.0;
+            for (int r = 0; r < NV; r++) {
                 double out[NV];
 #pragma unroll
                 for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
-                chain_Z<NV>(cs, scale*cu, scale*cv, scale*cT, scale*cmu, scale*cmut, 0.0, 0.0, out);
+                if (line) {                                                     // D = -F
+                    double cw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const double fl = (r < 4) ? Fd[r < 4 ? r : 0][k] : nut_up*Fd[0][k];
+                        const double fr = (r < 4) ? Fd[r < 4 ? r : 0][4 + k] : nut_up*Fd[0][4 + k];
+                        double cwk = 0.0;
+                        if (il == 0) cwk += fl*dl[k][0]; else if (il == 1) cwk += fl*dl[k][1]; else if (il == 2) cwk += fl*dl[k][2];
+                        if (ir == 0) cwk += fr*dr[k][0]; else if (ir == 1) cwk += fr*dr[k][1]; else if (ir == 2) cwk += fr*dr[k][2];
+                        cw[k] = -cwk;
+                    }
+                    chain_W<NV>(cs, cw, out);
+                    if (SA && r == 4 && ((n == 1 && upL) || (n == 2 && !upL))) {    // d(F0 nut_up)/d nut_up
+                        out[0] += F0*cs.nut*cs.ri;
+                        out[4] += -F0*cs.ri;
+                    }
+                }
+                if (dual && r >= 1) {
+                    if (r < 4) {
+                        const double cu = G_ux[r]*wx + G_uy[r]*wy + (r == 3 ? G_ub3*wb : 0.0);
+                        const double cv = G_vx[r]*wx + G_vy[r]*wy + (r == 3 ? G_vb3*wb : 0.0);
+                        const double cT = r == 3 ? (G_Tx3*wx + G_Ty3*wy) : 0.0;
+                        const double gk = r == 3 ? G_k3 : 0.0;
+                        const double cmu = (G_mu[r] + gk*dk_dmu)*wb;
+                        const double cmut = SA ? (G_mu[r] + gk*dk_dmut)*wb : 0.0;
+                        chain_Z<NV>(cs, cu, cv, cT, cmu, cmut, 0.0, 0.0, out);
+                    } else {                                                    // G4 = (mub + rnb)/sigma (grad nut . n)
+                        chain_Z<NV>(cs, 0.0, 0.0, 0.0, gn*wb, 0.0, musa_s*(wx*nxf + wy*nyf), gn*wb, out);
+                    }
+                }
 #pragma unroll
                 for (int c2 = 0; c2 < NV; c2++) blk[r*NV + c2] = out[c2];
             }
-            if (SA) {                                                    // G4 = (mub + rnb)/sigma (grad nut . n)
-                double out[NV];
+        }
+        double* p = S + ((size_t)n*NV*NV)*stride + fo;
 #pragma unroll
-                for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
-                chain_Z<NV>(cs, 0.0, 0.0, 0.0, scale*gn*wb, 0.0, scale*musa_s*(wx*nxf + wy*nyf), scale*gn*wb, out);
-#pragma unroll
-                for (int c2 = 0; c2 < NV; c2++) blk[4*NV + c2] = out[c2];
-            }
-            acc.add(slot, blk);
-        };
-        const double qx = 0.25*(fg.tx - fg.bx), qy = 0.25*(fg.ty - fg.by);
-        visc_cell(R, sR, (qx + fg.rx)*iv, (qy + fg.ry)*iv, 0.375);
-        visc_cell(L, sL, (qx - fg.lx)*iv, (qy - fg.ly)*iv, 0.375);
-        visc_cell(*P0, sP0, 0.25*fg.tx*iv, 0.25*fg.ty*iv, 0.0625);
-        visc_cell(*P1, sP1, 0.25*fg.tx*iv, 0.25*fg.ty*iv, 0.0625);
-        visc_cell(*M0, sM0, -0.25*fg.bx*iv, -0.25*fg.by*iv, 0.0625);
-        visc_cell(*M1, sM1, -0.25*fg.bx*iv, -0.25*fg.by*iv, 0.0625);
+        for (int e = 0; e < NV*NV; e++) p[e*stride] = blk[e];
+    }
+}
+
+// DIR = 0: chi faces (i in [0, nic], owned rows); DIR = 1: eta faces (rows j0 .. j1)
+template <int NV, int ORDER, int FLUX, bool VISC, int DIR>
+__global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
+    constexpr int NL = 2;
+    const View& v = prm.v; const Metrics& m = prm.m;
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    FaceGeom fg; CellRef cr[8];
+    if (DIR == 0) {
+        if (i > v.nic) return;
+        const int r = jl + JOFF, cf = i + IOFF;                    // chi face i lies left of cell i: L = cell i-1, R = cell i
+        fg.nx = m.ncx[v.at(r, cf)]; fg.ny = m.ncy[v.at(r, cf)];
+        if (VISC) {
+            const int ca = imax(i - 1, 0) + IOFF, cb = imin(i, v.nic - 1) + IOFF;
+            const int cR = imin(i + 1, v.ni - 1) + IOFF, cL = imax(i - 1, 0) + IOFF;
+            fg.tx = m.nex[v.at(r + 1, ca)] + m.nex[v.at(r + 1, cb)]; fg.ty = m.ney[v.at(r + 1, ca)] + m.ney[v.at(r + 1, cb)];
+            fg.bx = m.nex[v.at(r, ca)] + m.nex[v.at(r, cb)]; fg.by = m.ney[v.at(r, ca)] + m.ney[v.at(r, cb)];
+            fg.rx = fg.nx + m.ncx[v.at(r, cR)]; fg.ry = fg.ny + m.ncy[v.at(r, cR)];
+            fg.lx = fg.nx + m.ncx[v.at(r, cL)]; fg.ly = fg.ny + m.ncy[v.at(r, cL)];
+            fg.ivol2 = 1.0/(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
+        }
+        const int cL0 = cf - 1;                                    // plane column of the L cell
+        cr[0] = {r, imax(cL0 - 1, 0)}; cr[1] = {r, cL0}; cr[2] = {r, cL0 + 1}; cr[3] = {r, imin(cL0 + 2, v.pitch - 1)};
+        cr[4] = {r + 1, cL0}; cr[5] = {r + 1, cL0 + 1}; cr[6] = {r - 1, cL0}; cr[7] = {r - 1, cL0 + 1};
+        const bool Lint = i - 1 >= 0, Rint = i <= v.nic - 1;
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_chi, cr, Lint, Rint, prm.Schi, v.at(r, cf));
+    } else {
+        if (i >= v.nic || jl > v.njl) return;
+        const int fj = v.j0 + jl;                                  // global eta-face index; L = cell row fj-1, R = cell row fj
+        const int rf = jl + JOFF, c = i + IOFF;
+        fg.nx = m.nex[v.at(rf, c)]; fg.ny = m.ney[v.at(rf, c)];
+        if (VISC) {
+            const int a = imax(fj - 1, 0), b = imin(fj, v.njc - 1);
+            const int rA = a - v.j0 + JOFF, rB = b - v.j0 + JOFF;
+            const int rT = imin(fj + 1, v.nj - 1) - v.j0 + JOFF, rBo = imax(fj - 1, 0) - v.j0 + JOFF;
+            // generic roles: t* = plus side (right), b* = minus side (left), r* = D1 (top), l* = D0 (bottom)
+            fg.rx = fg.nx + m.nex[v.at(rT, c)]; fg.ry = fg.ny + m.ney[v.at(rT, c)];
+            fg.lx = fg.nx + m.nex[v.at(rBo, c)]; fg.ly = fg.ny + m.ney[v.at(rBo, c)];
+            fg.bx = m.ncx[v.at(rA, c)] + m.ncx[v.at(rB, c)]; fg.by = m.ncy[v.at(rA, c)] + m.ncy[v.at(rB, c)];
+            fg.tx = m.ncx[v.at(rA, c + 1)] + m.ncx[v.at(rB, c + 1)]; fg.ty = m.ncy[v.at(rA, c + 1)] + m.ncy[v.at(rB, c + 1)];
+            fg.ivol2 = 1.0/(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
+        }
+        const int rL = rf - 1;                                     // plane row of the L cell
+        cr[0] = {imax(rL - 1, 0), c}; cr[1] = {rL, c}; cr[2] = {rL + 1, c}; cr[3] = {imin(rL + 2, v.rows - 1), c};
+        cr[4] = {rL, c + 1}; cr[5] = {rL + 1, c + 1}; cr[6] = {rL, c - 1}; cr[7] = {rL + 1, c - 1};
+        const bool Lint = fj - 1 >= 0, Rint = fj <= v.njc - 1;
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_eta, cr, Lint, Rint, prm.Seta, v.at(rf, c));
     }
 }
 
@@ -392,86 +436,41 @@ __device__ __forceinline__ void bc_ghost_jacobian(const Gas& g, const GhostDesc&
     }
 }
 
-template <int NV, int ORDER, int FLUX, bool VISC>
-__global__ void __launch_bounds__(128) jacobian_kernel(const JacParams prm) {
+// Stage 2: one thread per ROW cell gathers, for each stencil slot, the blocks of the (at most four) faces whose
+// stencil contains that cell: J[slot] = sum_f sign_f/V * S_f[cell index within f].  Pure streaming; every scratch
+// block is read by exactly the two cells its face separates.  Then the SA source row, the ghost fold.
+//   face 0: chi face i   (-)   face 1: chi face i+1 (+)   face 2: eta face j (-)   face 3: eta face j+1 (+)
+__device__ __forceinline__ constexpr int gather_dx(int f, int n) {
+    return f < 2 ? ((n < 4 ? n - 2 : ((n & 1) ? 0 : -1)) + (f == 1 ? 1 : 0))
+                 : (n < 4 ? 0 : (n < 6 ? 1 : -1));
+}
+__device__ __forceinline__ constexpr int gather_dy(int f, int n) {
+    return f < 2 ? (n < 4 ? 0 : (n < 6 ? 1 : -1))
+                 : ((n < 4 ? n - 2 : ((n & 1) ? 0 : -1)) + (f == 3 ? 1 : 0));
+}
+__device__ __forceinline__ constexpr int gather_slot(int dx, int dy) {
+    return (dx == 0 && dy == 0) ? 0 : (dy == 0 ? (dx == -1 ? 1 : dx == 1 ? 2 : dx == -2 ? 9 : 10)
+         : dx == 0 ? (dy == -1 ? 3 : dy == 1 ? 4 : dy == -2 ? 11 : 12)
+         : (dy == -1 ? (dx == -1 ? 5 : 6) : (dx == -1 ? 7 : 8)));
+}
+
+template <int NV, int ORDER, bool VISC>
+__global__ void __launch_bounds__(128) jac_gather_kernel(const JacParams prm) {
     constexpr bool SA = NV > 4;
-    constexpr int NL = 2;
+    constexpr int NS = ORDER == 2 ? 13 : 9;
     const View& v = prm.v; const Gas& g = prm.g; const Metrics& m = prm.m;
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     const int jl = blockIdx.y;
     if (i >= v.nic) return;
     const int r = jl + JOFF, c = i + IOFF;
     const int gj = v.j0 + jl;
-    const size_t o = v.at(r, c);
+    const size_t o = v.at(r, c), pl = v.plane;
     const double V = m.vol[o], Vi = 1.0/V;
+    const size_t fo[4] = {o, v.at(r, c + 1), o, v.at(r + 1, c)};
 
-    SlotAcc<NV> acc; acc.J = prm.J; acc.stride = v.plane; acc.cell = o; acc.touched = 0u;
-
-    // the cells of the 3x3 block + cross arms, loaded on demand per face (registers are the scarce resource)
-    auto cell = [&](int dx, int dy, CellD<NV>& w) { load_cell<NV, VISC>(v, g, prm.q, r + dy, c + dx, w); };
-
-    // ---- chi faces: left (face i, sign -) and right (face i+1, sign +)
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-        const int fi = i + side;                                   // global chi-face index
-        const int cf = fi + IOFF;
-        const int ox = side - 1;                                   // dx of the face's L cell relative to the row cell
-        CellD<NV> LL, L, R, RR, P0, P1, M0, M1;
-        cell(ox, 0, L); cell(ox + 1, 0, R);
-        const bool Lint = fi - 1 >= 0, Rint = fi <= v.nic - 1;
-        if (ORDER == 2) { if (Lint) cell(ox - 1, 0, LL); if (Rint) cell(ox + 2, 0, RR); }
-        FaceGeom fg;
-        fg.nx = m.ncx[v.at(r, cf)]; fg.ny = m.ncy[v.at(r, cf)];
-        if (VISC) {
-            cell(ox, 1, P0); cell(ox + 1, 1, P1); cell(ox, -1, M0); cell(ox + 1, -1, M1);
-            const int ca = imax(fi - 1, 0) + IOFF, cb = imin(fi, v.nic - 1) + IOFF;
-            const int cR = imin(fi + 1, v.ni - 1) + IOFF, cL = imax(fi - 1, 0) + IOFF;
-            fg.tx = m.nex[v.at(r + 1, ca)] + m.nex[v.at(r + 1, cb)]; fg.ty = m.ney[v.at(r + 1, ca)] + m.ney[v.at(r + 1, cb)];
-            fg.bx = m.nex[v.at(r, ca)] + m.nex[v.at(r, cb)]; fg.by = m.ney[v.at(r, ca)] + m.ney[v.at(r, cb)];
-            fg.rx = fg.nx + m.ncx[v.at(r, cR)]; fg.ry = fg.ny + m.ncy[v.at(r, cR)];
-            fg.lx = fg.nx + m.ncx[v.at(r, cL)]; fg.ly = fg.ny + m.ncy[v.at(r, cL)];
-            fg.ivol2 = 1.0/(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
-        }
-        const double scale = (side == 0 ? -1.0 : 1.0)*Vi;
-        face_jacobian<NV, ORDER, FLUX, VISC, NL>(g, fg, scale, prm.eps_chi, &LL, L, R, &RR, Lint, Rint, &P0, &P1, &M0, &M1,
-            slot_of(ox - 1, 0), slot_of(ox, 0), slot_of(ox + 1, 0), slot_of(ox + 2, 0),
-            slot_of(ox, 1), slot_of(ox + 1, 1), slot_of(ox, -1), slot_of(ox + 1, -1), acc);
-    }
-    // ---- eta faces: bottom (face gj, sign -) and top (face gj+1, sign +)
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-        const int fj = gj + side;                                  // global eta-face index
-        const int rf = fj - v.j0 + JOFF;
-        const int oy = side - 1;
-        CellD<NV> LL, L, R, RR, P0, P1, M0, M1;
-        cell(0, oy, L); cell(0, oy + 1, R);
-        const bool Lint = fj - 1 >= 0, Rint = fj <= v.njc - 1;
-        if (ORDER == 2) { if (Lint) cell(0, oy - 1, LL); if (Rint) cell(0, oy + 2, RR); }
-        FaceGeom fg;
-        fg.nx = m.nex[v.at(rf, c)]; fg.ny = m.ney[v.at(rf, c)];
-        if (VISC) {
-            // "plus" side = right vertex average (cells i+1), "minus" side = left (cells i-1); direct: D1 = top, D0 = bottom
-            cell(1, oy, P0); cell(1, oy + 1, P1); cell(-1, oy, M0); cell(-1, oy + 1, M1);
-            const int a = imax(fj - 1, 0), b = imin(fj, v.njc - 1);
-            const int rA = a - v.j0 + JOFF, rB = b - v.j0 + JOFF;
-            const int rT = imin(fj + 1, v.nj - 1) - v.j0 + JOFF, rBo = imax(fj - 1, 0) - v.j0 + JOFF;
-            // generic roles: t* = plus side (right), b* = minus side (left), r* = D1 (top), l* = D0 (bottom)
-            fg.rx = fg.nx + m.nex[v.at(rT, c)]; fg.ry = fg.ny + m.ney[v.at(rT, c)];
-            fg.lx = fg.nx + m.nex[v.at(rBo, c)]; fg.ly = fg.ny + m.ney[v.at(rBo, c)];
-            fg.bx = m.ncx[v.at(rA, c)] + m.ncx[v.at(rB, c)]; fg.by = m.ncy[v.at(rA, c)] + m.ncy[v.at(rB, c)];
-            fg.tx = m.ncx[v.at(rA, c + 1)] + m.ncx[v.at(rB, c + 1)]; fg.ty = m.ncy[v.at(rA, c + 1)] + m.ncy[v.at(rB, c + 1)];
-            fg.ivol2 = 1.0/(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
-        }
-        const double scale = (side == 0 ? -1.0 : 1.0)*Vi;
-        face_jacobian<NV, ORDER, FLUX, VISC, NL>(g, fg, scale, prm.eps_eta, &LL, L, R, &RR, Lint, Rint, &P0, &P1, &M0, &M1,
-            slot_of(0, oy - 1), slot_of(0, oy), slot_of(0, oy + 1), slot_of(0, oy + 2),
-            slot_of(1, oy), slot_of(1, oy + 1), slot_of(-1, oy), slot_of(-1, oy + 1), acc);
-    }
-
-    // ---- SA source: depends on the own cell and, through the cell-centred Green-Gauss gradients of the face
-    //      averages, on the 3x3 block
+    // SA source sensitivities (3x3 block, row 4 only)
+    double Wx[3][3], Wy[3][3], Sd[6] = {0, 0, 0, 0, 0, 0}, sgn = 1.0;
     if (SA) {
-        double Wx[3][3], Wy[3][3];
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -479,13 +478,14 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const JacParams prm) {
         const double cxr = m.ncx[v.at(r, c + 1)], cyr = m.ncy[v.at(r, c + 1)], cxl = m.ncx[o], cyl = m.ncy[o];
         const double ext = m.nex[v.at(r + 1, c)], eyt = m.ney[v.at(r + 1, c)], exb = m.nex[o], eyb = m.ney[o];
         auto addw = [&](int dx, int dy, double w, double nxx, double nyy) { Wx[dx + 1][dy + 1] += w*nxx*Vi; Wy[dx + 1][dy + 1] += w*nyy*Vi; };
-        // chi face i+1 (+), chi face i (-): bar = 3/8 (two direct cells) + 1/16 (four neighbours)
-        for (int s = 0; s < 2; s++) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {                              // chi faces i (-), i+1 (+): 3/8 direct cells, 1/16 neighbours
             const double sg_ = s ? 1.0 : -1.0, nxx = sg_*(s ? cxr : cxl), nyy = sg_*(s ? cyr : cyl);
             const int x0 = s ? 0 : -1;
             addw(x0, 0, 0.375, nxx, nyy); addw(x0 + 1, 0, 0.375, nxx, nyy);
             addw(x0, 1, 0.0625, nxx, nyy); addw(x0 + 1, 1, 0.0625, nxx, nyy); addw(x0, -1, 0.0625, nxx, nyy); addw(x0 + 1, -1, 0.0625, nxx, nyy);
         }
+#pragma unroll
         for (int s = 0; s < 2; s++) {
             const double sg_ = s ? 1.0 : -1.0, nxx = sg_*(s ? ext : exb), nyy = sg_*(s ? eyt : eyb);
             const int y0 = s ? 0 : -1;
@@ -493,44 +493,77 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const JacParams prm) {
             addw(1, y0, 0.0625, nxx, nyy); addw(1, y0 + 1, 0.0625, nxx, nyy); addw(-1, y0, 0.0625, nxx, nyy); addw(-1, y0 + 1, 0.0625, nxx, nyy);
         }
         double dvdx = 0, dudy = 0, dndx = 0, dndy = 0;
-#pragma unroll 1
+#pragma unroll
         for (int dy = -1; dy <= 1; dy++)
-#pragma unroll 1
+#pragma unroll
             for (int dx = -1; dx <= 1; dx++) {
-                CellD<NV> w; cell(dx, dy, w);
-                dvdx += Wx[dx + 1][dy + 1]*w.v; dudy += Wy[dx + 1][dy + 1]*w.u;
-                dndx += Wx[dx + 1][dy + 1]*w.nut; dndy += Wy[dx + 1][dy + 1]*w.nut;
+                const size_t oc = v.at(r + dy, c + dx);
+                const double ri = 1.0/prm.q[oc], uu = prm.q[pl + oc]*ri, vv = prm.q[2*pl + oc]*ri, nn = prm.q[4*pl + oc]*ri;
+                dvdx += Wx[dx + 1][dy + 1]*vv; dudy += Wy[dx + 1][dy + 1]*uu;
+                dndx += Wx[dx + 1][dy + 1]*nn; dndy += Wy[dx + 1][dy + 1]*nn;
             }
-        const double aa = dvdx - dudy, sgn = aa < 0.0 ? -1.0 : 1.0;
-        CellD<NV> w0; cell(0, 0, w0);
+        const double aa = dvdx - dudy;
+        sgn = aa < 0.0 ? -1.0 : 1.0;
+        CellD<NV> w0; load_cell<NV, VISC>(v, g, prm.q, r, c, w0);
         typedef Dual<6> D6;
         D6 a_rho(w0.r), a_nut(w0.nut), a_mu(w0.mu), a_om(fabs(aa)), a_nx(dndx), a_ny(dndy);
         a_rho.d[0] = 1; a_nut.d[1] = 1; a_mu.d[2] = 1; a_om.d[3] = 1; a_nx.d[4] = 1; a_ny.d[5] = 1;
         const D6 S = sa_source<D6>(a_rho, a_nut, a_mu, a_om, a_nx, a_ny, prm.wdist[o], prm.beta[o]);
-        // rhs[4] += S*V then /V  ->  d rhs4 = dS
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll 1
-            for (int dx = -1; dx <= 1; dx++) {
-                CellD<NV> w; cell(dx, dy, w);
-                double blk[NV*NV];
 #pragma unroll
-                for (int e = 0; e < NV*NV; e++) blk[e] = 0.0;
-                double out[NV];
-#pragma unroll
-                for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
-                const double wx = Wx[dx + 1][dy + 1], wy = Wy[dx + 1][dy + 1];
-                chain_Z<NV>(w, -S.d[3]*sgn*wy, S.d[3]*sgn*wx, 0.0, 0.0, 0.0, S.d[4]*wx + S.d[5]*wy, 0.0, out);
-                if (dx == 0 && dy == 0) {
-                    out[0] += S.d[0];
-                    chain_Z<NV>(w, 0.0, 0.0, 0.0, S.d[2], 0.0, S.d[1], 0.0, out);
-                }
-#pragma unroll
-                for (int c2 = 0; c2 < NV; c2++) blk[4*NV + c2] = out[c2];
-                acc.add(slot_of(dx, dy), blk);
-            }
+        for (int k = 0; k < 6; k++) Sd[k] = S.d[k];
     }
 
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (!VISC && s >= 5 && s <= 8) {                           // corners exist through the viscous stencil only
+            continue;
+        }
+        double blk[NV*NV];
+#pragma unroll
+        for (int e = 0; e < NV*NV; e++) blk[e] = 0.0;
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const double* S = (f < 2 ? prm.Schi : prm.Seta) + fo[f];
+            const double sc = (f & 1) ? Vi : -Vi;
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+                if (gather_slot(gather_dx(f, n), gather_dy(f, n)) != s) continue;
+                if (ORDER == 1 && (n == 0 || n == 3)) continue;
+                if (!VISC && n >= 4) continue;
+#pragma unroll
+                for (int e = 0; e < NV*NV; e++) blk[e] += sc*S[((size_t)n*NV*NV + e)*pl];
+            }
+        }
+        if (SA && s < 9) {                                         // rhs[4] += S*V then /V  ->  d rhs4 = dS
+            const int dx = (s == 1 || s == 5 || s == 7) ? -1 : ((s == 2 || s == 6 || s == 8) ? 1 : 0);
+            const int dy = (s == 3 || s == 5 || s == 6) ? -1 : ((s == 4 || s == 7 || s == 8) ? 1 : 0);
+            CellD<NV> w; load_cell<NV, VISC>(v, g, prm.q, r + dy, c + dx, w);
+            double out[NV];
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
+            const double wx = Wx[dx + 1][dy + 1], wy = Wy[dx + 1][dy + 1];
+            chain_Z<NV>(w, -Sd[3]*sgn*wy, Sd[3]*sgn*wx, 0.0, 0.0, 0.0, Sd[4]*wx + Sd[5]*wy, 0.0, out);
+            if (s == 0) {
+                out[0] += Sd[0];
+                chain_Z<NV>(w, 0.0, 0.0, 0.0, Sd[2], 0.0, Sd[1], 0.0, out);
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) blk[4*NV + c2] += out[c2];
+        }
+        double* p = prm.J + ((size_t)s*NV*NV)*pl + o;
+#pragma unroll
+        for (int e = 0; e < NV*NV; e++) p[e*pl] = blk[e];
+    }
+    if (!VISC) {                                                   // corner slots of an inviscid stencil hold zeros
+        for (int s = 5; s <= 8 && s < NS; s++) {
+            double* p = prm.J + ((size_t)s*NV*NV)*pl + o;
+            for (int e = 0; e < NV*NV; e++) p[e*pl] = 0.0;
+        }
+    }
+
+    struct { unsigned touched; double* J; size_t stride, cell;
+             __device__ void add(int slot, const double* blk) { double* p = J + ((size_t)slot*NV*NV)*stride + cell; for (int e = 0; e < NV*NV; e++) p[e*stride] += blk[e]; } } acc;
+    acc.touched = (1u << NS) - 1u; acc.J = prm.J; acc.stride = pl; acc.cell = o;
     // ---- fold ghost slots into the interior cells they are functions of (corners first, then arms, then edges)
     const int ip0 = i + 1, jp0 = gj + 1;                           // padded coordinates of the row cell
     const bool near_boundary = (i < 2) || (i > v.nic - 3) || (gj < 2) || (gj > v.njc - 3);
@@ -544,6 +577,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const JacParams prm) {
             if (s >= prm.nslots || !(acc.touched & (1u << s))) continue;
             int ip = ip0 + c_slot_dx[s], jp = jp0 + c_slot_dy[s];
             if (!gt.is_ghost(ip, jp)) continue;
+            if (ip < 0 || ip > gt.nic + 1 || jp < 0 || jp > gt.njc + 1) continue;   // beyond the ghost layer: never read
             gt.resolve(ip, jp);
             if (!gt.is_ghost(ip, jp)) continue;                    // copy-type ghost: keeps its slot, column remapped at export
             const GhostDesc& gd = gt.at(ip, jp);
@@ -601,14 +635,6 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const JacParams prm) {
                 acc.add(ts, blk);
             }
         }
-    }
-    // ---- untouched slots hold zeros
-#pragma unroll 1
-    for (int s = 0; s < prm.nslots; s++) {
-        if (acc.touched & (1u << s)) continue;
-        double* p = prm.J + ((size_t)s*NV*NV)*v.plane + o;
-#pragma unroll
-        for (int e = 0; e < NV*NV; e++) p[e*v.plane] = 0.0;
     }
 }
 

@@ -41,6 +41,7 @@ struct sgpu_ctx {
     double* halo_recv[2] = {nullptr, nullptr};
     double* halo_peer[2] = {nullptr, nullptr};
     JacStore jac{};
+    double* jac_scratch = nullptr; size_t jac_scratch_cap = 0;
     void* ghost_tab = nullptr;
     int* jac_err = nullptr;
     bool have_grid = false, have_dt = false;
@@ -167,6 +168,7 @@ int sgpu_destroy(sgpu_ctx* c) {
                       c->stage, c->halo_recv[0], c->halo_recv[1]})
         if (p) cudaFree(p);
     jac_free(c->jac);
+    if (c->jac_scratch) cudaFree(c->jac_scratch);
     if (c->ghost_tab) cudaFree(c->ghost_tab);
     if (c->jac_err) cudaFree(c->jac_err);
     for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
