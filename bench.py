@@ -187,7 +187,8 @@ def run_ours(args):
     nic, njc_total, njc_per = workload_dims(args, n_gpus)
     nv = 4 + args.ntrans
     case = build_case(nic, njc_total, args.ntrans)
-    j0, j1 = rank * njc_per, (rank + 1) * njc_per
+    from structured_b200.slab import partition_rows
+    j0, j1 = partition_rows(njc_total, world)[rank]
     eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0)
     # synthetic state, generated per rank for its rows only would need the global index: build rows lazily
     # each rank generates only its own rows (+2 ghost rows each side) of the synthetic state
@@ -198,25 +199,11 @@ def run_ours(args):
     cells_local = nic * njc_per
     cells_total = nic * njc_total
 
-    halo = None
-    if world > 1:
-        n = eq.halo_count()
-        halo = {s: (torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")) for s in (0, 1)}
+    from structured_b200.slab import HaloExchanger
+    halo = HaloExchanger(rank, world, eq.halo_count(), "cuda", dist) if world > 1 else None
 
     def exchange():
-        ops = []
-        for side, nb in ((0, rank - 1), (1, rank + 1)):
-            if 0 <= nb < world:
-                send, recv = halo[side]
-                eq.halo_pack(0, side, send.data_ptr())
-                ops.append(dist.P2POp(dist.isend, send, nb))
-                ops.append(dist.P2POp(dist.irecv, recv, nb))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for side, nb in ((0, rank - 1), (1, rank + 1)):
-            if 0 <= nb < world:
-                eq.halo_unpack(0, side, halo[side][1].data_ptr())
+        halo.exchange(lambda side, t: eq.halo_pack(0, side, t.data_ptr()), lambda side, t: eq.halo_unpack(0, side, t.data_ptr()))
 
     l2 = np.zeros(nv)
 
