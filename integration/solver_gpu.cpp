@@ -1,0 +1,127 @@
+// Drop-in replacement of the reference's src/solver/solver.cpp (same class `Solver<Tx,Tad>` declared in the
+// reference's own src/solver/solver.h): the explicit branch of Solver::step runs on the B200 through the C ABI of
+// include/structured_gpu.h.  main.cpp, Config, Mesh, IOManager, the .inp format and the grid loaders are the
+// reference's unmodified sources, compiled from /root/reference by integration/Makefile.
+//   reference lines replaced: calc_dt + residual + stage updates + norms   src/solver/solver.cpp:66,103-134
+#include "solver.h"
+#include "structured_gpu.h"
+#include <map>
+#include <cstdlib>
+
+template<class Tx> void set_rarray(size_t size, Tx* __restrict__ dest, Tx* __restrict__ src) { for (size_t i = 0; i < size; i++) dest[i] = src[i]; }
+template<class Tx> void update_forward_euler(size_t size, Tx* __restrict__ q, Tx* __restrict__ rhs, Tx* __restrict__ dt) { for (size_t i = 0; i < size; i++) q[i] = q[i] + rhs[i]*dt[i]; }
+template<class Tx, class To> void update_rk4(size_t size, Tx* __restrict__ q_i, Tx* __restrict__ q, Tx* __restrict__ rhs, Tx* __restrict__ dt, To order) { for (size_t i = 0; i < size; i++) q_i[i] = q[i] + rhs[i]*dt[i]/(4.0 - order); }
+
+static void gpu_check(int rc, sgpu_ctx* ctx, const char* what) {
+    if (rc == 0) return;
+    spdlog::get("console")->critical("{}: {}", what, sgpu_last_error(ctx));
+    std::abort();
+}
+
+// builds the context from what Mesh/Config/BoundaryContainer hold (src/model/bc.cpp:470-488, src/utils/config.cpp:32-87)
+template <class Tx, class Tad>
+static sgpu_ctx* make_ctx(std::shared_ptr<Mesh<Tx, Tad>> mesh, std::shared_ptr<Config<Tx>> cfg) {
+    static const std::map<std::string, int> T{{"freestream", 0}, {"slipwall", 1}, {"wall", 2}, {"isothermalwall", 3}, {"wake", 4}, {"outflow", 5}, {"periodic", 6}};
+    static const std::map<std::string, int> F{{"bottom", 0}, {"right", 1}, {"top", 2}, {"left", 3}};
+    std::vector<sgpu_bc> bcs;
+    auto toml = cpptoml::parse_file(cfg->filename);
+    for (const auto& b : *toml->get_table_array("boundary")) {
+        const std::string type = b->template get_qualified_as<std::string>("type").value_or("");
+        const std::string face = b->template get_qualified_as<std::string>("face").value_or("");
+        if (!T.count(type)) { spdlog::get("console")->info("Wrong type of BC."); continue; }
+        sgpu_bc e{};
+        e.type = T.at(type); e.face = F.at(face);
+        e.start = (int)b->template get_qualified_as<int64_t>("start").value_or(0);
+        e.end = (int)b->template get_qualified_as<int64_t>("end").value_or(0);
+        e.u = b->template get_qualified_as<double>("u").value_or(0.0);
+        e.v = b->template get_qualified_as<double>("v").value_or(0.0);
+        e.T = b->template get_qualified_as<double>("T").value_or(0.0);
+        bcs.push_back(e);
+    }
+    sgpu_desc d{};
+    d.ni = (int)mesh->ni; d.nj = (int)mesh->nj; d.ntrans = (int)mesh->solution->ntrans;
+    d.order = (int)cfg->solver->order; d.lhs_order = (int)cfg->solver->lhs_order;
+    d.flux = cfg->solver->flux == "roe" ? SGPU_FLUX_ROE : SGPU_FLUX_AUSM;
+    d.rho_inf = cfg->freestream->rho_inf; d.u_inf = cfg->freestream->u_inf; d.v_inf = cfg->freestream->v_inf;
+    d.p_inf = cfg->freestream->p_inf; d.T_inf = cfg->freestream->T_inf; d.mu_inf = cfg->freestream->mu_inf;
+    d.pr_inf = cfg->freestream->pr_inf; d.dpdx = cfg->solver->dpdx; d.dpdy = cfg->solver->dpdy;
+    d.n_bc = (int)bcs.size(); d.bc = bcs.data(); d.device = 0;
+    sgpu_ctx* ctx = nullptr;
+    if (sgpu_create(&d, &ctx)) { spdlog::get("console")->critical("sgpu_create: {}", sgpu_last_error(nullptr)); std::abort(); }
+    gpu_check(sgpu_set_grid(ctx, mesh->xv.data(), mesh->yv.data()), ctx, "sgpu_set_grid");
+    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q, mesh->solution->q.data()), ctx, "sgpu_set_state");
+    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q_TMP, mesh->solution->q_tmp.data()), ctx, "sgpu_set_state");
+    return ctx;
+}
+
+template<class Tx, class Tad>
+void Solver<Tx, Tad>::add_mesh(std::shared_ptr<Mesh<Tx,Tad>> mesh) { mesh_list.push_back(mesh); }
+
+template <class Tx, class Tad>
+Solver<Tx, Tad>::Solver(std::shared_ptr<Config<Tx>> val_config) {
+    config = val_config;
+    label = config->io->label;
+    logger_convergence = spdlog::basic_logger_mt("convergence", label + ".history", true);
+    logger_convergence->info(" ");
+    logger = spdlog::get("console");
+    CFL = config->solver->cfl;
+    UNDER_RELAXATION = config->solver->under_relaxation;
+}
+template <class Tx, class Tad> Solver<Tx, Tad>::~Solver() {}
+
+template <class Tx, class Tad>
+bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, Tx t) {
+    static sgpu_ctx* ctx = make_ctx<Tx, Tad>(mesh, config);        // one context per Mesh (main adds exactly one, src/main.cpp:40)
+    auto solution = mesh->solution;
+    const size_t nv = solution->nq + solution->ntrans;
+    double l2sq[8] = {0}, l2norm[8] = {0};
+    config->profiler->reset_time_residual();
+    int scheme = -1;
+    if (config->solver->scheme == "forward_euler") scheme = 0;
+    else if (config->solver->scheme == "rk4_jameson") scheme = 1;
+    else logger->critical("scheme not defined.");
+    if (scheme >= 0) gpu_check(sgpu_explicit_step(ctx, scheme, CFL, l2sq), ctx, "sgpu_explicit_step");
+    config->profiler->update_time_residual();
+    for (size_t k = 0; k < nv; k++) l2norm[k] = sqrt(l2sq[k]);
+    auto sync_host = [&]() { gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state"); };
+    if (counter > config->solver->iteration_max) {
+        logger->info("Max iteration reached!");
+        sync_host();
+        mesh->iomanager->write(counter);
+        auto dt_main = config->profiler->current_time();
+        logger->info("Final:: Step: {:08d} Time: {:.2e} Wall Time: {:.2e} CFL: {:.2e} Density Norm: {:.2e}", counter, t, dt_main, CFL, l2norm[0]);
+        logger_convergence->info("{:08d} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e}", counter, t, dt_main, CFL, l2norm[0], l2norm[1], l2norm[2], l2norm[3]);
+        return true;
+    }
+    if (counter % config->io->stdout_frequency == 0) {
+        auto dt_main = config->profiler->current_time();
+        logger->info("Step: {:08d} Time: {:.2e} Wall Time: {:.2e} CFL: {:.2e} Density Norm: {:.2e}", counter, t, dt_main, CFL, l2norm[0]);
+        logger_convergence->info("{:08d} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e} {:.2e}", counter, t, dt_main, CFL, l2norm[0], l2norm[1], l2norm[2], l2norm[3]);
+    }
+    if (counter % config->io->fileout_frequency == 0) { sync_host(); mesh->iomanager->write(counter); }
+    return false;
+}
+
+template <class Tx, class Tad>
+void Solver<Tx, Tad>::solve() {
+    size_t counter = 0;
+    Tx t = 0.0;
+    logger->info("Welcome to structured! (residual path on the GPU)");
+    config->profiler->timer_main->reset();
+    while (1) {
+        bool if_break = true;
+        for (auto&& mesh : mesh_list) if_break = step(mesh, counter, t) && if_break;
+        if (if_break) break;
+        counter += 1;
+        if (config->solver->cfl_ramp && counter > config->solver->cfl_ramp_iteration) {
+            CFL = pow(CFL, config->solver->cfl_ramp_exponent);
+            CFL = std::min(CFL, static_cast<Tx>(1e12));
+        }
+        if (config->solver->under_relaxation_ramp && counter > config->solver->under_relaxation_ramp_iteration) {
+            UNDER_RELAXATION = pow(UNDER_RELAXATION, config->solver->under_relaxation_ramp_exponent);
+            UNDER_RELAXATION = std::min(UNDER_RELAXATION, static_cast<Tx>(10.0));
+        }
+    }
+}
+
+template class Solver<double, double>;

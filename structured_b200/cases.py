@@ -140,6 +140,13 @@ def write_grid_p3d(filename: str, xv: np.ndarray, yv: np.ndarray) -> None:
             np.savetxt(f, a.T.reshape(-1), fmt="%.17e")
 
 
+def write_grid_simple(filename: str, xv: np.ndarray, yv: np.ndarray) -> None:
+    """the reference's "simple" format: `x y` per line, j outer / i inner (src/utils/mesh.cpp:134-143)"""
+    ni, nj = xv.shape
+    with open(filename, "w") as f:
+        np.savetxt(f, np.stack([xv.T.reshape(-1), yv.T.reshape(-1)], axis=1), fmt="%.17e")
+
+
 def case_from_toml(text: str, xv: Optional[np.ndarray] = None, yv: Optional[np.ndarray] = None, base_dir: str = ".") -> Case:
     """Parse reference `.inp` TOML text like Config / BoundaryContainer do; the grid is read from
     geometry.filename unless vertex arrays are passed."""
