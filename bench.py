@@ -107,9 +107,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_case(nic, njc_total, ntrans):
+def build_case(nic, njc_total, ntrans, cell_rows=None):
     from structured_b200.cases import turbulent_channel_case
-    return turbulent_channel_case(nic, njc_total, ntrans=ntrans, order=2, flux="roe", mach=0.2, reynolds=5e6, periodic=True)
+    return turbulent_channel_case(nic, njc_total, ntrans=ntrans, order=2, flux="roe", mach=0.2, reynolds=5e6, periodic=True,
+                                  cell_rows=cell_rows)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -186,11 +187,12 @@ def run_ours(args):
     n_gpus = world
     nic, njc_total, njc_per = workload_dims(args, n_gpus)
     nv = 4 + args.ntrans
-    case = build_case(nic, njc_total, args.ntrans)
     from structured_b200.slab import partition_rows
     j0, j1 = partition_rows(njc_total, world)[rank]
-    eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0)
-    # synthetic state, generated per rank for its rows only would need the global index: build rows lazily
+    # each rank generates only the grid rows its slab needs (own rows + 2 ghost rows per interior side)
+    win = (max(j0 - 2, 0), min(j1 + 2, njc_total)) if world > 1 else None
+    case = build_case(nic, njc_total, args.ntrans, cell_rows=win)
+    eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0, window=case.window)
     # each rank generates only its own rows (+2 ghost rows each side) of the synthetic state
     jw0, jw1 = (max(j0 - 2, 0), min(j1 + 2, njc_total)) if world > 1 else (0, njc_total)
     q = case.perturbed_q(j_first=jw0, j_count=jw1 - jw0)

@@ -89,6 +89,11 @@ int sgpu_dims(const sgpu_ctx* ctx, int* nic, int* njc, int* nv, int* j_begin, in
 /* replaces Mesh::simple_loader / plot3d_loader output + Mesh::calc_metrics (src/utils/mesh.cpp:134-279):
  * GLOBAL vertex arrays [ni][nj]; the metrics are evaluated on the device from these. */
 int sgpu_set_grid(sgpu_ctx* ctx, const double* xv, const double* yv);
+/* Window forms for slab runs: the host arrays hold only vertex rows [jv_first, jv_first + jv_count) (shape
+ * [ni][jv_count]) resp. cell rows [j_first, j_first + j_count) (shape [nic][j_count]); the window must cover the
+ * slab's rows plus its two ghost rows on each interior side. */
+int sgpu_set_grid_window(sgpu_ctx* ctx, const double* xv, const double* yv, int jv_first, int jv_count);
+int sgpu_set_field_window(sgpu_ctx* ctx, const char* name, const double* field, int j_first, int j_count);
 /* SA extension inputs, GLOBAL [nic][njc]: name = "wall_distance" | "beta" (no reference counterpart) */
 int sgpu_set_field(sgpu_ctx* ctx, const char* name, const double* field);
 /* metrics as Mesh::calc_metrics leaves them, for parity checks: normal_chi [ni][njc][2],

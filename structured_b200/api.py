@@ -21,7 +21,7 @@ _U = ctypes.POINTER(ctypes.c_uint)
 
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
-    "sgpu_set_grid", "sgpu_set_field", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
+    "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_set_peer",
@@ -96,7 +96,8 @@ def make_desc(case: Case, device: int = 0, j_begin: int = 0, j_end: int = 0):
 class GpuEulerEquation:
     """EulerEquation + the explicit/implicit pieces of Solver::step on one B200 (or one j-slab of a grid)."""
 
-    def __init__(self, case: Case, device: int = 0, j_begin: int = 0, j_end: int = 0, stream: Optional[int] = None):
+    def __init__(self, case: Case, device: int = 0, j_begin: int = 0, j_end: int = 0, stream: Optional[int] = None,
+                 window: Optional[tuple] = None):
         self.L = load_library()
         self.case = case
         d, self._keep = make_desc(case, device, j_begin, j_end)
@@ -109,13 +110,24 @@ class GpuEulerEquation:
         self.j_begin, self.j_end = (j_begin, j_end) if (j_begin or j_end) else (0, case.njc)
         if stream is not None:
             self._ck(self.L.sgpu_set_stream(self.h, ctypes.c_void_p(stream)))
-        self._ck(self.L.sgpu_set_grid(self.h, _dp(np.ascontiguousarray(case.xv, dtype=np.float64)),
-                                      _dp(np.ascontiguousarray(case.yv, dtype=np.float64))))
-        if case.ntrans:
-            if case.wall_distance is not None:
-                self.set_field("wall_distance", case.wall_distance)
-            if case.beta is not None:
-                self.set_field("beta", case.beta)
+        if window is None:
+            self._ck(self.L.sgpu_set_grid(self.h, _dp(np.ascontiguousarray(case.xv, dtype=np.float64)),
+                                          _dp(np.ascontiguousarray(case.yv, dtype=np.float64))))
+            if case.ntrans:
+                if case.wall_distance is not None:
+                    self.set_field("wall_distance", case.wall_distance)
+                if case.beta is not None:
+                    self.set_field("beta", case.beta)
+        else:
+            # slab runs: case.xv / yv hold only vertex rows [jv_first, ...), the fields only cell rows [jc_first, ...)
+            jv_first, jc_first = window
+            xv = np.ascontiguousarray(case.xv, dtype=np.float64); yv = np.ascontiguousarray(case.yv, dtype=np.float64)
+            self._ck(self.L.sgpu_set_grid_window(self.h, _dp(xv), _dp(yv), jv_first, xv.shape[1]))
+            if case.ntrans:
+                for name, f in (("wall_distance", case.wall_distance), ("beta", case.beta)):
+                    if f is not None:
+                        f = np.ascontiguousarray(f, dtype=np.float64)
+                        self._ck(self.L.sgpu_set_field_window(self.h, name.encode(), _dp(f), jc_first, f.shape[1]))
 
     # ---- plumbing
     def _ck(self, rc: int):

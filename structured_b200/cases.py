@@ -68,6 +68,7 @@ class Case:
     wall_distance: Optional[np.ndarray] = None  # [nic][njc]
     beta: Optional[np.ndarray] = None
     label: str = "case"
+    window: Optional[tuple] = None  # (first vertex row, first cell row) when xv/yv/fields hold only a row window
 
     @property
     def nic(self) -> int:
@@ -218,11 +219,13 @@ def write_case(case: Case, directory: str, name: str = "case") -> str:
 # synthetic grids
 # ------------------------------------------------------------------------------------------------
 def bump_channel_grid(nic: int, njc: int, L: float = 1.0, H: float = 0.25, s: float = 2.5, bump: float = 0.05,
-                      skew: float = 0.0):
+                      skew: float = 0.0, j_first: int = 0, j_count: Optional[int] = None):
     """x_i = L i/nic ; y_j = H [1 + tanh(s(2j/njc - 1))/tanh(s)]/2 with a Gaussian bump on the lower wall.
-    `skew` shears the interior grid lines so that chi normals are not axis aligned either."""
+    `skew` shears the interior grid lines so that chi normals are not axis aligned either.
+    j_first / j_count select a window of vertex rows (slab runs generate only their own rows)."""
+    j_count = njc + 1 - j_first if j_count is None else j_count
     i = np.arange(nic + 1, dtype=np.float64)[:, None]
-    j = np.arange(njc + 1, dtype=np.float64)[None, :]
+    j = (j_first + np.arange(j_count, dtype=np.float64))[None, :]
     x = L * i / nic + 0.0 * j
     y = H * (1.0 + np.tanh(s * (2.0 * j / njc - 1.0)) / math.tanh(s)) / 2.0 + 0.0 * i
     y = y + bump * H * (1.0 - y / H) * np.exp(-(((x - L / 2.0) / (0.1 * L)) ** 2))
@@ -231,29 +234,41 @@ def bump_channel_grid(nic: int, njc: int, L: float = 1.0, H: float = 0.25, s: fl
     return np.ascontiguousarray(x), np.ascontiguousarray(y)
 
 
-def channel_wall_distance(case: Case) -> np.ndarray:
-    """Distance of each cell centre to the nearer of the bottom (j=0) / top (j=nj-1) grid lines."""
-    xc = 0.25 * (case.xv[:-1, :-1] + case.xv[1:, :-1] + case.xv[:-1, 1:] + case.xv[1:, 1:])
-    yc = 0.25 * (case.yv[:-1, :-1] + case.yv[1:, :-1] + case.yv[:-1, 1:] + case.yv[1:, 1:])
-    xb = 0.5 * (case.xv[:-1, 0] + case.xv[1:, 0])[:, None]
-    yb = 0.5 * (case.yv[:-1, 0] + case.yv[1:, 0])[:, None]
-    xt = 0.5 * (case.xv[:-1, -1] + case.xv[1:, -1])[:, None]
-    yt = 0.5 * (case.yv[:-1, -1] + case.yv[1:, -1])[:, None]
+def _cell_centres(xv, yv):
+    xc = 0.25 * (xv[:-1, :-1] + xv[1:, :-1] + xv[:-1, 1:] + xv[1:, 1:])
+    yc = 0.25 * (yv[:-1, :-1] + yv[1:, :-1] + yv[:-1, 1:] + yv[1:, 1:])
+    return xc, yc
+
+
+def channel_wall_distance(case: "Case", bottom=None, top=None) -> np.ndarray:
+    """Distance of each cell centre to the nearer of the bottom (j=0) / top (j=nj-1) grid lines.
+    bottom / top = (x, y) vertex rows of the walls when case.xv only holds a window of rows."""
+    xc, yc = _cell_centres(case.xv, case.yv)
+    bx, by = (case.xv[:, 0], case.yv[:, 0]) if bottom is None else bottom
+    tx, ty = (case.xv[:, -1], case.yv[:, -1]) if top is None else top
+    xb = 0.5 * (bx[:-1] + bx[1:])[:, None]; yb = 0.5 * (by[:-1] + by[1:])[:, None]
+    xt = 0.5 * (tx[:-1] + tx[1:])[:, None]; yt = 0.5 * (ty[:-1] + ty[1:])[:, None]
     d = np.minimum(np.hypot(xc - xb, yc - yb), np.hypot(xc - xt, yc - yt))
     return np.ascontiguousarray(d)
 
 
-def synthetic_beta(case: Case, L: float = 1.0, H: float = 0.25) -> np.ndarray:
-    xc = 0.25 * (case.xv[:-1, :-1] + case.xv[1:, :-1] + case.xv[:-1, 1:] + case.xv[1:, 1:])
-    yc = 0.25 * (case.yv[:-1, :-1] + case.yv[1:, :-1] + case.yv[:-1, 1:] + case.yv[1:, 1:])
+def synthetic_beta(case: "Case", L: float = 1.0, H: float = 0.25) -> np.ndarray:
+    xc, yc = _cell_centres(case.xv, case.yv)
     return np.ascontiguousarray(1.0 + 0.1 * np.sin(2.0 * np.pi * xc / L) * np.cos(np.pi * yc / H))
 
 
 def turbulent_channel_case(nic: int, njc: int, ntrans: int = 1, order: int = 2, lhs_order: Optional[int] = None,
-                           flux: str = "roe", mach: float = 0.2, reynolds: float = 5e6, periodic: bool = True) -> Case:
+                           flux: str = "roe", mach: float = 0.2, reynolds: float = 5e6, periodic: bool = True,
+                           cell_rows: Optional[tuple] = None) -> Case:
     """The C2/C3/C5 synthetic workload: bump channel, isothermal bottom wall, adiabatic top wall,
-    periodic (or freestream/outflow) in i, M = 0.2, Re_L = 5e6, MUSCL + Roe + viscous (+ SA)."""
-    xv, yv = bump_channel_grid(nic, njc)
+    periodic (or freestream/outflow) in i, M = 0.2, Re_L = 5e6, MUSCL + Roe + viscous (+ SA).
+    cell_rows = (ja, jb): generate only the window of cell rows [ja, jb) (vertex rows [ja, jb]) of the GLOBAL
+    nic x njc grid -- what one rank of a slab run needs; the case then carries `window = (ja, ja)`."""
+    if cell_rows is None:
+        xv, yv = bump_channel_grid(nic, njc)
+    else:
+        ja, jb = cell_rows
+        xv, yv = bump_channel_grid(nic, njc, j_first=ja, j_count=jb - ja + 1)
     c = Case(ni=nic + 1, nj=njc + 1, xv=xv, yv=yv)
     c.rho_inf, c.u_inf, c.v_inf, c.p_inf, c.T_inf = 1.0, mach, 0.0, 1.0 / 1.4, 1.0 / 1.4
     c.mu_inf = c.rho_inf * c.u_inf * 1.0 / reynolds
@@ -268,8 +283,14 @@ def turbulent_channel_case(nic: int, njc: int, ntrans: int = 1, order: int = 2, 
     else:
         c.boundaries += [Boundary("freestream", "left", 0, -1), Boundary("outflow", "right", 0, -1)]
     if ntrans:
-        c.wall_distance = channel_wall_distance(c)
+        if cell_rows is None:
+            c.wall_distance = channel_wall_distance(c)
+        else:
+            bx, by = bump_channel_grid(nic, njc, j_first=0, j_count=1)
+            tx, ty = bump_channel_grid(nic, njc, j_first=njc, j_count=1)
+            c.wall_distance = channel_wall_distance(c, (bx[:, 0], by[:, 0]), (tx[:, 0], ty[:, 0]))
         c.beta = synthetic_beta(c)
+    c.window = None if cell_rows is None else (cell_rows[0], cell_rows[0])
     c.label = "channel_%dx%d" % (nic, njc)
     return c
 

@@ -41,7 +41,7 @@ struct sgpu_ctx {
     double* halo_recv[2] = {nullptr, nullptr};
     double* halo_peer[2] = {nullptr, nullptr};
     JacStore jac{};
-    double* jac_scratch = nullptr; size_t jac_scratch_cap = 0;
+    double* jac_scratch = nullptr; size_t jac_scratch_cap = 0; bool jac_two_stage = false;
     void* ghost_tab = nullptr;
     int* jac_err = nullptr;
     bool have_grid = false, have_dt = false;
@@ -186,17 +186,18 @@ int sgpu_dims(const sgpu_ctx* c, int* nic, int* njc, int* nv, int* j_begin, int*
 long long sgpu_launch_count(const sgpu_ctx* c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- grid
-int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
+int sgpu_set_grid_window(sgpu_ctx* c, const double* xv, const double* yv, int jv_first, int jv_count) {
     if (!c || !xv || !yv) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
     const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.nj - 1);       // vertex rows [ja, jb]
+    if (jv_first > ja || jv_first + jv_count < jb + 1) FAIL(c, SGPU_ERR_ARG, "vertex window [%d,%d) does not cover rows [%d,%d]", jv_first, jv_first + jv_count, ja, jb);
     const int nrows = jb - ja + 1, r0 = ja - v.j0 + JOFF;
     if (int rc = ensure_stage(c, (size_t)v.ni*nrows)) return rc;
     const dim3 blk(32, 8), grd((nrows + 31)/32, (v.ni + 31)/32);
     const double* src[2] = {xv, yv}; double* dst[2] = {c->xv, c->yv};
     for (int n = 0; n < 2; n++) {
-        CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*nrows, src[n] + ja, sizeof(double)*v.nj, sizeof(double)*nrows, v.ni,
+        CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*nrows, src[n] + (ja - jv_first), sizeof(double)*jv_count, sizeof(double)*nrows, v.ni,
                                 cudaMemcpyHostToDevice, c->stream));
         vertex_to_plane_kernel<<<grd, blk, 0, c->stream>>>(v, c->stage, dst[n], r0, nrows);
         CKL(c); c->launches++;
@@ -209,20 +210,29 @@ int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
     c->have_grid = true;
     return SGPU_OK;
 }
+int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
+    if (!c) return SGPU_ERR_ARG;
+    return sgpu_set_grid_window(c, xv, yv, 0, c->v.nj);
+}
 
-int sgpu_set_field(sgpu_ctx* c, const char* name, const double* f) {
+int sgpu_set_field_window(sgpu_ctx* c, const char* name, const double* f, int j_first, int j_count) {
     if (!c || !name || !f) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     double* dst = !strcmp(name, "wall_distance") ? c->wdist : (!strcmp(name, "beta") ? c->beta : nullptr);
     if (!dst) FAIL(c, SGPU_ERR_ARG, "unknown field '%s' (wall_distance | beta)", name);
     const View& v = c->v;
+    if (j_first > v.j0 || j_first + j_count < v.j1) FAIL(c, SGPU_ERR_ARG, "field window [%d,%d) does not cover the owned rows [%d,%d)", j_first, j_first + j_count, v.j0, v.j1);
     if (int rc = ensure_stage(c, (size_t)v.nic*v.njl)) return rc;
-    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*v.njl, f + v.j0, sizeof(double)*v.njc, sizeof(double)*v.njl, v.nic,
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*v.njl, f + (v.j0 - j_first), sizeof(double)*j_count, sizeof(double)*v.njl, v.nic,
                             cudaMemcpyHostToDevice, c->stream));
     field_to_plane_kernel<<<dim3((v.njl + 31)/32, (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, dst, JOFF, v.njl);
     CKL(c); c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
     return SGPU_OK;
+}
+int sgpu_set_field(sgpu_ctx* c, const char* name, const double* f) {
+    if (!c) return SGPU_ERR_ARG;
+    return sgpu_set_field_window(c, name, f, 0, c->v.njc);
 }
 
 // download a cell plane group to a GLOBAL host AoS array (owned rows only); window = host holds owned rows only

@@ -150,3 +150,22 @@ def test_two_slabs_equal_one_slab_bit_for_bit(ntrans, split):
     assert np.array_equal(got2, want2)
     for s in (one, lo, hi):
         s.close()
+
+
+def test_windowed_slab_inputs_equal_global_inputs():
+    """a rank that only generates / uploads its own rows of grid, fields and state gets the same residual rows"""
+    nic, njc, split = 96, 48, 20
+    full = turbulent_channel_case(nic, njc, ntrans=1, reynolds=1e5)
+    one = gpu_eq(full)
+    want = one.calc_residual(full.perturbed_q())
+    for (j0, j1) in ((0, split), (split, njc)):
+        ja, jb = max(j0 - 2, 0), min(j1 + 2, njc)
+        part = turbulent_channel_case(nic, njc, ntrans=1, reynolds=1e5, cell_rows=(ja, jb))
+        eq = gpu_eq(part, j_begin=j0, j_end=j1, window=part.window)
+        eq.set_state_window(part.perturbed_q(j_first=ja, j_count=jb - ja), ja)
+        eq.residual_device(0)
+        got = np.zeros((nic, j1 - j0, 5))
+        eq.get_rhs_window(got)
+        assert np.array_equal(got, want[:, j0:j1, :])
+        eq.close()
+    one.close()
