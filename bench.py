@@ -263,13 +263,11 @@ def run_ours(args):
         k_e2e = max(2, min(args.steps, 5))
 
         def e2e_step():
-            # host q window -> device, residual, owned rhs rows -> host (what sgpu_residual_host does on a whole grid)
-            eq.set_state_window(qn, jw0, 0)
-            eq.residual_device(0)
+            # host q (pinned) -> device, residual, owned rhs rows -> host: the call-site form of calc_residual
             if world > 1:
-                eq.get_rhs_window(rn)
+                eq.calc_residual_window(qn, jw0, rn)
             else:
-                eq.get_rhs(out=rn)
+                eq.calc_residual(qn, out=rn)
 
         e2e_step()
         barrier()

@@ -125,6 +125,9 @@ int sgpu_residual(sgpu_ctx* ctx, int which, int lhs, double* l2sq);
 /* Same through HOST buffers: q -> device, residual, rhs -> host.  This is the call-site form of
  * `equation->calc_residual(solution->q, solution->rhs)` (src/solver/solver.cpp:104). */
 int sgpu_residual_host(sgpu_ctx* ctx, const double* q, double* rhs, int lhs);
+/* slab form: q holds rows [j_first, j_first + j_count) (owned rows + ghost rows), rhs_owned is [nic][j_end-j_begin][nv].
+ * Both host forms are software pipelined over row chunks (H2D || kernel || D2H on three streams). */
+int sgpu_residual_host_window(sgpu_ctx* ctx, const double* q, int j_first, int j_count, double* rhs_owned, int lhs);
 /* update_rk4: q_tmp = q + rhs*dt/(4-order)   (src/solver/solver.cpp:20-26,111) */
 int sgpu_rk_stage(sgpu_ctx* ctx, int order);
 /* update_forward_euler: q = q + rhs*dt       (src/solver/solver.cpp:12-18,105) */

@@ -22,7 +22,7 @@ _U = ctypes.POINTER(ctypes.c_uint)
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
-    "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_rk_stage",
+    "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_set_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
@@ -224,6 +224,12 @@ class GpuEulerEquation:
         q = np.ascontiguousarray(q, dtype=np.float64)
         out = self._state_array() if out is None else out
         self._ck(self.L.sgpu_residual_host(self.h, _dp(q), _dp(out), int(lhs)))
+        return out
+
+    def calc_residual_window(self, q: np.ndarray, j_first: int, out: np.ndarray, lhs: bool = False) -> np.ndarray:
+        """slab form of calc_residual: q holds rows [j_first, j_first + q.shape[1]), out the owned rows only"""
+        assert q.flags.c_contiguous and out.flags.c_contiguous and out.shape == (self.nic, self.j_end - self.j_begin, self.nv)
+        self._ck(self.L.sgpu_residual_host_window(self.h, _dp(q), j_first, q.shape[1], _dp(out), int(lhs)))
         return out
 
     def rk_stage(self, order: int):

@@ -31,6 +31,7 @@ struct ResParams {
     double* partial;                    // [items][nv] sums of rhs^2, or nullptr
     double eps_chi, eps_eta, dpdx, dpdy;
     int nstrips, nchunks, rpc;
+    int row0, row1;                     // local cell rows [row0, row1) this launch covers (whole slab: 0, njl)
 };
 
 // vertex-average / dual-cell variable set
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
     const int t = threadIdx.x;
     const int strip = blockIdx.x % prm.nstrips, chunk = blockIdx.x / prm.nstrips;
     const int i0 = strip*RCELLS;
-    const int ra = chunk*prm.rpc, rb = imin(ra + prm.rpc, v.njl);
+    const int ra = prm.row0 + chunk*prm.rpc, rb = imin(ra + prm.rpc, prm.row1);
     const int i = i0 - 2 + t;                            // global index of own cell column / own chi face
     const bool face_ok = t >= 2 && t <= RW - 2 && i <= v.nic;
     const bool cell_ok = t >= 2 && t <= RW - 3 && i < v.nic;

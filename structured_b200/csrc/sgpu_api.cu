@@ -41,6 +41,11 @@ struct sgpu_ctx {
     double* halo_recv[2] = {nullptr, nullptr};
     double* halo_peer[2] = {nullptr, nullptr};
     JacStore jac{};
+    // pipelined host path
+    bool pipe_init = false;
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_up[16] = {}, pipe_cmp[16] = {}, pipe_start = nullptr;
+    double* pipe_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pipe_stage_cap = 0;
     double* jac_scratch = nullptr; size_t jac_scratch_cap = 0; bool jac_two_stage = false;
     void* ghost_tab = nullptr;
     int* jac_err = nullptr;
@@ -169,6 +174,12 @@ int sgpu_destroy(sgpu_ctx* c) {
         if (p) cudaFree(p);
     jac_free(c->jac);
     if (c->jac_scratch) cudaFree(c->jac_scratch);
+    for (int k = 0; k < 4; k++) if (c->pipe_stage[k]) cudaFree(c->pipe_stage[k]);
+    if (c->pipe_init) {
+        for (int k = 0; k < 3; k++) cudaStreamDestroy(c->pipe_stream[k]);
+        for (int k = 0; k < 16; k++) { cudaEventDestroy(c->pipe_up[k]); cudaEventDestroy(c->pipe_cmp[k]); }
+        cudaEventDestroy(c->pipe_start);
+    }
     if (c->ghost_tab) cudaFree(c->ghost_tab);
     if (c->jac_err) cudaFree(c->jac_err);
     for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -320,18 +331,20 @@ int sgpu_copy_state(sgpu_ctx* c, int dst, int src) {
 
 } // extern "C"
 // ---------------------------------------------------------------------------------------------- hot path
-static int apply_bcs(sgpu_ctx* c, int which) {
+// Applies the [[boundary]] tables in file order.  [jlo, jhi] (padded row indices, inclusive) restricts the work to
+// the ghost cells a row range needs (pipelined host path); the default covers everything this slab holds.
+static int apply_bcs(sgpu_ctx* c, int which, int jlo = -(1 << 30), int jhi = (1 << 30)) {
     const View& v = c->v;
     Metrics m = metrics_of(c);
     for (const sgpu_bc& b : c->bcs) {
         BcArgs a; a.type = b.type; a.face = b.face; a.u = b.u; a.v = b.v; a.T = b.T;
         const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
         if (horiz) {
-            if (b.face == SGPU_FACE_BOTTOM && v.j0 != 0) continue;
-            if (b.face == SGPU_FACE_TOP && v.j1 != v.njc) continue;
+            if (b.face == SGPU_FACE_BOTTOM && (v.j0 != 0 || jlo > 0)) continue;
+            if (b.face == SGPU_FACE_TOP && (v.j1 != v.njc || jhi < v.njc + 1)) continue;
             a.lo = b.start; a.hi = b.end;
         } else {                                                   // rows this slab holds: padded j in [j0, j1+1]
-            a.lo = std::max(b.start, v.j0); a.hi = std::min(b.end, v.j1 + 1);
+            a.lo = std::max(std::max(b.start, v.j0), jlo); a.hi = std::min(std::min(b.end, v.j1 + 1), jhi);
         }
         if (a.hi < a.lo) continue;
         const int n = a.hi - a.lo + 1;
@@ -345,20 +358,21 @@ static int apply_bcs(sgpu_ctx* c, int which) {
 // integer number of full waves of (SM count x resident CTAs per SM) -- a partial last wave would idle most
 // SMs for a whole chunk -- while chunks stay tall enough to amortise the 4-row prologue.
 static void shape_grid(const View& v, int ctas_per_sm, int sms, ResParams& p) {
+    const int nrows = p.row1 - p.row0;
     p.nstrips = (v.nic + RCELLS - 1)/RCELLS;
     const int wave = std::max(1, ctas_per_sm*sms);
     int best = 1; double best_cost = 1e300;
-    const int max_chunks = std::max(1, v.njl/8);
+    const int max_chunks = std::max(1, nrows/8);
     for (int nch = 1; nch <= max_chunks; nch++) {
-        const int rpc = (v.njl + nch - 1)/nch;
-        const int nchunks = (v.njl + rpc - 1)/rpc;
+        const int rpc = (nrows + nch - 1)/nch;
+        const int nchunks = (nrows + rpc - 1)/rpc;
         const long long ctas = (long long)p.nstrips*nchunks;
         const long long waves = (ctas + wave - 1)/wave;
         const double cost = (double)waves*(rpc + 5.0);          // time ~ waves x (rows + prologue) per CTA
         if (cost < best_cost - 1e-9) { best_cost = cost; best = nchunks; }
     }
-    p.rpc = (v.njl + best - 1)/best;
-    p.nchunks = (v.njl + p.rpc - 1)/p.rpc;
+    p.rpc = (nrows + best - 1)/best;
+    p.nchunks = (nrows + p.rpc - 1)/p.rpc;
 }
 
 template <int NV, int ORDER, int FLUX, bool VISC>
@@ -397,9 +411,10 @@ static int launch_residual_t(sgpu_ctx* c, ResParams& p, int* grid_out) {
     return SGPU_OK;
 }
 
-static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms) {
+static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms, int row0 = 0, int row1 = -1) {
     const View& v = c->v;
     ResParams p;
+    p.row0 = row0; p.row1 = row1 < 0 ? v.njl : row1;
     p.v = v; p.g = c->g; p.m = metrics_of(c);
     p.q = c->q[which]; p.rhs = c->rhs; p.wdist = c->wdist; p.beta = c->beta;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.dpdx = c->d.dpdx; p.dpdy = c->d.dpdy;
@@ -443,11 +458,91 @@ int sgpu_residual(sgpu_ctx* c, int which, int lhs, double* l2sq) {
     return SGPU_OK;
 }
 
+} // extern "C"
+
+// Host-buffer form of calc_residual, software pipelined over j-chunks on three streams so that the PCIe link runs
+// full duplex: H2D + AoS->SoA of chunk c+1  ||  boundary conditions + residual of chunk c  ||  SoA->AoS + D2H of
+// chunk c-1.  q holds rows [qj0, qj0+qjn) with qjn*nv doubles per i-row; rhs holds rows [rj0, rj0+rjn).
+static int residual_host_pipelined(sgpu_ctx* c, const double* q, int qj0, int qjn, double* rhs, int rj0, int rjn, int lhs) {
+    const View& v = c->v;
+    const int ulo = std::max(std::max(v.j0 - 2, 0), qj0), uhi = std::min(std::min(v.j1 + 2, v.njc), qj0 + qjn);
+    bool horiz_periodic = false;
+    for (const sgpu_bc& b : c->bcs) if (b.type == SGPU_BC_PERIODIC && (b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP)) horiz_periodic = true;
+    int nch = std::min(8, v.njl/64);
+    if (nch < 2 || horiz_periodic) {                             // small grids / wrap-around ghosts: plain sequence
+        if (int rc = sgpu_set_state_window(c, SGPU_STATE_Q, q, qj0, qjn)) return rc;
+        if (int rc = sgpu_residual(c, SGPU_STATE_Q, lhs, nullptr)) return rc;
+        return download_planes(c, c->rhs, v.nv, rhs, !(rj0 == 0 && rjn == v.njc));
+    }
+    if (!c->pipe_init) {
+        for (int k = 0; k < 3; k++) CK(c, cudaStreamCreateWithFlags(&c->pipe_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 16; k++) { CK(c, cudaEventCreateWithFlags(&c->pipe_up[k], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->pipe_cmp[k], cudaEventDisableTiming)); }
+        CK(c, cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
+        c->pipe_init = true;
+    }
+    const int rows_per = (v.njl + nch - 1)/nch;
+    const size_t stage_rows = (size_t)rows_per + 4;
+    const size_t stage_dbl = (size_t)v.nic*stage_rows*v.nv;
+    if (stage_dbl > c->pipe_stage_cap) {
+        for (int k = 0; k < 4; k++) { if (c->pipe_stage[k]) CK(c, cudaFree(c->pipe_stage[k])); c->pipe_stage[k] = nullptr; }
+        for (int k = 0; k < 4; k++) CK(c, cudaMalloc(&c->pipe_stage[k], stage_dbl*sizeof(double)));
+        c->pipe_stage_cap = stage_dbl;
+    }
+    cudaStream_t s_in = c->pipe_stream[0], s_cmp = c->pipe_stream[1], s_out = c->pipe_stream[2];
+    cudaStream_t user = c->stream;
+    CK(c, cudaEventRecord(c->pipe_start, user));                 // order after whatever the caller enqueued before
+    for (int k = 0; k < 3; k++) CK(c, cudaStreamWaitEvent(c->pipe_stream[k], c->pipe_start, 0));
+    int rc = SGPU_OK;
+    for (int ch = 0; ch < nch && rc == SGPU_OK; ch++) {
+        const int a = v.j0 + ch*rows_per, b = std::min(a + rows_per, v.j1);          // owned rows of this chunk
+        const int ul = ch == 0 ? ulo : std::min(a + 2, uhi), uh = ch == nch - 1 ? uhi : std::min(b + 2, uhi);
+        // ---- upload rows [ul, uh)
+        if (uh > ul) {
+            const int nrows = uh - ul; const size_t M = (size_t)nrows*v.nv;
+            double* st = c->pipe_stage[ch & 1];
+            CK(c, cudaMemcpy2DAsync(st, sizeof(double)*M, q + (size_t)(ul - qj0)*v.nv, sizeof(double)*qjn*v.nv, sizeof(double)*M, v.nic, cudaMemcpyHostToDevice, s_in));
+            aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, s_in>>>(v, st, c->q[0], ul - v.j0 + JOFF, nrows);
+            CKL(c); c->launches++;
+        }
+        CK(c, cudaEventRecord(c->pipe_up[ch], s_in));
+        // ---- boundary conditions for the ghost cells this chunk reads + residual of its rows
+        CK(c, cudaStreamWaitEvent(s_cmp, c->pipe_up[ch], 0));
+        c->stream = s_cmp;
+        rc = apply_bcs(c, SGPU_STATE_Q, a, b + 1);               // padded rows a .. b+1  (cells a-1 .. b)
+        if (rc == SGPU_OK) rc = launch_residual(c, SGPU_STATE_Q, lhs, false, a - v.j0, b - v.j0);
+        c->stream = user;
+        if (rc != SGPU_OK) break;
+        CK(c, cudaEventRecord(c->pipe_cmp[ch], s_cmp));
+        // ---- download the chunk's rhs rows
+        CK(c, cudaStreamWaitEvent(s_out, c->pipe_cmp[ch], 0));
+        {
+            const int nrows = b - a; const size_t M = (size_t)nrows*v.nv;
+            double* st = c->pipe_stage[2 + (ch & 1)];
+            planes_to_aos_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, s_out>>>(v, st, c->rhs, a - v.j0 + JOFF, nrows, v.nv);
+            CKL(c); c->launches++;
+            CK(c, cudaMemcpy2DAsync(rhs + (size_t)(a - rj0)*v.nv, sizeof(double)*rjn*v.nv, st, sizeof(double)*M, sizeof(double)*M, v.nic, cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_in);
+    if (rc != SGPU_OK) return rc;
+    CK(c, e1); CK(c, e2); CK(c, e3);
+    return SGPU_OK;
+}
+
+extern "C" {
+
 int sgpu_residual_host(sgpu_ctx* c, const double* q, double* rhs, int lhs) {
     if (!c || !q || !rhs) return SGPU_ERR_ARG;
-    if (int rc = sgpu_set_state(c, SGPU_STATE_Q, q)) return rc;
-    if (int rc = sgpu_residual(c, SGPU_STATE_Q, lhs, nullptr)) return rc;
-    return sgpu_get_rhs(c, rhs);
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    return residual_host_pipelined(c, q, 0, c->v.njc, rhs, 0, c->v.njc, lhs);
+}
+int sgpu_residual_host_window(sgpu_ctx* c, const double* q, int j_first, int j_count, double* rhs_owned, int lhs) {
+    if (!c || !q || !rhs_owned) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    if (j_first > c->v.j0 || j_first + j_count < c->v.j1) FAIL(c, SGPU_ERR_ARG, "state window does not cover the owned rows");
+    CK(c, cudaSetDevice(c->device));
+    return residual_host_pipelined(c, q, j_first, j_count, rhs_owned, c->v.j0, c->v.njl, lhs);
 }
 
 int sgpu_calc_dt(sgpu_ctx* c, double cfl) {
