@@ -469,6 +469,7 @@ static int residual_host_pipelined(sgpu_ctx* c, const double* q, int qj0, int qj
     bool horiz_periodic = false;
     for (const sgpu_bc& b : c->bcs) if (b.type == SGPU_BC_PERIODIC && (b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP)) horiz_periodic = true;
     int nch = std::min(8, v.njl/64);
+    if (const char* e = getenv("SGPU_PIPE_CHUNKS")) nch = std::max(1, std::min(16, std::min(atoi(e), v.njl/8)));
     if (nch < 2 || horiz_periodic) {                             // small grids / wrap-around ghosts: plain sequence
         if (int rc = sgpu_set_state_window(c, SGPU_STATE_Q, q, qj0, qjn)) return rc;
         if (int rc = sgpu_residual(c, SGPU_STATE_Q, lhs, nullptr)) return rc;

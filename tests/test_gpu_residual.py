@@ -169,3 +169,37 @@ def test_windowed_slab_inputs_equal_global_inputs():
         assert np.array_equal(got, want[:, j0:j1, :])
         eq.close()
     one.close()
+
+
+@pytest.mark.parametrize("nic,njc", [(2, 2), (3, 5), (124, 9), (125, 7), (249, 3)])
+def test_ragged_and_minimum_sizes(nic, njc):
+    """edge sizes: the smallest grid the ABI accepts, strips that end exactly at / one past a strip seam, few rows"""
+    from oracle.bindings import PortOracle
+    from structured_b200.cases import Boundary
+    case = zoo_case("A", nic, njc)
+    case.boundaries = [Boundary("wall", "bottom", 1, -2), Boundary("freestream", "top", 0, -1),
+                       Boundary("freestream", "left", 0, -1), Boundary("outflow", "right", 0, -1)]
+    port = PortOracle(case); eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    for lhs in (False, True):
+        assert field_rel_err(eq.calc_residual(q, lhs=lhs), port.residual(q, lhs)).max() <= TOL
+    eq.close(); port.close()
+
+
+def test_error_behaviour_mirrors_reference_messages():
+    from structured_b200.api import GpuEulerEquation, SgpuError
+    from structured_b200.cases import Boundary
+    case = zoo_case("A")
+    case.boundaries.append(Boundary("slipwall", "left", 1, -2))          # "Boundary condition not implemented!" (bc.cpp:116-126)
+    with pytest.raises(SgpuError, match="not implemented"):
+        GpuEulerEquation(case)
+    case = zoo_case("A"); case.flux = "hllc"
+    with pytest.raises(SgpuError, match="Flux not found"):
+        GpuEulerEquation(case)
+    case = zoo_case("A")
+    eq = GpuEulerEquation(case)
+    with pytest.raises(SgpuError, match="scheme not defined"):
+        eq.explicit_step(0.1, "rk3")
+    with pytest.raises(SgpuError, match="calc_dt"):
+        eq.set_state(case.perturbed_q()); eq.jacobian_coo(apply_lhs_transform=True)
+    eq.close()
