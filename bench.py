@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost-row transport for N > 1")
     return ap.parse_args()
 
 
@@ -201,11 +202,34 @@ def run_ours(args):
     cells_local = nic * njc_per
     cells_total = nic * njc_total
 
-    from structured_b200.slab import HaloExchanger
+    from structured_b200.slab import HIGH, LOW, HaloExchanger
     halo = HaloExchanger(rank, world, eq.halo_count(), "cuda", dist) if world > 1 else None
+    halo_mode = "none"
+    if world > 1:
+        halo_mode = args.halo
+        if halo_mode == "p2p":
+            # NVLink peer memory: every rank opens its neighbours' receive buffers through CUDA IPC handles
+            try:
+                mine = (eq.halo_ipc_handle(LOW), eq.halo_ipc_handle(HIGH))
+                allh = [None] * world
+                dist.all_gather_object(allh, mine)
+                if rank > 0:
+                    eq.halo_open_peer(LOW, allh[rank - 1][HIGH])
+                if rank < world - 1:
+                    eq.halo_open_peer(HIGH, allh[rank + 1][LOW])
+                ok = torch.tensor([1.0], device="cuda")
+            except Exception:  # noqa: BLE001
+                ok = torch.tensor([0.0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1.0:
+                halo_mode = "nccl"
 
     def exchange():
-        halo.exchange(lambda side, t: eq.halo_pack(0, side, t.data_ptr()), lambda side, t: eq.halo_unpack(0, side, t.data_ptr()))
+        if halo_mode == "p2p":
+            eq.halo_push(0)          # boundary rows stored straight into the neighbours' memory + sequence flag
+            eq.halo_pull(0)          # device-side wait on the neighbours' flags, then unpack into the ghost rows
+        else:
+            halo.exchange(lambda side, t: eq.halo_pack(0, side, t.data_ptr()), lambda side, t: eq.halo_unpack(0, side, t.data_ptr()))
 
     l2 = np.zeros(nv)
 
@@ -330,7 +354,7 @@ def run_ours(args):
                "config": {"workload": "SA turbulent bump channel %dx%d cells, MUSCL+Roe+viscous, nv=%d, fp64%s" % (
                               nic, njc_total, nv, "" if n_gpus == 1 else ", j-slabs of %dx%d per GPU" % (nic, njc_per)),
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
-                          "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel"},
+                          "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                "jacobian": jac, "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)

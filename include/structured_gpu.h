@@ -160,13 +160,19 @@ int sgpu_jacobian_apply(sgpu_ctx* ctx, int transpose, const double* x, double* y
 int sgpu_halo_count(const sgpu_ctx* ctx);
 int sgpu_halo_pack(sgpu_ctx* ctx, int which, int side, double* dev_buf);
 int sgpu_halo_unpack(sgpu_ctx* ctx, int which, int side, const double* dev_buf);
-/* Peer-memory variant: register the neighbour's ghost-row buffer (a device pointer valid on this
- * device, e.g. from cudaIpcOpenMemHandle) so that sgpu_halo_push stores the boundary rows straight
- * into the neighbour's memory over NVLink. */
+/* Peer-memory variant (NVLink P2P): each slab owns, per side, a receive buffer (two slots + a sequence flag).
+ * After the neighbour's buffer has been registered -- same process: sgpu_halo_recv_buffer + sgpu_halo_enable_peer +
+ * sgpu_halo_set_peer; one process per GPU: sgpu_halo_ipc_handle on the owner, sgpu_halo_open_peer on the writer --
+ * sgpu_halo_push packs the two boundary rows with a kernel whose stores go STRAIGHT into the neighbour's memory and
+ * then publishes a sequence number; sgpu_halo_pull waits (on the device) for the neighbour's sequence number and
+ * unpacks into the ghost rows.  Call push on every slab, then pull: no host synchronisation, no NCCL. */
 int sgpu_halo_recv_buffer(sgpu_ctx* ctx, int side, double** dev_ptr);
+int sgpu_halo_enable_peer(sgpu_ctx* ctx, int peer_device);
 int sgpu_halo_set_peer(sgpu_ctx* ctx, int side, double* peer_recv_buf);
+int sgpu_halo_ipc_handle(sgpu_ctx* ctx, int side, void* handle64 /* 64 bytes out */);
+int sgpu_halo_open_peer(sgpu_ctx* ctx, int side, const void* handle64);
 int sgpu_halo_push(sgpu_ctx* ctx, int which);
-int sgpu_halo_pull(sgpu_ctx* ctx, int which);   /* ghost rows <- own recv buffers */
+int sgpu_halo_pull(sgpu_ctx* ctx, int which);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of kernels this library launched on the context since creation */

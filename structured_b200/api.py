@@ -24,7 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
-    "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_set_peer",
+    "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
 
@@ -284,6 +284,32 @@ class GpuEulerEquation:
 
     def halo_unpack(self, which: int, side: int, dev_ptr: int):
         self._ck(self.L.sgpu_halo_unpack(self.h, which, side, ctypes.c_void_p(dev_ptr)))
+
+    # peer-memory exchange (NVLink P2P)
+    def halo_recv_buffer(self, side: int) -> int:
+        p = ctypes.c_void_p()
+        self._ck(self.L.sgpu_halo_recv_buffer(self.h, side, ctypes.byref(p)))
+        return p.value
+
+    def halo_enable_peer(self, peer_device: int):
+        self._ck(self.L.sgpu_halo_enable_peer(self.h, peer_device))
+
+    def halo_set_peer(self, side: int, dev_ptr: int):
+        self._ck(self.L.sgpu_halo_set_peer(self.h, side, ctypes.c_void_p(dev_ptr)))
+
+    def halo_ipc_handle(self, side: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.L.sgpu_halo_ipc_handle(self.h, side, buf))
+        return buf.raw
+
+    def halo_open_peer(self, side: int, handle: bytes):
+        self._ck(self.L.sgpu_halo_open_peer(self.h, side, ctypes.c_char_p(handle)))
+
+    def halo_push(self, which: int = 0):
+        self._ck(self.L.sgpu_halo_push(self.h, which))
+
+    def halo_pull(self, which: int = 0):
+        self._ck(self.L.sgpu_halo_pull(self.h, which))
 
     # ---- instrumentation
     def enable_kernel_timing(self, on: bool = True):

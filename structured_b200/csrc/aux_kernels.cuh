@@ -280,6 +280,17 @@ __global__ void halo_unpack_kernel(View v, double* __restrict__ q, const double*
     q[k*v.plane + v.at(r_first + rr, i + IOFF)] = buf[((size_t)k*2 + rr)*v.nic + i];
 }
 
+// sequence flags of the peer-memory halo exchange (system scope: the flag lives in another GPU's memory)
+__global__ void halo_signal_kernel(unsigned long long* flag, unsigned long long seq) {
+    __threadfence_system();
+    *(volatile unsigned long long*)flag = seq;
+    __threadfence_system();
+}
+__global__ void halo_wait_kernel(const unsigned long long* flag, unsigned long long seq) {
+    while (*(volatile const unsigned long long*)flag < seq) { }
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Final stage of the residual-norm reduction (src/solver/solver.cpp:125-134): partial[item][nv] -> out[nv]
 // ------------------------------------------------------------------------------------------------

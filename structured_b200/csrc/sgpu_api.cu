@@ -40,6 +40,8 @@ struct sgpu_ctx {
     double* stage = nullptr; size_t stage_cap = 0;
     double* halo_recv[2] = {nullptr, nullptr};
     double* halo_peer[2] = {nullptr, nullptr};
+    bool halo_peer_ipc[2] = {false, false};
+    unsigned long long halo_seq = 0;
     JacStore jac{};
     // pipelined host path
     bool pipe_init = false;
@@ -141,8 +143,10 @@ int sgpu_create(const sgpu_desc* d, sgpu_ctx** out) {
     if (ce == cudaSuccess) ce = alloc(&c->wdist, pl);
     if (ce == cudaSuccess) ce = alloc(&c->beta, pl);
     if (ce == cudaSuccess) ce = alloc(&c->l2sq_dev, 8);
-    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[0], (size_t)2*v.nv*nic);
-    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[1], (size_t)2*v.nv*nic);
+    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[0], (size_t)4*v.nv*nic + 2);
+    if (ce == cudaSuccess) ce = alloc(&c->halo_recv[1], (size_t)4*v.nv*nic + 2);
+    if (ce == cudaSuccess) ce = cudaMemset(c->halo_recv[0], 0, ((size_t)4*v.nv*nic + 2)*sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemset(c->halo_recv[1], 0, ((size_t)4*v.nv*nic + 2)*sizeof(double));
     if (ce != cudaSuccess) {
         g_create_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(ce);
         sgpu_destroy(c); return SGPU_ERR_CUDA;
@@ -172,6 +176,7 @@ int sgpu_destroy(sgpu_ctx* c) {
     for (double* p : {c->q[0], c->q[1], c->rhs, c->dt, c->xv, c->yv, c->met, c->wdist, c->beta, c->partial, c->l2sq_dev,
                       c->stage, c->halo_recv[0], c->halo_recv[1]})
         if (p) cudaFree(p);
+    for (int k = 0; k < 2; k++) if (c->halo_peer_ipc[k] && c->halo_peer[k]) cudaIpcCloseMemHandle(c->halo_peer[k]);
     jac_free(c->jac);
     if (c->jac_scratch) cudaFree(c->jac_scratch);
     for (int k = 0; k < 4; k++) if (c->pipe_stage[k]) cudaFree(c->pipe_stage[k]);
@@ -378,8 +383,9 @@ static void shape_grid(const View& v, int ctas_per_sm, int sms, ResParams& p) {
 template <int NV, int ORDER, int FLUX, bool VISC>
 static int launch_residual_t(sgpu_ctx* c, ResParams& p, int* grid_out) {
     using Cfg = ResCfg<NV, VISC>;
-    static int occ = 0, sms = 0;
+    static int occ_dev[64] = {0}, sms_dev[64] = {0};           // function attributes are per device
     auto kern = residual_kernel<NV, ORDER, FLUX, VISC>;
+    int& occ = occ_dev[c->device & 63]; int& sms = sms_dev[c->device & 63];
     if (!occ) {
         CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
         CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RW, Cfg::smem_bytes));
@@ -612,9 +618,22 @@ int sgpu_halo_unpack(sgpu_ctx* c, int which, int side, const double* buf) {
     CKL(c); c->launches++;
     return SGPU_OK;
 }
+// receive buffer layout per side: [2 slots][halo_count doubles] + one 64-bit sequence flag
+static size_t halo_slot_doubles(const sgpu_ctx* c) { return (size_t)2*c->v.nv*c->v.nic; }
+static unsigned long long* halo_flag(const sgpu_ctx* c, double* buf) { return (unsigned long long*)(buf + 2*halo_slot_doubles(c)); }
+
 int sgpu_halo_recv_buffer(sgpu_ctx* c, int side, double** p) {
     if (!c || !p || side < 0 || side > 1) return SGPU_ERR_ARG;
     *p = c->halo_recv[side];
+    return SGPU_OK;
+}
+int sgpu_halo_enable_peer(sgpu_ctx* c, int peer_device) {
+    if (!c) return SGPU_ERR_ARG;
+    if (peer_device == c->device) return SGPU_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SGPU_OK; }
+    CK(c, e);
     return SGPU_OK;
 }
 int sgpu_halo_set_peer(sgpu_ctx* c, int side, double* peer) {
@@ -622,17 +641,53 @@ int sgpu_halo_set_peer(sgpu_ctx* c, int side, double* peer) {
     c->halo_peer[side] = peer;
     return SGPU_OK;
 }
+int sgpu_halo_ipc_handle(sgpu_ctx* c, int side, void* handle64) {
+    if (!c || !handle64 || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, c->halo_recv[side]));
+    memcpy(handle64, &h, 64);
+    return SGPU_OK;
+}
+int sgpu_halo_open_peer(sgpu_ctx* c, int side, const void* handle64) {
+    if (!c || !handle64 || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->halo_peer[side] = (double*)p;
+    c->halo_peer_ipc[side] = true;
+    return SGPU_OK;
+}
 int sgpu_halo_push(sgpu_ctx* c, int which) {
     if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
-    for (int side = 0; side < 2; side++)
-        if (c->halo_peer[side]) if (int rc = sgpu_halo_pack(c, which, side, c->halo_peer[side])) return rc;   // stores go over NVLink
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    c->halo_seq++;
+    const size_t slot = (size_t)(c->halo_seq & 1ull)*halo_slot_doubles(c);
+    for (int side = 0; side < 2; side++) {
+        if (!c->halo_peer[side]) continue;
+        // the two boundary rows go straight into the neighbour's receive slot (stores over NVLink), then the flag
+        halo_pack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], c->halo_peer[side] + slot, halo_rows(c, side, false));
+        CKL(c);
+        halo_signal_kernel<<<1, 1, 0, c->stream>>>(halo_flag(c, c->halo_peer[side]), c->halo_seq);
+        CKL(c); c->launches += 2;
+    }
     return SGPU_OK;
 }
 int sgpu_halo_pull(sgpu_ctx* c, int which) {
     if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    const size_t slot = (size_t)(c->halo_seq & 1ull)*halo_slot_doubles(c);
     for (int side = 0; side < 2; side++) {
-        const bool has_nb = side == 0 ? c->v.j0 > 0 : c->v.j1 < c->v.njc;
-        if (has_nb) if (int rc = sgpu_halo_unpack(c, which, side, c->halo_recv[side])) return rc;
+        const bool has_nb = side == 0 ? v.j0 > 0 : v.j1 < v.njc;
+        if (!has_nb) continue;
+        halo_wait_kernel<<<1, 1, 0, c->stream>>>(halo_flag(c, c->halo_recv[side]), c->halo_seq);
+        CKL(c);
+        halo_unpack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], c->halo_recv[side] + slot, halo_rows(c, side, true));
+        CKL(c); c->launches += 2;
     }
     return SGPU_OK;
 }
