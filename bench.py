@@ -72,7 +72,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -263,7 +263,7 @@ def run_ours(args):
     launches = eq.launch_count - launches0
     ktimes = eq.kernel_times()
     eq.enable_kernel_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,6 +310,8 @@ def run_ours(args):
                "h2d_bytes_per_step": int(nic * rows_in * nv * 8) * 1, "d2h_bytes_per_step": int(nic * njc_per * nv * 8),
                "steps": k_e2e, "note": "per-GPU bytes; sgpu_residual_host(q_host, rhs_host) from pinned host arrays"}
 
+    if rank == 0:
+        clocks = sampler.stop()                          # sampled across the timed residual loop and the e2e loop
     # ---- Jacobian build (second half of the metric); skipped when the device form is unavailable
     jac = None
     if not args.no_jacobian:
