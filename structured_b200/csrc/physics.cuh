@@ -20,16 +20,18 @@ constexpr double SA_CW2 = 0.3, SA_CW3 = 2.0, SA_CV1 = 7.1, SA_PRT = 0.9;
 // measured max relative error 1.1e-16 / 2.2e-16 on B200, i.e. 1 ulp -- far inside the 1e-12 parity bar.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0); r = fma(r, e, r);
-    e = fma(-x, r, 1.0); r = fma(r, e, r);
-    return r;
+    // one third-order step: e = 1 - x r0 (|e| <= 2^-20), r = r0 (1 + e + e^2): error e^3 ~ 2^-60, 3 dependent DFMAs
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 __device__ __forceinline__ double rsqrt_fast(double x) {
     double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5*x;
-    double e = fma(-h*y, y, 0.5); y = fma(y, e, y);
-    e = fma(-h*y, y, 0.5); y = fma(y, e, y);
-    return y;
+    // third-order step: e = 1 - x y0^2, y = y0 (1 + e/2 + 3 e^2/8)
+    const double t = x*y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5)*e;
+    return fma(y, p, y);
 }
 __device__ __forceinline__ double s_rcp(double x) { return rcp_fast(x); }
 __device__ __forceinline__ double s_rsqrt(double x) { return rsqrt_fast(x); }
