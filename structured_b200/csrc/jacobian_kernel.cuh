@@ -88,21 +88,21 @@ template <int NV, bool VISC>
 __device__ __forceinline__ void load_cell(const View& v, const Gas& g, const double* __restrict__ q, int r, int c, CellD<NV>& w) {
     const size_t o = v.at(r, c);
     cons_to_prim<double>(g, q[o], q[v.plane + o], q[2*v.plane + o], q[3*v.plane + o], w.r, w.u, w.v, w.p, w.T);
-    w.ri = 1.0/w.r;
+    w.ri = rcp_fast(w.r);
     const double ke = 0.5*(w.u*w.u + w.v*w.v), iR = 1.0/g.R;
     // T = p/(rho R):  dT = (dp - p/rho drho)/(rho R)
     w.dT[0] = (GM1*ke - w.p*w.ri)*w.ri*iR; w.dT[1] = -GM1*w.u*w.ri*iR; w.dT[2] = -GM1*w.v*w.ri*iR; w.dT[3] = GM1*w.ri*iR;
     w.mu = 0; w.nut = 0; w.mut = 0; w.rn = 0;
     if (VISC) {
         w.mu = laminar_viscosity<double>(g, w.T);
-        const double dmudT = (2.0/3.0)*w.mu/w.T;
+        const double dmudT = (2.0/3.0)*w.mu*rcp_fast(w.T);
 #pragma unroll
         for (int k = 0; k < 4; k++) w.dmu[k] = dmudT*w.dT[k];
     }
     if (NV > 4) {
         w.rn = q[4*v.plane + o];
         w.nut = w.rn*w.ri;
-        const double chi = w.rn/w.mu, c3 = SA_CV1*SA_CV1*SA_CV1, x3 = chi*chi*chi, den = 1.0/(x3 + c3);
+        const double chi = w.rn*rcp_fast(w.mu), c3 = SA_CV1*SA_CV1*SA_CV1, x3 = chi*chi*chi, den = rcp_fast(x3 + c3);
         const double fv1 = x3*den, dfv1 = 3.0*chi*chi*c3*den*den;
         w.mut = w.rn*fv1;
         w.dmut[4] = fv1 + chi*dfv1;
@@ -158,6 +158,14 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
                                             const CellRef* cr, bool Lint, bool Rint, double* __restrict__ S, size_t fo) {
     constexpr bool SA = NV > 4;
     const size_t stride = v.plane;
+    // the eight stencil cells are each loaded twice below (aggregates, then blocks): pull their lines into L1 now so
+    // that the later dependent loads cost an L1 hit instead of an exposed L2/HBM round trip
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        const size_t o = v.at(cr[n].r, cr[n].c);
+#pragma unroll
+        for (int k = 0; k < NV; k++) asm volatile("prefetch.global.L1 [%0];" :: "l"(q + k*stride + o));
+    }
     // ---- 1. primitives of the line cells, reconstruction and its derivative scalars
     double W[4][4];                               // [LL,L,R,RR][rho,u,v,p]
 #pragma unroll
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
             fg.bx = m.nex[v.at(r, ca)] + m.nex[v.at(r, cb)]; fg.by = m.ney[v.at(r, ca)] + m.ney[v.at(r, cb)];
             fg.rx = fg.nx + m.ncx[v.at(r, cR)]; fg.ry = fg.ny + m.ncy[v.at(r, cR)];
             fg.lx = fg.nx + m.ncx[v.at(r, cL)]; fg.ly = fg.ny + m.ncy[v.at(r, cL)];
-            fg.ivol2 = 1.0/(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
+            fg.ivol2 = rcp_fast(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
         }
         const int cL0 = cf - 1;                                    // plane column of the L cell
         cr[0] = {r, imax(cL0 - 1, 0)}; cr[1] = {r, cL0}; cr[2] = {r, cL0 + 1}; cr[3] = {r, imin(cL0 + 2, v.pitch - 1)};
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
             fg.lx = fg.nx + m.nex[v.at(rBo, c)]; fg.ly = fg.ny + m.ney[v.at(rBo, c)];
             fg.bx = m.ncx[v.at(rA, c)] + m.ncx[v.at(rB, c)]; fg.by = m.ncy[v.at(rA, c)] + m.ncy[v.at(rB, c)];
             fg.tx = m.ncx[v.at(rA, c + 1)] + m.ncx[v.at(rB, c + 1)]; fg.ty = m.ncy[v.at(rA, c + 1)] + m.ncy[v.at(rB, c + 1)];
-            fg.ivol2 = 1.0/(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
+            fg.ivol2 = rcp_fast(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
         }
         const int rL = rf - 1;                                     // plane row of the L cell
         cr[0] = {imax(rL - 1, 0), c}; cr[1] = {rL, c}; cr[2] = {rL + 1, c}; cr[3] = {imin(rL + 2, v.rows - 1), c};

@@ -114,3 +114,24 @@ def test_device_jacobian_products_and_adjoint_identity(ntrans):
     lhs, rhs = float((JTpsi * v).sum()), float((psi * Jv).sum())
     assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
     eq.close()
+
+
+@pytest.mark.parametrize("ntrans,split", [(0, 9), (1, 14)])
+def test_slab_jacobians_concatenate_to_the_global_jacobian(ntrans, split):
+    """each j-slab builds its own rows with GLOBAL row / column indices; no exchange beyond the q ghost rows"""
+    case = turbulent_channel_case(37, 30, ntrans=ntrans, reynolds=2e4, periodic=(ntrans == 0))
+    q = case.perturbed_q(0.02)
+    one = gpu_eq(case); one.set_state(q)
+    want = one.jacobian_coo()
+    parts = []
+    for (j0, j1) in ((0, split), (split, case.njc)):
+        eq = gpu_eq(case, j_begin=j0, j_end=j1)
+        eq.set_state(q)
+        parts.append(eq.jacobian_coo())
+        eq.close()
+    got = tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+    order = np.lexsort((got[1], got[0]))
+    got = tuple(g[order] for g in got)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(got[2], want[2])
+    one.close()
