@@ -152,6 +152,9 @@ int sgpu_jacobian_coo(sgpu_ctx* ctx, int* nnz, unsigned int** rind, unsigned int
 int sgpu_jacobian_device(sgpu_ctx* ctx, int* slots, float* build_ms);
 /* y = J x  and  y = J^T x with the device-resident Jacobian (adjoint building block); x, y host [nic][njc][nv] */
 int sgpu_jacobian_apply(sgpu_ctx* ctx, int transpose, const double* x, double* y);
+/* SA extension / field inversion: d rhs[i][j][4] / d beta[i][j] at state q (diagonal), GLOBAL host [nic][njc]
+ * (owned rows written).  Gradient of an objective w.r.t. the correction field = psi^T dR/dbeta. */
+int sgpu_dres_dbeta(sgpu_ctx* ctx, double* out);
 
 /* ---- multi-GPU j-slabs ---------------------------------------------------------------------- */
 /* Two ghost rows of q per interior slab edge.  side: 0 = low-j neighbour, 1 = high-j neighbour.

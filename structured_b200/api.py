@@ -23,7 +23,7 @@ SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
-    "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply",
+    "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
@@ -274,6 +274,12 @@ class GpuEulerEquation:
         y = self._state_array()
         self._ck(self.L.sgpu_jacobian_apply(self.h, int(transpose), _dp(x), _dp(y)))
         return y
+
+    def dres_dbeta(self) -> np.ndarray:
+        """d rhs4 / d beta per cell at the device state (SA extension; field-inversion gradient building block)"""
+        out = np.zeros((self.nic, self.njc))
+        self._ck(self.L.sgpu_dres_dbeta(self.h, _dp(out)))
+        return out
 
     # ---- halos (multi-GPU j-slabs)
     def halo_count(self) -> int:

@@ -182,6 +182,26 @@ int sgpu_jacobian_coo(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int**
                         : jacobian_export_t<4>(c, nnz, rind, cind, values, apply_lhs_transform);
 }
 
+int sgpu_dres_dbeta(sgpu_ctx* c, double* out) {
+    if (!c || !out) return SGPU_ERR_ARG;
+    if (c->v.nv != 5) FAIL(c, SGPU_ERR_ARG, "d rhs / d beta exists only with the SA extension (ntrans = 1)");
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    if (int rc = apply_bcs(c, SGPU_STATE_Q)) return rc;
+    double* tmp = nullptr;
+    CK(c, cudaMalloc(&tmp, v.plane*sizeof(double)));
+    sa_dbeta_kernel<true><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->g, metrics_of(c), c->q[0], c->wdist, tmp);
+    CKL(c); c->launches++;
+    // per-cell field [nic][njc]: reuse the state download with one plane broadcast, then compact on the host side
+    std::vector<double> h((size_t)v.plane);
+    CK(c, cudaMemcpyAsync(h.data(), tmp, v.plane*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+    for (int i = 0; i < v.nic; i++) for (int jl = 0; jl < v.njl; jl++) out[(size_t)i*v.njc + v.j0 + jl] = h[v.at(jl + JOFF, i + IOFF)];
+    return SGPU_OK;
+}
+
 int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) {
     if (!c || !x || !y) return SGPU_ERR_ARG;
     if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");

@@ -646,6 +646,47 @@ __global__ void __launch_bounds__(128) jac_gather_kernel(const JacParams prm) {
     }
 }
 
+// d rhs4 / d beta per cell (field inversion: the gradient of an objective w.r.t. the correction field is
+// psi^T dR/dbeta, and dR/dbeta is diagonal): the SA source is linear in beta, so the derivative is S(beta=1) - S(beta=0)
+// evaluated with the same cell-centred Green-Gauss gradients as the residual kernel's epilogue.
+template <bool VISC>
+__global__ void sa_dbeta_kernel(View v, Gas g, Metrics m, const double* __restrict__ q, const double* __restrict__ wdist, double* __restrict__ out) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const int r = jl + JOFF, c = i + IOFF;
+    const size_t o = v.at(r, c), pl = v.plane;
+    const double V = m.vol[o], Vi = 1.0/V;
+    double Wx[3][3], Wy[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { Wx[a][b] = 0.0; Wy[a][b] = 0.0; }
+    const double cxr = m.ncx[v.at(r, c + 1)], cyr = m.ncy[v.at(r, c + 1)], cxl = m.ncx[o], cyl = m.ncy[o];
+    const double ext = m.nex[v.at(r + 1, c)], eyt = m.ney[v.at(r + 1, c)], exb = m.nex[o], eyb = m.ney[o];
+    auto addw = [&](int dx, int dy, double w, double nxx, double nyy) { Wx[dx + 1][dy + 1] += w*nxx*Vi; Wy[dx + 1][dy + 1] += w*nyy*Vi; };
+    for (int s = 0; s < 2; s++) {
+        const double sg_ = s ? 1.0 : -1.0, nxx = sg_*(s ? cxr : cxl), nyy = sg_*(s ? cyr : cyl);
+        const int x0 = s ? 0 : -1;
+        addw(x0, 0, 0.375, nxx, nyy); addw(x0 + 1, 0, 0.375, nxx, nyy);
+        addw(x0, 1, 0.0625, nxx, nyy); addw(x0 + 1, 1, 0.0625, nxx, nyy); addw(x0, -1, 0.0625, nxx, nyy); addw(x0 + 1, -1, 0.0625, nxx, nyy);
+    }
+    for (int s = 0; s < 2; s++) {
+        const double sg_ = s ? 1.0 : -1.0, nxx = sg_*(s ? ext : exb), nyy = sg_*(s ? eyt : eyb);
+        const int y0 = s ? 0 : -1;
+        addw(0, y0, 0.375, nxx, nyy); addw(0, y0 + 1, 0.375, nxx, nyy);
+        addw(1, y0, 0.0625, nxx, nyy); addw(1, y0 + 1, 0.0625, nxx, nyy); addw(-1, y0, 0.0625, nxx, nyy); addw(-1, y0 + 1, 0.0625, nxx, nyy);
+    }
+    double dvdx = 0, dudy = 0, dndx = 0, dndy = 0;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            const size_t oc = v.at(r + dy, c + dx);
+            const double ri = 1.0/q[oc], uu = q[pl + oc]*ri, vv = q[2*pl + oc]*ri, nn = q[4*pl + oc]*ri;
+            dvdx += Wx[dx + 1][dy + 1]*vv; dudy += Wy[dx + 1][dy + 1]*uu;
+            dndx += Wx[dx + 1][dy + 1]*nn; dndy += Wy[dx + 1][dy + 1]*nn;
+        }
+    CellD<5> w0; load_cell<5, VISC>(v, g, q, r, c, w0);
+    const double om = fabs(dvdx - dudy);
+    out[o] = sa_source<double>(w0.r, w0.nut, w0.mu, om, dndx, dndy, wdist[o], 1.0) - sa_source<double>(w0.r, w0.nut, w0.mu, om, dndx, dndy, wdist[o], 0.0);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Slot -> column cell, shared by the COO export and the matrix-vector products
 // ---------------------------------------------------------------------------------------------------

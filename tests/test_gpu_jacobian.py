@@ -135,3 +135,19 @@ def test_slab_jacobians_concatenate_to_the_global_jacobian(ntrans, split):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     assert np.array_equal(got[2], want[2])
     one.close()
+
+
+def test_dres_dbeta_matches_oracle_difference():
+    """the SA source is linear in beta: dR4/dbeta = R4(beta+1) - R4(beta), exact up to round-off (oracle statement)"""
+    from oracle.bindings import PortOracle
+    case = turbulent_channel_case(40, 28, ntrans=1, reynolds=2e4)
+    q = case.perturbed_q(0.02)
+    eq = gpu_eq(case); eq.set_state(q)
+    got = eq.dres_dbeta()
+    r0 = PortOracle(case).residual(q)
+    case2 = turbulent_channel_case(40, 28, ntrans=1, reynolds=2e4); case2.beta = case.beta + 1.0
+    r1 = PortOracle(case2).residual(q)
+    want = r1[..., 4] - r0[..., 4]
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    assert np.abs(r1[..., :4] - r0[..., :4]).max() == 0.0
+    eq.close()
