@@ -8,6 +8,16 @@
 #include <map>
 #include <cstdlib>
 
+#if defined(STRUCTURED_GPU_IMPLICIT)
+// The implicit branch of Solver::step (src/solver/solver.cpp:66-101,154-183) WITHOUT ADOL-C: the sparse Jacobian comes
+// from sgpu_jacobian_coo and is consumed by the reference's own, unmodified LinearSolverEigen (Eigen SparseLU,
+// src/linearsolver/ls_eigen.cpp).  That file instantiates the class for <double, adouble>; with Tad = double there
+// is no adouble, so the name is mapped onto double for this one include.
+#define adouble double
+#include "ls_eigen.cpp"
+#undef adouble
+#endif
+
 template<class Tx> void set_rarray(size_t size, Tx* __restrict__ dest, Tx* __restrict__ src) { for (size_t i = 0; i < size; i++) dest[i] = src[i]; }
 template<class Tx> void update_forward_euler(size_t size, Tx* __restrict__ q, Tx* __restrict__ rhs, Tx* __restrict__ dt) { for (size_t i = 0; i < size; i++) q[i] = q[i] + rhs[i]*dt[i]; }
 template<class Tx, class To> void update_rk4(size_t size, Tx* __restrict__ q_i, Tx* __restrict__ q, Tx* __restrict__ rhs, Tx* __restrict__ dt, To order) { for (size_t i = 0; i < size; i++) q_i[i] = q[i] + rhs[i]*dt[i]/(4.0 - order); }
@@ -76,12 +86,39 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
     const size_t nv = solution->nq + solution->ntrans;
     double l2sq[8] = {0}, l2norm[8] = {0};
     config->profiler->reset_time_residual();
+#if !defined(STRUCTURED_GPU_IMPLICIT)
     int scheme = -1;
     if (config->solver->scheme == "forward_euler") scheme = 0;
     else if (config->solver->scheme == "rk4_jameson") scheme = 1;
     else logger->critical("scheme not defined.");
     if (scheme >= 0) gpu_check(sgpu_explicit_step(ctx, scheme, CFL, l2sq), ctx, "sgpu_explicit_step");
     config->profiler->update_time_residual();
+#else
+    static LinearSolverEigen<Tx, Tad>* linearsolver = new LinearSolverEigen<Tx, Tad>(mesh, config);
+    gpu_check(sgpu_calc_dt(ctx, CFL), ctx, "sgpu_calc_dt");                                   // solver.cpp:66
+    gpu_check(sgpu_residual(ctx, SGPU_STATE_Q, /*lhs=*/0, l2sq), ctx, "sgpu_residual");     // rhs with solver.order (solver.cpp:92-101)
+    gpu_check(sgpu_get_rhs(ctx, solution->rhs.data()), ctx, "sgpu_get_rhs");
+    config->profiler->update_time_residual();
+    if (!(counter > config->solver->iteration_max)) {
+        config->profiler->reset_time_jacobian();
+        // replaces trace_on .. trace_off + sparse_jac (solver.cpp:72-90,156) and the LHS loop (solver.cpp:162-171)
+        gpu_check(sgpu_jacobian_coo(ctx, &solution->nnz, &solution->rind, &solution->cind, &solution->values, 1), ctx, "sgpu_jacobian_coo");
+        config->profiler->update_time_jacobian();
+        logger->debug("NNZ = {}", solution->nnz);
+        if (counter == 0) linearsolver->preallocate(solution->nnz);
+        config->profiler->reset_time_linearsolver();
+        gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state");
+        linearsolver->set_lhs(solution->nnz, solution->rind, solution->cind, solution->values);
+        linearsolver->set_rhs(solution->rhs.data());
+        linearsolver->solve_and_update(solution->q.data(), UNDER_RELAXATION);
+        auto dt_perf = config->profiler->update_time_linearsolver();
+        logger->info("Linear algebra time = {:03.2f}", dt_perf);
+        gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_set_state");
+        free(solution->rind); solution->rind = nullptr;                                       // unchanged ownership (solver.cpp:181-183)
+        free(solution->cind); solution->cind = nullptr;
+        free(solution->values); solution->values = nullptr;
+    }
+#endif
     for (size_t k = 0; k < nv; k++) l2norm[k] = sqrt(l2sq[k]);
     auto sync_host = [&]() { gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state"); };
     if (counter > config->solver->iteration_max) {

@@ -35,3 +35,51 @@ def test_dropin_binary_reproduces_stock_binary(name, tmp_path):
     assert ours_hist[0] == ref_hist[0]                       # same step counter
     for a, b in zip(ours_hist[-4:], ref_hist[-4:]):          # L2 norms printed with 3 significant digits
         assert abs(float(a) - float(b)) <= 0.011 * abs(float(b))
+
+BIN_IMPLICIT = os.path.join(ROOT, "integration", "structured_gpu_implicit")
+
+
+@pytest.mark.skipif(not os.path.exists(BIN_IMPLICIT), reason="integration/structured_gpu_implicit not built (needs /root/reference at build time)")
+def test_implicit_dropin_with_reference_eigen_solver(tmp_path):
+    """The implicit branch of Solver::step with NO ADOL-C: sgpu_jacobian_coo feeds the reference's own LinearSolverEigen.
+    Checked against the same backward-Euler iteration done on the CPU with the oracle's residual/Jacobian and scipy's
+    sparse LU (src/solver/solver.cpp:66-101,154-183,212-220), and against plane Poiseuille flow."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle.bindings import PortOracle
+    from structured_b200.cases import case_from_toml
+    case, z = golden("channel")
+    n_it = 60
+    inp = (str(z["inp"]).replace("iteration_max = 100", "iteration_max = %d" % n_it)
+           .replace("stdout_frequency = 1", "stdout_frequency = 1000").replace("fileout_frequency = 1", "fileout_frequency = 100000"))
+    t = tomllib.loads(inp)
+    write_grid_p3d(str(tmp_path / os.path.basename(t["geometry"]["filename"])), z["xv"], z["yv"])
+    (tmp_path / "run.inp").write_text(inp)
+    res = subprocess.run([BIN_IMPLICIT, "-c", "run.inp"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    q_gpu = np.load(tmp_path / (t["io"]["label"] + ".npz"))["q"]
+
+    c = case_from_toml(inp, z["xv"], z["yv"])
+    port = PortOracle(c)
+    so = t["solver"]
+    q = c.freestream_q(); cfl = float(so["cfl"]); n = q.size; counter = 0
+    while True:
+        dt = port.calc_dt(q, cfl).reshape(-1)
+        rhs = port.residual(q, False).reshape(-1)
+        if counter > n_it:
+            break
+        ri, ci, va = port.jacobian(q, True)
+        A = sp.csc_matrix((-va, (ri, ci)), shape=(n, n)) + sp.diags(1.0 / dt)
+        q = q + float(so["under_relaxation"]) * spla.splu(A).solve(rhs).reshape(q.shape)
+        counter += 1
+        if so["cfl_ramp"] and counter > int(so["cfl_ramp_iteration"]):
+            cfl = min(cfl ** float(so["cfl_ramp_exponent"]), 1e12)
+    # rho v is zero to round-off in this flow: compare both momentum components at the momentum scale
+    err = field_rel_err(q_gpu, q)
+    err[2] = np.abs(q_gpu[..., 2] - q[..., 2]).max() / np.abs(q[..., 1]).max()
+    assert err.max() <= 1e-8, err
+    # plane Poiseuille flow: u_max = -dpdx h^2 / (2 mu), h = half height (SURVEY.md section 8c)
+    u = q_gpu[..., 1] / q_gpu[..., 0]
+    h = 0.5 * (z["yv"][0, -1] - z["yv"][0, 0])
+    u_max = -c.dpdx * h * h / (2.0 * c.mu_inf)
+    assert abs(u.max() - u_max) <= 0.02 * u_max
