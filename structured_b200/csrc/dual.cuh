@@ -33,6 +33,8 @@ template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N>& a) 
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, double b) { return a*(1.0/b); }
 __device__ __forceinline__ double rcp_fast(double x);
 __device__ __forceinline__ double rsqrt_fast(double x);
+__device__ __forceinline__ double s_pow23(double x);
+__device__ __forceinline__ double s_pow16(double x);
 template <int N> __device__ __forceinline__ Dual<N> s_rcp(const Dual<N>& a) { Dual<N> r; r.v = rcp_fast(a.v); const double s = -r.v*r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
 template <int N> __device__ __forceinline__ Dual<N> s_rsqrt(const Dual<N>& a) { Dual<N> r; r.v = rsqrt_fast(a.v); const double s = -0.5*r.v*r.v*r.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) { return a*s_rcp(b); }
@@ -41,10 +43,10 @@ template <int N> __device__ __forceinline__ Dual<N> s_sqrt(const Dual<N>& a) { D
 template <int N> __device__ __forceinline__ Dual<N> s_abs(const Dual<N>& a) { return a.v < 0.0 ? -a : a; }
 template <int N> __device__ __forceinline__ double s_val(const Dual<N>& a) { return a.v; }
 template <int N> __device__ __forceinline__ Dual<N> s_pow23(const Dual<N>& a) {
-    Dual<N> r; const double c = cbrt(a.v); r.v = c*c; const double s = (2.0/3.0)*r.v/a.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r;
+    Dual<N> r; r.v = s_pow23(a.v); const double s = (2.0/3.0)*r.v*rcp_fast(a.v); SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> s_pow16(const Dual<N>& a) {
-    Dual<N> r; r.v = cbrt(sqrt(a.v)); const double s = (1.0/6.0)*r.v/a.v; SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r;
+    Dual<N> r; r.v = s_pow16(a.v); const double s = (1.0/6.0)*r.v*rcp_fast(a.v); SG_DUAL_LOOP r.d[k] = s*a.d[k]; return r;
 }
 #undef SG_DUAL_LOOP
 

@@ -94,7 +94,9 @@ __device__ __forceinline__ void load_cell(const View& v, const Gas& g, const dou
     w.dT[0] = (GM1*ke - w.p*w.ri)*w.ri*iR; w.dT[1] = -GM1*w.u*w.ri*iR; w.dT[2] = -GM1*w.v*w.ri*iR; w.dT[3] = GM1*w.ri*iR;
     w.mu = 0; w.nut = 0; w.mut = 0; w.rn = 0;
     if (VISC) {
-        w.mu = laminar_viscosity<double>(g, w.T);
+        // libdevice cbrt (a call, not inlined) keeps the register pressure of these spill-bound kernels down; the value
+        // agrees with the residual kernel's s_pow23 to 1 ulp
+        { const double cb = cbrt(w.T*g.iT_ref); w.mu = g.mu_ref*cb*cb; }
         const double dmudT = (2.0/3.0)*w.mu*rcp_fast(w.T);
 #pragma unroll
         for (int k = 0; k < 4; k++) w.dmu[k] = dmudT*w.dT[k];
