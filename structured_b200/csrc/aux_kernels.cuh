@@ -200,39 +200,42 @@ __global__ void axpy_dt_div_kernel(View v, double* __restrict__ dst, const doubl
 // Host boundary: AoS [i][jr][k] staging  <->  SoA planes [k][r][c].   jr counts rows from local row r0.
 // 32x32 tiles through shared memory so that both sides are coalesced.
 // ------------------------------------------------------------------------------------------------
-__global__ void aos_to_planes_kernel(View v, const double* __restrict__ stage, double* __restrict__ planes, int r0, int nrows) {
+__global__ void aos_to_planes_kernel(View v, const double* __restrict__ stage, double* __restrict__ planes, int r0, int nrows,
+                                     int ia = 0, int ni = -1 /* stage holds columns [ia, ia+ni) ; default: all */) {
     __shared__ double tile[32][33];
+    if (ni < 0) ni = v.nic;
     const int M = nrows*v.nv;                      // contiguous length per i in the staging buffer
     const int m0 = blockIdx.x*32, i0 = blockIdx.y*32;
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         const int i = i0 + dy, mm = m0 + threadIdx.x;
-        if (i < v.nic && mm < M) tile[dy][threadIdx.x] = stage[(size_t)i*M + mm];
+        if (i < ni && mm < M) tile[dy][threadIdx.x] = stage[(size_t)i*M + mm];
     }
     __syncthreads();
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         const int mm = m0 + dy, i = i0 + threadIdx.x;
-        if (i < v.nic && mm < M) {
+        if (i < ni && mm < M) {
             const int jr = mm/v.nv, k = mm - jr*v.nv;
-            planes[k*v.plane + v.at(r0 + jr, i + IOFF)] = tile[threadIdx.x][dy];
+            planes[k*v.plane + v.at(r0 + jr, ia + i + IOFF)] = tile[threadIdx.x][dy];
         }
     }
 }
 __global__ void planes_to_aos_kernel(View v, double* __restrict__ stage, const double* __restrict__ planes, int r0, int nrows,
-                                     int nvp /* planes available: nv, or 1 to broadcast a per-cell plane */) {
+                                     int nvp /* planes available: nv, or 1 to broadcast a per-cell plane */, int ia = 0, int ni = -1) {
     __shared__ double tile[32][33];
+    if (ni < 0) ni = v.nic;
     const int M = nrows*v.nv;
     const int m0 = blockIdx.x*32, i0 = blockIdx.y*32;
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         const int mm = m0 + dy, i = i0 + threadIdx.x;
-        if (i < v.nic && mm < M) {
+        if (i < ni && mm < M) {
             const int jr = mm/v.nv, k = mm - jr*v.nv;
-            tile[threadIdx.x][dy] = planes[(nvp == 1 ? 0 : k)*v.plane + v.at(r0 + jr, i + IOFF)];
+            tile[threadIdx.x][dy] = planes[(nvp == 1 ? 0 : k)*v.plane + v.at(r0 + jr, ia + i + IOFF)];
         }
     }
     __syncthreads();
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         const int i = i0 + dy, mm = m0 + threadIdx.x;
-        if (i < v.nic && mm < M) stage[(size_t)i*M + mm] = tile[dy][threadIdx.x];
+        if (i < ni && mm < M) stage[(size_t)i*M + mm] = tile[dy][threadIdx.x];
     }
 }
 // per-cell field [i][jr] -> one plane

@@ -32,6 +32,7 @@ struct ResParams {
     double eps_chi, eps_eta, dpdx, dpdy;
     int nstrips, nchunks, rpc;
     int row0, row1;                     // local cell rows [row0, row1) this launch covers (whole slab: 0, njl)
+    int strip0;                         // first strip of this launch (column-chunked host pipeline), normally 0
 };
 
 // vertex-average / dual-cell variable set
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
 
     const View& v = prm.v; const Gas& g = prm.g;
     const int t = threadIdx.x;
-    const int strip = blockIdx.x % prm.nstrips, chunk = blockIdx.x / prm.nstrips;
+    const int strip = prm.strip0 + blockIdx.x % prm.nstrips, chunk = blockIdx.x / prm.nstrips;
     const int i0 = strip*RCELLS;
     const int ra = prm.row0 + chunk*prm.rpc, rb = imin(ra + prm.rpc, prm.row1);
     const int i = i0 - 2 + t;                            // global index of own cell column / own chi face
