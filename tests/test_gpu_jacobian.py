@@ -151,3 +151,37 @@ def test_dres_dbeta_matches_oracle_difference():
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
     assert np.abs(r1[..., :4] - r0[..., :4]).max() == 0.0
     eq.close()
+
+
+def test_field_inversion_size_2048x1024_properties():
+    """BASELINE.json config 4 (2048 x 1024, SA + beta field): device Jacobian, J v against a central difference of the
+    residual, the adjoint identity psi.(J v) = (J^T psi).v and dR/dbeta against the (linear) beta dependence."""
+    case = turbulent_channel_case(2048, 1024, ntrans=1)
+    eq = gpu_eq(case)
+    q = case.perturbed_q()
+    eq.set_state(q)
+    slots, ms = eq.jacobian_device()
+    assert slots == 13 and ms > 0
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(q.shape) * np.abs(q).mean(axis=(0, 1))
+    psi = rng.standard_normal(q.shape)
+    Jv = eq.jacobian_apply(v)
+    JTpsi = eq.jacobian_apply(psi, transpose=True)
+    a, b = float((JTpsi * v).sum()), float((psi * Jv).sum())
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    h = 1e-7
+    fd = (eq.calc_residual(q + h * v) - eq.calc_residual(q - h * v)) / (2 * h)
+    # AD differentiates the taken branch of the non-smooth pieces (|.| in the Roe flux, the upwind switch of the SA
+    # flux where the wall-normal mass flux changes sign, min/max in the SA source); a central difference straddles
+    # them in a few wall cells, so the comparison is in the L2 norm plus a bound on the share of outliers
+    for k in range(5):
+        d = Jv[..., k] - fd[..., k]
+        assert np.sqrt((d * d).sum()) <= 1e-3 * np.sqrt((fd[..., k] ** 2).sum()), k
+        assert (np.abs(d) > 1e-5 * np.abs(fd[..., k]).max()).mean() <= 1e-3, k
+    eq.set_state(q)
+    dRdb = eq.dres_dbeta()
+    r0 = eq.calc_residual(q)
+    eq.set_field("beta", case.beta + 1.0)
+    r1 = eq.calc_residual(q)
+    assert np.abs(dRdb - (r1[..., 4] - r0[..., 4])).max() <= 1e-10 * np.abs(dRdb).max()
+    eq.close()

@@ -203,3 +203,36 @@ def test_error_behaviour_mirrors_reference_messages():
     with pytest.raises(SgpuError, match="calc_dt"):
         eq.set_state(case.perturbed_q()); eq.jacobian_coo(apply_lhs_transform=True)
     eq.close()
+
+
+def test_full_size_4096_properties():
+    """BASELINE.json's 1-GPU size (4096 x 4096, SA): size-independent properties instead of an oracle run --
+    device norms == norms of the downloaded field; two j-slabs reproduce the one-slab field bit for bit
+    (checksum of checksums + sampled rows); explicit-step bookkeeping keeps q finite."""
+    n = 4096
+    case = turbulent_channel_case(n, n, ntrans=1)
+    q = case.perturbed_q()
+    eq = gpu_eq(case)
+    eq.set_state(q)
+    l2 = eq.residual_device(0, norms=True)
+    rhs = eq.get_rhs()
+    assert np.isfinite(rhs).all()
+    want = np.einsum("ijk,ijk->k", rhs, rhs)
+    assert np.abs(l2 - want).max() <= 1e-12 * want.max()
+    col_sum = rhs.sum(axis=0)                                  # [njc][nv] checksum per row
+    sample = rhs[::511, :, :].copy()
+    eq.close()
+    del rhs
+    split = 1500
+    got_sum = np.zeros_like(col_sum)
+    for (j0, j1) in ((0, split), (split, n)):
+        ja, jb = max(j0 - 2, 0), min(j1 + 2, n)
+        s = gpu_eq(case, j_begin=j0, j_end=j1)
+        s.set_state_window(np.ascontiguousarray(q[:, ja:jb, :]), ja)
+        s.residual_device(0)
+        part = np.zeros((n, j1 - j0, 5))
+        s.get_rhs_window(part)
+        got_sum[j0:j1] = part.sum(axis=0)
+        assert np.array_equal(part[::511], sample[:, j0:j1, :])
+        s.close()
+    assert np.array_equal(got_sum, col_sum)
