@@ -7,8 +7,14 @@
 namespace sg {
 
 constexpr double GAMMA = 1.4;                 // src/common.h:40
-constexpr double GM1 = GAMMA - 1.0;
-constexpr double OGM1 = 1.0/GM1;
+constexpr double GM1_C = GAMMA - 1.0;
+constexpr double OGM1 = 1.0/GM1_C;
+// Doubles whose low mantissa word is non-zero cannot be encoded as SASS immediates: as literals each use costs two
+// UMOV issue slots.  Read from the constant bank they are free operands of DFMA/DMUL.
+__constant__ double c_kc[4] = {GAMMA - 1.0, 2.0/3.0, 4.0/3.0, GAMMA};
+#define GM1 (c_kc[0])
+#define K23 (c_kc[1])
+#define K43 (c_kc[2])
 
 // Spalart-Allmaras constants (extension, DESIGN.md "SA extension")
 constexpr double SA_CB1 = 0.1355, SA_CB2 = 0.622, SA_SIGMA = 2.0/3.0, SA_KAPPA = 0.41;
@@ -88,7 +94,7 @@ __device__ __forceinline__ S laminar_viscosity(const Gas& g, S T) { return g.mu_
 // its high face (becomes that face's LEFT state) and to its low face (that face's RIGHT state).
 template <class S>
 __device__ __forceinline__ void muscl_cell(S qm, S q0, S qp, double eps, S& to_high, S& to_low) {
-    const double thm = 2.0/3.0, thp = 4.0/3.0;          // reconstruction.h:55-56
+    const double thm = K23, thp = K43;                  // reconstruction.h:55-56
     S f2a = q0 - qm, f2b = qp - q0;
     S a1 = 3.0*f2b*f2a;
     S d = f2b - f2a;
@@ -168,8 +174,8 @@ __device__ __forceinline__ void viscous_flux(double nx, double ny, S dudx, S dud
                                              S ubar, S vbar, S mu, S k, S* f) {
     S div = dudx + dvdy;
     S tau_xy = mu*(dudy + dvdx);
-    S tau_xx = mu*(2.0*dudx - (2.0/3.0)*div);
-    S tau_yy = mu*(2.0*dvdy - (2.0/3.0)*div);
+    S tau_xx = mu*(2.0*dudx - K23*div);
+    S tau_yy = mu*(2.0*dvdy - K23*div);
     S q_x = -(k*dTdx), q_y = -(k*dTdy);
     f[1] = tau_xx*nx + tau_xy*ny;
     f[2] = tau_xy*nx + tau_yy*ny;
