@@ -328,8 +328,8 @@ def run_ours(args):
     achieved = cells_local * B_PER_CELL[nv] / (kt * 1e-3) / 1e9 if kt else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "residual_traffic.json")
-    if os.path.exists(tp):
-        try:
+    if os.path.exists(tp) and nv == 5 and nic * njc_per == 4096 * 4096:
+        try:                                             # ncu --set full capture of this kernel on the 16.8 M-cell SA workload
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None

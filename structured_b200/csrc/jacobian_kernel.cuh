@@ -523,8 +523,15 @@ __global__ void __launch_bounds__(128) jac_gather_kernel(const JacParams prm) {
         for (int k = 0; k < 6; k++) Sd[k] = S.d[k];
     }
 
+    // slot order: runs of slots along i first -- the scratch plane (n, e) of chi face i+1 feeds slot A of this cell
+    // and slot A+1 of the right neighbour, so walking the i-runs makes the two reads of every chi plane line
+    // adjacent in time (L1/L2 hits instead of a second HBM read)
+    constexpr int ORD[13] = {9, 1, 0, 2, 10, 7, 4, 8, 5, 3, 6, 11, 12};
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
+    for (int si = 0; si < 13; si++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int s = ORD[si];
+        if (s >= NS) continue;
         if (!VISC && s >= 5 && s <= 8) {                           // corners exist through the viscous stencil only
             continue;
         }
