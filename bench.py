@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--no-linsolve", action="store_true", help="skip the device GMRES sample on the built Jacobian (N=1 only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost-row transport for N > 1")
     return ap.parse_args()
 
@@ -323,6 +324,22 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             jac = {"unavailable": str(ex)[:120]}
 
+    # ---- device linear solve on that Jacobian: a bounded GMRES sample, N = 1 only
+    lin = None
+    if jac and "build_ms" in jac and world == 1 and not args.no_linsolve:
+        try:
+            eq.calc_dt(20.0)
+            _, info = eq.linear_solve("lhs", precond="line_j", restart=20, max_iter=40, rtol=1e-8, want_x=False)
+            mv_bytes = cells_local * (jac["slots"] * nv * nv + 2 * nv + 1) * 8
+            lin = {"system": "(-J + 1/dt) dq = rhs at CFL 20 (src/solver/solver.cpp:162-175)", "method": "GMRES(20), right j-line block-tridiagonal preconditioner",
+                   "iterations": info["iterations"], "rel_residual": info["rel_residual"],
+                   "ms_per_iteration": round(info["solve_ms"] / max(info["iterations"], 1), 3), "setup_ms": round(info["setup_ms"], 3),
+                   "matvec_ms": round(info["matvec_ms"], 4), "precond_ms": round(info["precond_ms"], 4),
+                   "matvec_GBps": round(mv_bytes / (info["matvec_ms"] * 1e-3) / 1e9, 1) if info["matvec_ms"] > 0 else None,
+                   "matvec_roofline_frac": round(mv_bytes / (info["matvec_ms"] * 1e-3) / 1e9 / measured_peak()[0], 4) if info["matvec_ms"] > 0 else None}
+        except Exception as ex:  # noqa: BLE001
+            lin = {"unavailable": str(ex)[:120]}
+
     peak, peak_src = measured_peak()
     kt = float(np.mean(ktimes)) if len(ktimes) else None
     achieved = cells_local * B_PER_CELL[nv] / (kt * 1e-3) / 1e9 if kt else None
@@ -358,7 +375,7 @@ def run_ours(args):
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "l2norm": [float(x) for x in np.sqrt(l2)]}
+               "jacobian": jac, "linear_solve": lin, "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()
     if world > 1:

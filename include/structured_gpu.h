@@ -156,6 +156,46 @@ int sgpu_jacobian_apply(sgpu_ctx* ctx, int transpose, const double* x, double* y
  * (owned rows written).  Gradient of an objective w.r.t. the correction field = psi^T dR/dbeta. */
 int sgpu_dres_dbeta(sgpu_ctx* ctx, double* out);
 
+/* ---- device linear solve ---------------------------------------------------- */
+/* Replaces, for a Jacobian that stays on the device, the reference's linear-solver plug-in
+ *     linearsolver->set_lhs(nnz, rind, cind, values); set_rhs(rhs); solve_and_update(q, UNDER_RELAXATION)
+ * (src/solver/solver.cpp:172-175; src/linearsolver/ls_eigen.h:26-31, ls_eigen.cpp:32-70; ls_petsc.cpp GMRES).
+ * No COO is exported, so neither the `int nnz` limit nor the D2H of the matrix applies.
+ * Method: restarted right-preconditioned GMRES on the block-stencil planes. */
+enum sgpu_matrix {
+    SGPU_MAT_LHS = 0,          /* A = -J + delta/dt: the matrix of src/solver/solver.cpp:162-171 (needs sgpu_calc_dt) */
+    SGPU_MAT_J   = 1,          /* A = J  = d rhs / d q                                              */
+    SGPU_MAT_JT  = 2,          /* A = J^T (adjoint systems)                          */
+    SGPU_MAT_LHS_T = 3         /* A = (-J + delta/dt)^T: one pseudo-time step of the adjoint        */
+};
+enum sgpu_precond {
+    SGPU_PC_BLOCK_JACOBI = 0,  /* inverse of the nv x nv diagonal block of every cell               */
+    SGPU_PC_LINE_J       = 1   /* exact block-tridiagonal solve along every grid line i = const     */
+};
+#define SGPU_GMRES_MAX 200
+typedef struct sgpu_linsolve {
+    /* in (0 selects the default) */
+    int    precond;            /* enum sgpu_precond                                                 */
+    int    restart;            /* GMRES restart length m (default 30, at most SGPU_GMRES_MAX)       */
+    int    max_iter;           /* cap on Krylov iterations over all restarts (default 500)          */
+    int    reorthogonalize;    /* != 0: second Gram-Schmidt pass per iteration                      */
+    double rtol;               /* stop when |b - A x| <= rtol |b| (default 1e-10)                   */
+    /* out */
+    int    iterations;
+    int    converged;
+    double rel_residual;       /* true |b - A x| / |b| of the returned x                            */
+    float  setup_ms, solve_ms; /* device time: preconditioner factorisation, Krylov iterations      */
+    float  matvec_ms, precond_ms; /* device time of ONE operator / preconditioner application (first iteration) */
+} sgpu_linsolve;
+/* Solves A x = b with the Jacobian of the last sgpu_jacobian_device / sgpu_jacobian_coo / sgpu_implicit_step.
+ * b: host [nic][njc][nv], or NULL for the device rhs of the last sgpu_residual (what set_rhs receives).
+ * x: host [nic][njc][nv] or NULL (the solution also stays on the device for sgpu_implicit_step). */
+int sgpu_linear_solve(sgpu_ctx* ctx, int matrix, const double* b, double* x, sgpu_linsolve* io);
+/* The whole ENABLE_ADOLC branch of Solver::step on the device (src/solver/solver.cpp:66-101,154-175):
+ * calc_dt(cfl); rhs = residual(q) with solver.order; J = d residual(lhs_order)/dq; solve (-J + 1/dt) dq = rhs;
+ * q += under_relaxation * dq (ls_eigen.cpp:66-70).  l2sq as in sgpu_residual. */
+int sgpu_implicit_step(sgpu_ctx* ctx, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq);
+
 /* ---- multi-GPU j-slabs ---------------------------------------------------------------------- */
 /* Two ghost rows of q per interior slab edge.  side: 0 = low-j neighbour, 1 = high-j neighbour.
  * pack writes this slab's two boundary rows into a contiguous DEVICE buffer of sgpu_halo_count()

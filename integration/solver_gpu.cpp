@@ -8,7 +8,7 @@
 #include <map>
 #include <cstdlib>
 
-#if defined(STRUCTURED_GPU_IMPLICIT)
+#if defined(STRUCTURED_GPU_IMPLICIT) && !defined(STRUCTURED_GPU_DEVICE_SOLVE)
 // The implicit branch of Solver::step (src/solver/solver.cpp:66-101,154-183) WITHOUT ADOL-C: the sparse Jacobian comes
 // from sgpu_jacobian_coo and is consumed by the reference's own, unmodified LinearSolverEigen (Eigen SparseLU,
 // src/linearsolver/ls_eigen.cpp).  That file instantiates the class for <double, adouble>; with Tad = double there
@@ -86,7 +86,21 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
     const size_t nv = solution->nq + solution->ntrans;
     double l2sq[8] = {0}, l2norm[8] = {0};
     config->profiler->reset_time_residual();
-#if !defined(STRUCTURED_GPU_IMPLICIT)
+#if defined(STRUCTURED_GPU_DEVICE_SOLVE)
+    // The whole implicit branch on the device (src/solver/solver.cpp:66-101,154-175): no COO export, no host linear solver.
+    // The reference solves its LHS exactly (SparseLU); GMRES is driven to round-off so the iteration history matches it.
+    if (!(counter > config->solver->iteration_max)) {
+        sgpu_linsolve ls{};
+        ls.precond = SGPU_PC_LINE_J; ls.restart = 60; ls.max_iter = 2000; ls.rtol = 1e-13;
+        gpu_check(sgpu_implicit_step(ctx, CFL, UNDER_RELAXATION, &ls, l2sq), ctx, "sgpu_implicit_step");
+        if (!ls.converged) logger->warn("GMRES stopped at |r|/|b| = {:.2e} after {} iterations", ls.rel_residual, ls.iterations);
+        logger->debug("GMRES iterations = {}", ls.iterations);
+    } else {
+        gpu_check(sgpu_calc_dt(ctx, CFL), ctx, "sgpu_calc_dt");
+        gpu_check(sgpu_residual(ctx, SGPU_STATE_Q, 0, l2sq), ctx, "sgpu_residual");
+    }
+    config->profiler->update_time_residual();
+#elif !defined(STRUCTURED_GPU_IMPLICIT)
     int scheme = -1;
     if (config->solver->scheme == "forward_euler") scheme = 0;
     else if (config->solver->scheme == "rk4_jameson") scheme = 1;

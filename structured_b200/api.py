@@ -24,6 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
+    "sgpu_linear_solve", "sgpu_implicit_step",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
@@ -42,6 +43,18 @@ class SgpuDesc(ctypes.Structure):
                 ("pr_inf", ctypes.c_double), ("dpdx", ctypes.c_double), ("dpdy", ctypes.c_double),
                 ("n_bc", ctypes.c_int), ("bc", ctypes.POINTER(SgpuBc)), ("device", ctypes.c_int),
                 ("j_begin", ctypes.c_int), ("j_end", ctypes.c_int)]
+
+
+class SgpuLinsolve(ctypes.Structure):
+    """sgpu_linsolve of include/structured_gpu.h: GMRES controls in, iteration report out."""
+    _fields_ = [("precond", ctypes.c_int), ("restart", ctypes.c_int), ("max_iter", ctypes.c_int), ("reorthogonalize", ctypes.c_int),
+                ("rtol", ctypes.c_double),
+                ("iterations", ctypes.c_int), ("converged", ctypes.c_int), ("rel_residual", ctypes.c_double),
+                ("setup_ms", ctypes.c_float), ("solve_ms", ctypes.c_float), ("matvec_ms", ctypes.c_float), ("precond_ms", ctypes.c_float)]
+
+
+MATRICES = {"lhs": 0, "J": 1, "JT": 2, "lhsT": 3}
+PRECONDS = {"block_jacobi": 0, "line_j": 1}
 
 
 class SgpuError(RuntimeError):
@@ -274,6 +287,41 @@ class GpuEulerEquation:
         y = self._state_array()
         self._ck(self.L.sgpu_jacobian_apply(self.h, int(transpose), _dp(x), _dp(y)))
         return y
+
+    # ---- device linear solve / implicit step (replaces src/linearsolver/*)
+    @staticmethod
+    def _linsolve(precond, restart, max_iter, rtol, reorthogonalize) -> SgpuLinsolve:
+        if precond not in PRECONDS:
+            raise SgpuError("unknown preconditioner %r" % (precond,))
+        return SgpuLinsolve(PRECONDS[precond], restart, max_iter, int(reorthogonalize), rtol, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+    @staticmethod
+    def _linsolve_info(io: SgpuLinsolve) -> dict:
+        return {"iterations": io.iterations, "converged": bool(io.converged), "rel_residual": io.rel_residual,
+                "setup_ms": io.setup_ms, "solve_ms": io.solve_ms, "matvec_ms": io.matvec_ms, "precond_ms": io.precond_ms}
+
+    def linear_solve(self, matrix: str = "lhs", b: Optional[np.ndarray] = None, precond: str = "block_jacobi", restart: int = 30,
+                     max_iter: int = 500, rtol: float = 1e-10, reorthogonalize: bool = False, want_x: bool = True):
+        """Solve A x = b on the device with the Jacobian of the last jacobian_device()/jacobian_coo()/implicit_step().
+        matrix "lhs": A = -J + 1/dt (what linearsolver->set_lhs receives, solver.cpp:162-173), "J", "JT" (adjoint) or
+        "lhsT" (transposed LHS: one pseudo-time step of the adjoint).
+        b = None uses the device rhs of the last residual (linearsolver->set_rhs(solution->rhs), solver.cpp:174)."""
+        if matrix not in MATRICES:
+            raise SgpuError("unknown matrix %r" % (matrix,))
+        io = self._linsolve(precond, restart, max_iter, rtol, reorthogonalize)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        x = self._state_array() if want_x else None
+        self._ck(self.L.sgpu_linear_solve(self.h, MATRICES[matrix], None if bb is None else _dp(bb), None if x is None else _dp(x),
+                                          ctypes.byref(io)))
+        return x, self._linsolve_info(io)
+
+    def implicit_step(self, cfl: float, under_relaxation: float = 1.0, precond: str = "line_j", restart: int = 30, max_iter: int = 500,
+                      rtol: float = 1e-10, reorthogonalize: bool = False):
+        """The ENABLE_ADOLC branch of Solver::step, device-resident (solver.cpp:66-101,154-175); returns (l2norm, info)."""
+        io = self._linsolve(precond, restart, max_iter, rtol, reorthogonalize)
+        l2 = np.zeros(self.nv)
+        self._ck(self.L.sgpu_implicit_step(self.h, ctypes.c_double(cfl), ctypes.c_double(under_relaxation), ctypes.byref(io), _dp(l2)))
+        return np.sqrt(l2), self._linsolve_info(io)
 
     def dres_dbeta(self) -> np.ndarray:
         """d rhs4 / d beta per cell at the device state (SA extension; field-inversion gradient building block)"""

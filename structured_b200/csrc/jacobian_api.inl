@@ -231,3 +231,5 @@ int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) 
     cudaFree(xp); cudaFree(yp);
     return rc;
 }
+
+} // extern "C"

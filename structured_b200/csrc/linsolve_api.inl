@@ -1,0 +1,305 @@
+// Host side of the device linear solve and of the device-resident implicit step (included by sgpu_api.cu).
+// Replaces, for a Jacobian that stays on the GPU, the sequence
+//     linearsolver->set_lhs(nnz, rind, cind, values); set_rhs(rhs); solve_and_update(q, UNDER_RELAXATION)
+// of src/solver/solver.cpp:172-175 (src/linearsolver/ls_eigen.cpp:32-70: SparseLU; ls_petsc.cpp: GMRES + LU).
+// Method: restarted GMRES, right-preconditioned (so the monitored residual is the true one), classical
+// Gram-Schmidt with one optional re-orthogonalisation pass, Givens rotations on the host (m x m doubles).
+
+struct LinWork {
+    size_t n = 0;                  // doubles per vector
+    int m = 0;                     // basis capacity (restart length)
+    double* V = nullptr;           // (m+1) basis vectors
+    double *w = nullptr, *z = nullptr, *x = nullptr, *b = nullptr, *u = nullptr;
+    double* Dinv = nullptr;        // block-Jacobi inverse (nv*nv planes) or the line factors Dinv, DA, DC (3*nv*nv planes)
+    double* partial = nullptr;     // [blocks][ldp]
+    double* hdev = nullptr;        // ldp doubles: projections, then norm^2 in the last used column
+    double* ydev = nullptr;        // m doubles
+    double* hhost = nullptr;       // pinned, ldp doubles
+    int* err = nullptr;
+    int blocks = 0, ldp = 0;
+};
+
+static void lin_free(LinWork*& L) {
+    if (!L) return;
+    cudaFree(L->V); cudaFree(L->w); cudaFree(L->z); cudaFree(L->x); cudaFree(L->b); cudaFree(L->u);
+    cudaFree(L->Dinv); cudaFree(L->partial); cudaFree(L->hdev); cudaFree(L->ydev); cudaFree(L->err);
+    if (L->hhost) cudaFreeHost(L->hhost);
+    delete L; L = nullptr;
+}
+
+static int lin_prepare(sgpu_ctx* c, int m) {
+    const View& v = c->v;
+    const size_t n = v.plane*v.nv;
+    LinWork*& L = c->lin;
+    if (L && (L->n != n || L->m < m)) lin_free(L);
+    if (L) return SGPU_OK;
+    L = new LinWork();
+    L->n = n; L->m = m; L->ldp = m + 2;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    L->blocks = 4*sms;
+    const size_t vb = n*sizeof(double);
+    CK(c, cudaMalloc(&L->V, vb*(m + 1)));
+    CK(c, cudaMalloc(&L->w, vb)); CK(c, cudaMalloc(&L->z, vb)); CK(c, cudaMalloc(&L->x, vb)); CK(c, cudaMalloc(&L->b, vb)); CK(c, cudaMalloc(&L->u, vb));
+    CK(c, cudaMalloc(&L->Dinv, 3*v.plane*v.nv*v.nv*sizeof(double)));
+    CK(c, cudaMalloc(&L->partial, (size_t)L->blocks*L->ldp*sizeof(double)));
+    CK(c, cudaMalloc(&L->hdev, L->ldp*sizeof(double))); CK(c, cudaMalloc(&L->ydev, (m + 1)*sizeof(double)));
+    CK(c, cudaMalloc(&L->err, sizeof(int)));
+    CK(c, cudaMallocHost(&L->hhost, L->ldp*sizeof(double)));
+    // ghosts / padding of every vector stay 0 from here on: the kernels either write owned cells only or are flat combinations
+    CK(c, cudaMemsetAsync(L->V, 0, vb*(m + 1), c->stream));
+    for (double* p : {L->w, L->z, L->x, L->b, L->u}) CK(c, cudaMemsetAsync(p, 0, vb, c->stream));
+    CK(c, cudaMemsetAsync(L->Dinv, 0, 3*v.plane*v.nv*v.nv*sizeof(double), c->stream));
+    return SGPU_OK;
+}
+
+static inline bool mat_transposed(int matrix) { return matrix == SGPU_MAT_JT || matrix == SGPU_MAT_LHS_T; }
+static inline int mat_op(int matrix) { return (matrix == SGPU_MAT_LHS || matrix == SGPU_MAT_LHS_T) ? OP_LHS : OP_J; }
+
+// y = A x for matrix in {SGPU_MAT_LHS, SGPU_MAT_J, SGPU_MAT_JT, SGPU_MAT_LHS_T}
+static int lin_apply_op(sgpu_ctx* c, int matrix, const double* x, double* y) {
+    const View& v = c->v;
+    const dim3 grd((v.nic + 127)/128, v.njl);
+    const GhostTable gt = ghost_table_of(c);
+    const bool order2 = c->d.lhs_order == 2;
+    const int op = mat_op(matrix);
+    if (mat_transposed(matrix)) {
+        CK(c, cudaMemsetAsync(y, 0, v.plane*v.nv*sizeof(double), c->stream));
+        if (v.nv == 5) jac_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, 1);
+        else jac_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, 1);
+        if (op == OP_LHS) {
+            CKL(c); c->launches++;
+            if (v.nv == 5) lhs_fixup_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->dt, x, y);
+            else lhs_fixup_kernel<4><<<grd, 128, 0, c->stream>>>(v, c->dt, x, y);
+        }
+    } else if (v.nv == 5) op_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, c->dt, op, x, y);
+    else op_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, c->dt, op, x, y);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+
+static int lin_factor(sgpu_ctx* c, int matrix, int precond) {
+    const View& v = c->v; LinWork* L = c->lin;
+    const int op = mat_op(matrix);
+    CK(c, cudaMemsetAsync(L->err, 0, sizeof(int), c->stream));
+    if (precond == SGPU_PC_LINE_J) {
+        const int nb = (v.nic + 31)/32;
+        if (v.nv == 5) line_factor_kernel<5><<<nb, 32, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err);
+        else line_factor_kernel<4><<<nb, 32, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err);
+    } else {
+        const dim3 grd((v.nic + 127)/128, v.njl);
+        if (v.nv == 5) bj_factor_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, L->Dinv, L->err);
+        else bj_factor_kernel<4><<<grd, 128, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, L->Dinv, L->err);
+    }
+    CKL(c); c->launches++;
+    int e = 0;
+    CK(c, cudaMemcpyAsync(&e, L->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (e) FAIL(c, SGPU_ERR_STATE, "singular diagonal block in the preconditioner");
+    return SGPU_OK;
+}
+
+static int lin_apply_pc(sgpu_ctx* c, int matrix, int precond, const double* r, double* z) {
+    const View& v = c->v; LinWork* L = c->lin;
+    if (precond == SGPU_PC_LINE_J) {
+        const int nb = (v.nic + 31)/32;
+#define LINE_APPLY(NV_, TR_) do { \
+        CK(c, cudaFuncSetAttribute(line_apply_kernel<NV_, TR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)line_ring_bytes<NV_>())); \
+        line_apply_kernel<NV_, TR_><<<nb, 32, line_ring_bytes<NV_>(), c->stream>>>(v, L->Dinv, r, z); } while (0)
+        if (mat_transposed(matrix)) { if (v.nv == 5) LINE_APPLY(5, true); else LINE_APPLY(4, true); }
+        else { if (v.nv == 5) LINE_APPLY(5, false); else LINE_APPLY(4, false); }
+#undef LINE_APPLY
+    } else {
+        const dim3 grd((v.nic + 127)/128, v.njl);
+        const int tr = mat_transposed(matrix);
+        if (v.nv == 5) bj_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, L->Dinv, r, z, tr);
+        else bj_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, L->Dinv, r, z, tr);
+    }
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+
+// out[j0 .. j0+cnt) on the device (L->hdev) = w . V_j ; no synchronisation
+static int lin_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, int j0 = 0) {
+    LinWork* L = c->lin;
+    for (int g = 0; g < cnt; g += DOT_GROUP) {
+        const int k = std::min(DOT_GROUP, cnt - g);
+        dots_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, j0 + g);
+        CKL(c); c->launches++;
+    }
+    return SGPU_OK;
+}
+static int lin_reduce(sgpu_ctx* c, int cnt) {
+    LinWork* L = c->lin;
+    reduce_partials_kernel<<<cnt, 256, 0, c->stream>>>(L->partial, L->blocks, L->ldp, L->hdev);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+static int lin_fetch(sgpu_ctx* c, int cnt) {
+    LinWork* L = c->lin;
+    CK(c, cudaMemcpyAsync(L->hhost, L->hdev, cnt*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+static int lin_norm(sgpu_ctx* c, const double* a, double* out) {
+    if (int rc = lin_dots(c, a, a, 1)) return rc;
+    if (int rc = lin_reduce(c, 1)) return rc;
+    if (int rc = lin_fetch(c, 1)) return rc;
+    *out = std::sqrt(c->lin->hhost[0]);
+    return SGPU_OK;
+}
+
+// Solves A x = b with b in L->b; the solution is left in L->x.
+static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io) {
+    LinWork* L = c->lin;
+    const size_t n = L->n, vb = n*sizeof(double);
+    const int m = std::min(io->restart > 0 ? io->restart : 30, L->m), G = L->blocks;   // L->m is the allocated capacity
+    int precond = io->precond;
+    const int max_iter = io->max_iter > 0 ? io->max_iter : 500;
+    const double rtol = io->rtol > 0 ? io->rtol : 1e-10;
+    cudaEvent_t e0, e1, e2, t0, t1, t2;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1)); CK(c, cudaEventCreate(&e2));
+    CK(c, cudaEventCreate(&t0)); CK(c, cudaEventCreate(&t1)); CK(c, cudaEventCreate(&t2));
+    bool timed = false;
+    io->matvec_ms = io->precond_ms = 0.0f;
+    CK(c, cudaEventRecord(e0, c->stream));
+    if (int rc = lin_factor(c, matrix, precond)) return rc;
+    CK(c, cudaEventRecord(e1, c->stream));
+    CK(c, cudaMemsetAsync(L->x, 0, vb, c->stream));
+    double bnorm = 0.0;
+    if (int rc = lin_norm(c, L->b, &bnorm)) return rc;
+    io->iterations = 0; io->converged = 1; io->rel_residual = 0.0;
+    std::vector<double> H((size_t)(m + 1)*m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
+    double beta = bnorm;
+    int iters = 0;
+    bool first = true;
+    while (bnorm > 0.0) {
+        // r = b - A x  (x = 0 on the first cycle) into w
+        if (first) { CK(c, cudaMemcpyAsync(L->w, L->b, vb, cudaMemcpyDeviceToDevice, c->stream)); first = false; }
+        else {
+            if (int rc = lin_apply_op(c, matrix, L->x, L->w)) return rc;
+            axpby_kernel<<<G, 256, 0, c->stream>>>(L->w, L->b, n, 1.0, -1.0); CKL(c); c->launches++;
+            if (int rc = lin_norm(c, L->w, &beta)) return rc;
+        }
+        io->rel_residual = beta/bnorm;
+        if (beta <= rtol*bnorm || iters >= max_iter) break;
+        // V0 = r/beta
+        if (int rc = lin_dots(c, L->w, L->w, 1)) return rc;
+        if (int rc = lin_reduce(c, 1)) return rc;
+        scale_rsqrt_kernel<<<G, 256, 0, c->stream>>>(L->V, L->w, n, L->hdev); CKL(c); c->launches++;
+        std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
+        int k = 0;
+        bool done = false;
+        for (; k < m && iters < max_iter && !done; k++, iters++) {
+            double* Vk = L->V + (size_t)k*n;
+            const bool tm = !timed && iters == 1;                  // the second application: caches and clocks are warm
+            if (tm) CK(c, cudaEventRecord(t0, c->stream));
+            if (int rc = lin_apply_pc(c, matrix, precond, Vk, L->z)) return rc;
+            if (tm) CK(c, cudaEventRecord(t1, c->stream));
+            if (int rc = lin_apply_op(c, matrix, L->z, L->w)) return rc;
+            if (tm) { CK(c, cudaEventRecord(t2, c->stream)); timed = true; }
+            // classical Gram-Schmidt against V_0..V_k, projections stay on the device for the update
+            if (int rc = lin_dots(c, L->w, L->V, k + 1)) return rc;
+            if (int rc = lin_reduce(c, k + 1)) return rc;
+            gs_update_kernel<<<G, 256, 0, c->stream>>>(L->w, L->V, n, k + 1, L->hdev); CKL(c); c->launches++;
+            std::vector<double> h(k + 2, 0.0);
+            if (io->reorthogonalize) {
+                if (int rc = lin_fetch(c, k + 1)) return rc;
+                for (int j = 0; j <= k; j++) h[j] = L->hhost[j];
+                if (int rc = lin_dots(c, L->w, L->V, k + 1)) return rc;
+                if (int rc = lin_reduce(c, k + 1)) return rc;
+                gs_update_kernel<<<G, 256, 0, c->stream>>>(L->w, L->V, n, k + 1, L->hdev); CKL(c); c->launches++;
+            }
+            // |w|^2 into column k+1, next basis vector scaled from the device value
+            if (int rc = lin_dots(c, L->w, L->w, 1, k + 1)) return rc;
+            reduce_partials_kernel<<<1, 256, 0, c->stream>>>(L->partial + (k + 1), G, L->ldp, L->hdev + (k + 1)); CKL(c); c->launches++;
+            scale_rsqrt_kernel<<<G, 256, 0, c->stream>>>(L->V + (size_t)(k + 1)*n, L->w, n, L->hdev + (k + 1)); CKL(c); c->launches++;
+            if (int rc = lin_fetch(c, k + 2)) return rc;
+            for (int j = 0; j <= k; j++) h[j] += L->hhost[j];
+            h[k + 1] = std::sqrt(L->hhost[k + 1]);
+            // Givens rotations (host, O(m))
+            for (int j = 0; j < k; j++) { const double t = cs[j]*h[j] + sn[j]*h[j + 1]; h[j + 1] = -sn[j]*h[j] + cs[j]*h[j + 1]; h[j] = t; }
+            const double den = std::hypot(h[k], h[k + 1]);
+            if (den == 0.0) { cs[k] = 1.0; sn[k] = 0.0; } else { cs[k] = h[k]/den; sn[k] = h[k + 1]/den; }
+            h[k] = cs[k]*h[k] + sn[k]*h[k + 1];
+            g[k + 1] = -sn[k]*g[k]; g[k] = cs[k]*g[k];
+            for (int j = 0; j <= k; j++) H[(size_t)j*m + k] = h[j];
+            if (std::fabs(g[k + 1]) <= rtol*bnorm || h[k + 1] == 0.0 || !std::isfinite(den)) done = true;
+        }
+        // y from the triangular system, x += M^-1 (V y)
+        for (int j = k - 1; j >= 0; j--) {
+            double s = g[j];
+            for (int l = j + 1; l < k; l++) s -= H[(size_t)j*m + l]*y[l];
+            y[j] = H[(size_t)j*m + j] != 0.0 ? s/H[(size_t)j*m + j] : 0.0;
+        }
+        if (k > 0) {
+            CK(c, cudaMemcpyAsync(L->ydev, y.data(), k*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            combine_kernel<<<G, 256, 0, c->stream>>>(L->u, L->V, n, k, L->ydev); CKL(c); c->launches++;
+            if (int rc = lin_apply_pc(c, matrix, precond, L->u, L->z)) return rc;
+            axpby_kernel<<<G, 256, 0, c->stream>>>(L->x, L->z, n, 1.0, 1.0); CKL(c); c->launches++;
+            CK(c, cudaStreamSynchronize(c->stream));             // y is a host vector reused by the next cycle
+        }
+        if (k == 0) break;
+    }
+    CK(c, cudaEventRecord(e2, c->stream));
+    CK(c, cudaEventSynchronize(e2));
+    cudaEventElapsedTime(&io->setup_ms, e0, e1); cudaEventElapsedTime(&io->solve_ms, e1, e2);
+    if (timed) { cudaEventElapsedTime(&io->precond_ms, t0, t1); cudaEventElapsedTime(&io->matvec_ms, t1, t2); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    io->iterations = iters;
+    io->converged = bnorm == 0.0 || io->rel_residual <= rtol;
+    return SGPU_OK;
+}
+
+static int lin_check(sgpu_ctx* c, int matrix, sgpu_linsolve* io) {
+    if (matrix < SGPU_MAT_LHS || matrix > SGPU_MAT_LHS_T) FAIL(c, SGPU_ERR_ARG, "matrix must be SGPU_MAT_LHS, SGPU_MAT_J, SGPU_MAT_JT or SGPU_MAT_LHS_T");
+    if (io->precond != SGPU_PC_BLOCK_JACOBI && io->precond != SGPU_PC_LINE_J) FAIL(c, SGPU_ERR_ARG, "unknown preconditioner");
+    if (io->restart < 0 || io->restart > SGPU_GMRES_MAX) FAIL(c, SGPU_ERR_ARG, "restart must be in 1..%d", SGPU_GMRES_MAX);
+    if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
+    if (mat_op(matrix) == OP_LHS && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS matrix needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
+    if (c->v.j0 != 0 || c->v.j1 != c->v.njc) FAIL(c, SGPU_ERR_STATE, "the device linear solve drives a whole grid (one GPU); slab-partitioned solves are not built yet");
+    return SGPU_OK;
+}
+
+// host AoS [nic][njc][nv] -> zero-padded planes
+static int upload_planes(sgpu_ctx* c, const double* host, double* planes) {
+    const View& v = c->v;
+    const size_t M = (size_t)v.njl*v.nv;
+    if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
+    CK(c, cudaMemsetAsync(planes, 0, v.plane*v.nv*sizeof(double), c->stream));
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, host + (size_t)v.j0*v.nv, sizeof(double)*v.njc*v.nv, sizeof(double)*M, v.nic, cudaMemcpyHostToDevice, c->stream));
+    aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, planes, JOFF, v.njl);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+
+extern "C" {
+
+int sgpu_linear_solve(sgpu_ctx* c, int matrix, const double* b, double* x, sgpu_linsolve* io) {
+    if (!c || !io) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = lin_check(c, matrix, io)) return rc;
+    if (int rc = lin_prepare(c, io->restart > 0 ? io->restart : 30)) return rc;
+    const View& v = c->v;
+    if (b) { if (int rc = upload_planes(c, b, c->lin->b)) return rc; }
+    else {
+        masked_copy_kernel<<<dim3((v.pitch + 127)/128, v.rows), 128, 0, c->stream>>>(v, c->rhs, c->lin->b);
+        CKL(c); c->launches++;
+    }
+    if (int rc = lin_gmres(c, matrix, io)) return rc;
+    if (x) return download_planes(c, c->lin->x, v.nv, x);
+    return SGPU_OK;
+}
+
+int sgpu_implicit_step(sgpu_ctx* c, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq) {
+    if (!c || !io) return SGPU_ERR_ARG;
+    if (int rc = sgpu_calc_dt(c, cfl)) return rc;                                   // solver.cpp:66
+    if (int rc = sgpu_residual(c, SGPU_STATE_Q, 0, l2sq)) return rc;                // rhs with solver.order (solver.cpp:80-101)
+    if (int rc = jacobian_build(c, nullptr)) return rc;                             // d rhs(lhs_order) / d q  (solver.cpp:80,156)
+    if (int rc = sgpu_linear_solve(c, SGPU_MAT_LHS, nullptr, nullptr, io)) return rc;   // solver.cpp:162-175
+    const size_t n = c->lin->n;
+    axpby_kernel<<<c->lin->blocks, 256, 0, c->stream>>>(c->q[0], c->lin->x, n, under_relaxation, 1.0);   // ls_eigen.cpp:66-70
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,534 @@
+// Device kernels of the matrix-free-storage Krylov solve that replaces src/linearsolver/* on the GPU
+// (reference API: src/linearsolver/ls_eigen.h:26-31, call site src/solver/solver.cpp:172-175).
+//
+// The matrix is never assembled into COO/CSR: the operator works on the block-stencil Jacobian planes
+// J[slot][r][c][cell] that jac_gather_kernel wrote (13 or 9 slots of nv x nv blocks per row cell), and the
+// LHS transform of src/solver/solver.cpp:162-171 (A = -J + delta/dt) is applied on the fly.
+//
+// Vectors are state-plane arrays (nv planes of rows x pitch doubles) whose ghost rows/columns and padding are
+// kept at exactly 0, so the BLAS-1 style kernels below run flat over plane*nv elements, fully coalesced.
+//
+// Roofline: op_apply_kernel streams every Jacobian block once -> (slots*nv*nv + 2*nv + 1)*8 B per cell
+// (2648 B at 13 slots, nv = 5); everything else is O(nv) per cell.  All of it is HBM-bound.
+#pragma once
+#include "jacobian_kernel.cuh"
+
+namespace sg {
+
+enum { OP_J = 0, OP_LHS = 1 };     // A = J   |   A = -J + delta/dt  (what linearsolver->set_lhs receives)
+
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// y = A x, one thread per row cell.  Cells whose whole stencil is interior take the natural-neighbour
+// fast path; the boundary band resolves each slot's column through the ghost table (periodic / wake
+// remaps, folded functional ghosts) exactly like the COO export does.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(128) op_apply_kernel(View v, GhostTable gt, int nslots, bool viscous, bool order2,
+                                                       const double* __restrict__ J, const double* __restrict__ dt, int op,
+                                                       const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const int gj = v.j0 + jl;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    const size_t pl = v.plane;
+    double yr[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) yr[r] = 0.0;
+    const bool inner = i >= 2 && i < v.nic - 2 && gj >= 2 && gj < v.njc - 2;
+    if (inner) {
+#pragma unroll 1
+        for (int s = 0; s < nslots; s++) {
+            if (!viscous && s >= 5 && s <= 8) continue;
+            if (!order2 && s >= 9) continue;
+            const size_t oc = o + (long long)c_slot_dy[s]*v.pitch + c_slot_dx[s];
+            double xs[NV];
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) xs[c2] = x[c2*pl + oc];
+            const double* Js = J + (size_t)s*NV*NV*pl + o;
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c2 = 0; c2 < NV; c2++) yr[r] += ld_stream(Js + (size_t)(r*NV + c2)*pl)*xs[c2];
+        }
+    } else {
+        SlotCols sc; resolve_slots(gt, nslots, i, gj, viscous, order2, sc);
+#pragma unroll 1
+        for (int s = 0; s < nslots; s++) {
+            if (sc.col[s] < 0) continue;
+            const int ci = sc.col[s]/v.njc, cj = sc.col[s] - ci*v.njc;
+            const int rr = cj - v.j0 + JOFF;
+            if (rr < 0 || rr >= v.rows) continue;                  // column outside this slab's planes
+            const size_t oc = v.at(rr, ci + IOFF);
+            double xs[NV];
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) xs[c2] = x[c2*pl + oc];
+            const double* Js = J + (size_t)s*NV*NV*pl + o;
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c2 = 0; c2 < NV; c2++) yr[r] += ld_stream(Js + (size_t)(r*NV + c2)*pl)*xs[c2];
+        }
+    }
+    if (op == OP_LHS) {
+        const double idt = 1.0/dt[o];                              // src/solver/solver.cpp:167-170
+#pragma unroll
+        for (int r = 0; r < NV; r++) yr[r] = x[r*pl + o]*idt - yr[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NV; r++) y[r*pl + o] = yr[r];
+}
+
+// after the scattered J^T x accumulation: y = -y + x/dt on the owned cells
+template <int NV>
+__global__ void lhs_fixup_kernel(View v, const double* __restrict__ dt, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    const double idt = 1.0/dt[o];
+    for (int r = 0; r < NV; r++) y[r*v.plane + o] = x[r*v.plane + o]*idt - y[r*v.plane + o];
+}
+
+// dst = src on the owned cells, 0 on ghosts and padding
+__global__ void masked_copy_kernel(View v, const double* __restrict__ src, double* __restrict__ dst) {
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= v.pitch) return;
+    const bool own = c >= IOFF && c < IOFF + v.nic && r >= JOFF && r < JOFF + v.njl;
+    const size_t o = v.at(r, c);
+    for (int k = 0; k < v.nv; k++) dst[k*v.plane + o] = own ? src[k*v.plane + o] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nv x nv inverse in registers: Gauss-Jordan with partial pivoting, every index a compile-time constant.
+// Returns false when a pivot is exactly zero.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ bool invert_block(double (&a)[NV][NV], double (&b)[NV][NV]) {
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) b[r][c] = r == c ? 1.0 : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        int p = k; double big = fabs(a[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < NV; r++) { const double t = fabs(a[r][k]); if (t > big) { big = t; p = r; } }
+#pragma unroll
+        for (int r = k + 1; r < NV; r++)
+            if (r == p) {
+#pragma unroll
+                for (int c = 0; c < NV; c++) { double t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; t = b[k][c]; b[k][c] = b[r][c]; b[r][c] = t; }
+            }
+        if (a[k][k] == 0.0) { ok = false; a[k][k] = 1.0; }
+        const double ip = 1.0/a[k][k];
+#pragma unroll
+        for (int c = 0; c < NV; c++) { a[k][c] *= ip; b[k][c] *= ip; }
+#pragma unroll
+        for (int r = 0; r < NV; r++) {
+            if (r == k) continue;
+            const double f = a[r][k];
+#pragma unroll
+            for (int c = 0; c < NV; c++) { a[r][c] -= f*a[k][c]; b[r][c] -= f*b[k][c]; }
+        }
+    }
+    return ok;
+}
+
+template <int NV>
+__device__ __forceinline__ void load_block(const double* __restrict__ J, size_t pl, size_t o, int s, int op, double idt, bool diag, double (&a)[NV][NV]) {
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            const double vj = J[((size_t)s*NV*NV + r*NV + c)*pl + o];
+            a[r][c] = op == OP_LHS ? ((diag && r == c) ? idt - vj : -vj) : vj;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-Jacobi preconditioner: Dinv = (diagonal block of A)^-1 per cell, stored as nv*nv planes
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void bj_factor_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, double* __restrict__ Dinv, int* __restrict__ err) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    double a[NV][NV], b[NV][NV];
+    load_block<NV>(J, v.plane, o, 0, op, op == OP_LHS ? 1.0/dt[o] : 0.0, true, a);
+    if (!invert_block<NV>(a, b)) atomicExch(err, 1);
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) Dinv[(size_t)(r*NV + c)*v.plane + o] = b[r][c];
+}
+
+// z = Dinv r (transpose = 0) or Dinv^T r (transpose = 1) on the owned cells
+template <int NV>
+__global__ void bj_apply_kernel(View v, const double* __restrict__ Dinv, const double* __restrict__ rv, double* __restrict__ z, int transpose) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    double xs[NV], zr[NV];
+#pragma unroll
+    for (int c = 0; c < NV; c++) { xs[c] = rv[c*v.plane + o]; zr[c] = 0.0; }
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            const double a = ld_stream(Dinv + (size_t)(r*NV + c)*v.plane + o);
+            if (!transpose) zr[r] += a*xs[c]; else zr[c] += a*xs[r];
+        }
+#pragma unroll
+    for (int r = 0; r < NV; r++) z[r*v.plane + o] = zr[r];
+}
+
+// ------------------------------------------------------------------------------------------------
+// j-line preconditioner: block-tridiagonal solve along each grid line i = const (the wall-normal, strongly
+// coupled direction of a boundary-layer grid).  One thread per line, block Thomas algorithm.
+// Line blocks: sub-diagonal A' = slot 3 (0,-1) + slot 11 (0,-2), diagonal slot 0, super-diagonal
+// C' = slot 4 (0,+1) + slot 12 (0,+2).  LUMPING the radius-2 arms of a second-order Jacobian onto their
+// radius-1 neighbours matters: the bare tridiagonal part of the kappa = 1/3 MUSCL stencil is not a usable
+// approximation of the line operator (the preconditioned spectrum reaches into the left half plane),
+// the lumped one clusters it in [0.27, 2.2] like the exact pentadiagonal line solve would.
+// Couplings that leave the line's natural neighbours (bottom/top ghosts -- already folded into the interior
+// slots -- or periodic/wake remaps) are not part of the preconditioner.
+// Stored factors (3 x nv*nv planes): Dinv = D'^-1, DA = D'^-1 A', DC = D'^-1 C' with
+//     D'_j = D_j - A'_j DC_{j-1}
+// so that both sweeps have ONE dependent nv x nv product per row on the critical path.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void matmul_block(const double (&a)[NV][NV], const double (&b)[NV][NV], double (&c)[NV][NV]) {
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int cc = 0; cc < NV; cc++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < NV; k++) s += a[r][k]*b[k][cc];
+            c[r][cc] = s;
+        }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, int nslots,
+                                                         double* __restrict__ F, int* __restrict__ err) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= v.nic) return;
+    const size_t pl = v.plane;
+    double* __restrict__ Dinv = F;
+    double* __restrict__ DA = F + (size_t)NV*NV*pl;
+    double* __restrict__ DC = F + (size_t)2*NV*NV*pl;
+    const bool arms = nslots > 9;
+    double DCp[NV][NV];                                            // DC_{j-1}
+    for (int jl = 0; jl < v.njl; jl++) {
+        const int gj = v.j0 + jl;
+        const size_t o = v.at(jl + JOFF, i + IOFF);
+        double D[NV][NV], A[NV][NV], T[NV][NV], I[NV][NV];
+        load_block<NV>(J, pl, o, 0, op, op == OP_LHS ? 1.0/dt[o] : 0.0, true, D);
+        const bool lo = jl > 0, hi = jl + 1 < v.njl;
+        if (lo) {
+            load_block<NV>(J, pl, o, 3, op, 0.0, false, A);
+            if (arms && gj - 2 >= 0) {
+                load_block<NV>(J, pl, o, 11, op, 0.0, false, T);
+#pragma unroll
+                for (int r = 0; r < NV; r++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) A[r][c] += T[r][c];
+            }
+            matmul_block<NV>(A, DCp, T);
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) D[r][c] -= T[r][c];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) A[r][c] = 0.0;
+        }
+        if (!invert_block<NV>(D, I)) atomicExch(err, 1);
+        matmul_block<NV>(I, A, T);
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DA[(size_t)(r*NV + c)*pl + o] = T[r][c]; }
+        if (hi) {
+            load_block<NV>(J, pl, o, 4, op, 0.0, false, A);
+            if (arms && gj + 2 <= v.njc - 1) {
+                load_block<NV>(J, pl, o, 12, op, 0.0, false, T);
+#pragma unroll
+                for (int r = 0; r < NV; r++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) A[r][c] += T[r][c];
+            }
+            matmul_block<NV>(I, A, DCp);
+        } else {
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) DCp[r][c] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) DC[(size_t)(r*NV + c)*pl + o] = DCp[r][c];
+    }
+}
+
+// z = M^-1 r:  forward  t_j = Dinv_j r_j - DA_j t_{j-1},  backward  z_j = t_j - DC_j z_{j+1}.
+// transpose (M = L U with L = blockdiag(D') + lower(A'), U = I + upper(DC), so M^T = U^T L^T):
+//           forward  y_j = r_j - DC_{j-1}^T y_{j-1},  backward  w_j = y_j - DA_{j+1}^T w_{j+1},  z_j = Dinv_j^T w_j.
+//
+// The recurrence is sequential in j, so the kernel is latency- not bandwidth-limited unless the rows ahead are
+// already on chip: one warp owns 32 adjacent lines and streams the rows it is about to need through a
+// LINE_STAGES-deep shared-memory ring with cp.async (LDGSTS), each lane copying exactly the 8-byte words it
+// will read itself -- so no barrier is needed, only cp.async.wait_group -- and every global access is a
+// coalesced 256-byte row segment per plane.
+constexpr int LINE_STAGES = 12;
+
+__device__ __forceinline__ void cp_async8(double* smem, const double* g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int NV> constexpr int line_ring_planes() { return 2*NV*NV + NV; }
+template <int NV> constexpr size_t line_ring_bytes() { return (size_t)LINE_STAGES*line_ring_planes<NV>()*32*sizeof(double); }
+
+template <int NV, bool TR>
+__global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __restrict__ F, const double* __restrict__ rv, double* __restrict__ z) {
+    extern __shared__ double ring[];
+    constexpr int B = NV*NV, NP = 2*NV*NV + NV, S = LINE_STAGES;
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x*32 + lane;
+    const bool live = i < v.nic;
+    const int ic = live ? i : v.nic - 1;                           // idle lanes shadow the last line and never store
+    const size_t pl = v.plane;
+    const double* __restrict__ Dinv = F;
+    const double* __restrict__ DA = F + (size_t)B*pl;
+    const double* __restrict__ DC = F + (size_t)2*B*pl;
+    auto slot = [&](int st, int p) -> double* { return ring + ((size_t)st*NP + p)*32 + lane; };
+    double t[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) t[r] = 0.0;
+
+    // ---- sweep 1: rows ascending
+    {
+        const double* __restrict__ P0 = TR ? DC : Dinv;            // first nv*nv planes of a stage
+        auto issue = [&](int jl) {
+            if (jl < v.njl) {
+                const size_t o = v.at(jl + JOFF, ic + IOFF);
+                const int st = jl % S;
+#pragma unroll
+                for (int e = 0; e < B; e++) cp_async8(slot(st, e), P0 + (size_t)e*pl + o);
+                if (!TR) {
+#pragma unroll
+                    for (int e = 0; e < B; e++) cp_async8(slot(st, B + e), DA + (size_t)e*pl + o);
+                }
+#pragma unroll
+                for (int k = 0; k < NV; k++) cp_async8(slot(st, 2*B + k), rv + (size_t)k*pl + o);
+            }
+            cp_async_commit();
+        };
+        for (int jl = 0; jl < S - 1; jl++) issue(jl);
+        for (int jl = 0; jl < v.njl; jl++) {
+            issue(jl + S - 1);
+            cp_async_wait<S - 1>();
+            const int st = jl % S;
+            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            double g[NV];
+            if (!TR) {
+                double rr[NV];
+#pragma unroll
+                for (int r = 0; r < NV; r++) rr[r] = *slot(st, 2*B + r);
+#pragma unroll
+                for (int r = 0; r < NV; r++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NV; c++) s += *slot(st, r*NV + c)*rr[c];
+                    g[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < NV; r++) {
+                    double s = g[r];
+#pragma unroll
+                    for (int c = 0; c < NV; c++) s -= *slot(st, B + r*NV + c)*t[c];
+                    g[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < NV; r++) t[r] = g[r];
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NV; r++) g[r] = *slot(st, 2*B + r) - t[r];
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
+                }
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NV; r++) s += *slot(st, r*NV + c)*g[r];
+                    t[c] = s;
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    __syncwarp();                                                  // z rows written above are re-read below by the same lane only
+
+    // ---- sweep 2: rows descending
+    {
+        const double* __restrict__ P0 = TR ? DA : DC;
+        const int jtop = TR ? v.njl - 1 : v.njl - 2;               // the untransposed last row is already final (t holds it)
+        if (TR) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) t[r] = 0.0;
+        }
+        auto issue = [&](int n) {                                  // n-th row of this sweep = row jtop - n
+            const int jl = jtop - n;
+            if (jl >= 0) {
+                const size_t o = v.at(jl + JOFF, ic + IOFF);
+                const int st = n % S;
+#pragma unroll
+                for (int e = 0; e < B; e++) cp_async8(slot(st, e), P0 + (size_t)e*pl + o);
+                if (TR) {
+#pragma unroll
+                    for (int e = 0; e < B; e++) cp_async8(slot(st, B + e), Dinv + (size_t)e*pl + o);
+                }
+#pragma unroll
+                for (int k = 0; k < NV; k++) cp_async8(slot(st, 2*B + k), z + (size_t)k*pl + o);
+            }
+            cp_async_commit();
+        };
+        for (int n = 0; n < S - 1; n++) issue(n);
+        for (int n = 0; n <= jtop; n++) {
+            issue(n + S - 1);
+            cp_async_wait<S - 1>();
+            const int st = n % S;
+            const int jl = jtop - n;
+            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            double g[NV];
+            if (!TR) {
+#pragma unroll
+                for (int r = 0; r < NV; r++) {
+                    double s = *slot(st, 2*B + r);
+#pragma unroll
+                    for (int c = 0; c < NV; c++) s -= *slot(st, r*NV + c)*t[c];
+                    g[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < NV; r++) t[r] = g[r];
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
+                }
+            } else {
+                double w[NV];
+#pragma unroll
+                for (int r = 0; r < NV; r++) w[r] = *slot(st, 2*B + r) - t[r];
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NV; r++) s += *slot(st, r*NV + c)*w[r];
+                    t[c] = s;
+                }
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NV; r++) s += *slot(st, B + r*NV + c)*w[r];
+                    g[c] = s;
+                }
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flat vector kernels (n = plane*nv elements; ghosts/padding are zero in every operand)
+// ------------------------------------------------------------------------------------------------
+constexpr int DOT_GROUP = 8;
+constexpr int DOT_THREADS = 256;
+
+// partial[block][ldp] at columns j0..j0+cnt-1  =  this block's share of  w . V_j
+__global__ void __launch_bounds__(DOT_THREADS) dots_kernel(const double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt,
+                                                           double* __restrict__ partial, int ldp, int j0) {
+    double acc[DOT_GROUP];
+#pragma unroll
+    for (int j = 0; j < DOT_GROUP; j++) acc[j] = 0.0;
+    const size_t stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
+        const double we = w[e];
+#pragma unroll
+        for (int j = 0; j < DOT_GROUP; j++) if (j < cnt) acc[j] += we*V[(size_t)j*n + e];
+    }
+    __shared__ double ws[DOT_GROUP][DOT_THREADS/32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < DOT_GROUP; j++) {
+        double s = acc[j];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) ws[j][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        double s = 0.0;
+        for (int k = 0; k < DOT_THREADS/32; k++) s += ws[threadIdx.x][k];
+        partial[(size_t)blockIdx.x*ldp + j0 + threadIdx.x] = s;
+    }
+}
+
+// w -= sum_j h[j] V_j   (h on the device: no host round trip between the projection and the update)
+__global__ void gs_update_kernel(double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ h) {
+    const size_t stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
+        double s = w[e];
+        for (int j = 0; j < cnt; j++) s -= h[j]*V[(size_t)j*n + e];
+        w[e] = s;
+    }
+}
+
+// dst = src * (1/sqrt(*normsq))
+__global__ void scale_rsqrt_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n, const double* __restrict__ normsq) {
+    const double sc = 1.0/sqrt(*normsq);
+    const size_t stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) dst[e] = src[e]*sc;
+}
+
+// dst = sum_j y[j] V_j  (y passed by value through a small device array)
+__global__ void combine_kernel(double* __restrict__ dst, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ y) {
+    const size_t stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
+        double s = 0.0;
+        for (int j = 0; j < cnt; j++) s += y[j]*V[(size_t)j*n + e];
+        dst[e] = s;
+    }
+}
+
+// y = a*x + b*y
+__global__ void axpby_kernel(double* __restrict__ y, const double* __restrict__ x, size_t n, double a, double b) {
+    const size_t stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) y[e] = a*x[e] + b*y[e];
+}
+
+} // namespace sg

@@ -14,10 +14,14 @@
 #include "aux_kernels.cuh"
 #include "residual_kernel.cuh"
 #include "jacobian_kernel.cuh"
+#include "linsolve_kernels.cuh"
 
 using namespace sg;
 
 static thread_local std::string g_create_error;
+
+struct LinWork;
+static void lin_free(LinWork*& L);
 
 struct sgpu_ctx {
     sgpu_desc d{};
@@ -43,6 +47,7 @@ struct sgpu_ctx {
     bool halo_peer_ipc[2] = {false, false};
     unsigned long long halo_seq = 0;
     JacStore jac{};
+    LinWork* lin = nullptr;              // device linear solve workspace (linsolve_api.inl)
     // pipelined host path
     bool pipe_init = false;
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
@@ -178,6 +183,7 @@ int sgpu_destroy(sgpu_ctx* c) {
         if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) if (c->halo_peer_ipc[k] && c->halo_peer[k]) cudaIpcCloseMemHandle(c->halo_peer[k]);
     jac_free(c->jac);
+    lin_free(c->lin);
     if (c->jac_scratch) cudaFree(c->jac_scratch);
     for (int k = 0; k < 4; k++) if (c->pipe_stage[k]) cudaFree(c->pipe_stage[k]);
     if (c->pipe_init) {
@@ -790,5 +796,5 @@ int sgpu_kernel_times(sgpu_ctx* c, float* ms, int n) {
 
 // ---------------------------------------------------------------------------------------------- Jacobian
 #include "jacobian_api.inl"
-
-} // extern "C"
+// ---------------------------------------------------------------------------------------------- linear solve
+#include "linsolve_api.inl"

@@ -83,3 +83,31 @@ def test_implicit_dropin_with_reference_eigen_solver(tmp_path):
     h = 0.5 * (z["yv"][0, -1] - z["yv"][0, 0])
     u_max = -c.dpdx * h * h / (2.0 * c.mu_inf)
     assert abs(u.max() - u_max) <= 0.02 * u_max
+
+
+BIN_IMPLICIT_DEVICE = os.path.join(ROOT, "integration", "structured_gpu_implicit_device")
+
+
+@pytest.mark.skipif(not (os.path.exists(BIN_IMPLICIT) and os.path.exists(BIN_IMPLICIT_DEVICE)),
+                    reason="integration/structured_gpu_implicit[_device] not built (needs /root/reference at build time)")
+def test_device_resident_implicit_dropin_matches_the_eigen_lu_dropin(tmp_path):
+    """Same implicit run twice: (a) sgpu_jacobian_coo + the reference's LinearSolverEigen (exact LU) and (b) the whole
+    step on the device (sgpu_implicit_step: block-stencil Jacobian + GMRES, no COO, no host solver)."""
+    case, z = golden("channel")
+    n_it = 40
+    inp = (str(z["inp"]).replace("iteration_max = 100", "iteration_max = %d" % n_it)
+           .replace("stdout_frequency = 1", "stdout_frequency = 1000").replace("fileout_frequency = 1", "fileout_frequency = 100000"))
+    t = tomllib.loads(inp)
+    qs = []
+    for k, binary in enumerate((BIN_IMPLICIT, BIN_IMPLICIT_DEVICE)):
+        d = tmp_path / ("run%d" % k)
+        d.mkdir()
+        write_grid_p3d(str(d / os.path.basename(t["geometry"]["filename"])), z["xv"], z["yv"])
+        (d / "run.inp").write_text(inp)
+        res = subprocess.run([binary, "-c", "run.inp"], cwd=d, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+        assert "GMRES stopped" not in res.stdout + res.stderr
+        qs.append(np.load(d / (t["io"]["label"] + ".npz"))["q"])
+    err = field_rel_err(qs[1], qs[0])
+    err[2] = np.abs(qs[1][..., 2] - qs[0][..., 2]).max() / np.abs(qs[0][..., 1]).max()
+    assert err.max() <= 1e-8, err
