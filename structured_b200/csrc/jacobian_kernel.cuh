@@ -85,9 +85,8 @@ struct CellD {
 };
 
 template <int NV, bool VISC>
-__device__ __forceinline__ void load_cell(const View& v, const Gas& g, const double* __restrict__ q, int r, int c, CellD<NV>& w) {
-    const size_t o = v.at(r, c);
-    cons_to_prim<double>(g, q[o], q[v.plane + o], q[2*v.plane + o], q[3*v.plane + o], w.r, w.u, w.v, w.p, w.T);
+__device__ __forceinline__ void cell_from_q(const Gas& g, double q0, double q1, double q2, double q3, double q4, CellD<NV>& w) {
+    cons_to_prim<double>(g, q0, q1, q2, q3, w.r, w.u, w.v, w.p, w.T);
     w.ri = rcp_fast(w.r);
     const double ke = 0.5*(w.u*w.u + w.v*w.v), iR = 1.0/g.R;
     // T = p/(rho R):  dT = (dp - p/rho drho)/(rho R)
@@ -102,7 +101,7 @@ __device__ __forceinline__ void load_cell(const View& v, const Gas& g, const dou
         for (int k = 0; k < 4; k++) w.dmu[k] = dmudT*w.dT[k];
     }
     if (NV > 4) {
-        w.rn = q[4*v.plane + o];
+        w.rn = q4;
         w.nut = w.rn*w.ri;
         const double chi = w.rn*rcp_fast(w.mu), c3 = SA_CV1*SA_CV1*SA_CV1, x3 = chi*chi*chi, den = rcp_fast(x3 + c3);
         const double fv1 = x3*den, dfv1 = 3.0*chi*chi*c3*den*den;
@@ -111,6 +110,19 @@ __device__ __forceinline__ void load_cell(const View& v, const Gas& g, const dou
 #pragma unroll
         for (int k = 0; k < 4; k++) w.dmut[k] = -chi*chi*dfv1*w.dmu[k];
     }
+}
+
+template <int NV, bool VISC>
+__device__ __forceinline__ void load_cell(const View& v, const Gas& g, const double* __restrict__ q, int r, int c, CellD<NV>& w) {
+    const size_t o = v.at(r, c);
+    cell_from_q<NV, VISC>(g, q[o], q[v.plane + o], q[2*v.plane + o], q[3*v.plane + o], NV > 4 ? q[4*v.plane + o] : 0.0, w);
+}
+// the same from the face kernel's shared-memory staging: sq[(n*NV + k)*FACE_THREADS] = q_k of stencil cell n (own thread's column)
+constexpr int FACE_THREADS = 128;
+template <int NV, bool VISC>
+__device__ __forceinline__ void load_cell_staged(const Gas& g, const double* sq, int n, CellD<NV>& w) {
+    const double* p = sq + (size_t)n*NV*FACE_THREADS;
+    cell_from_q<NV, VISC>(g, p[0], p[FACE_THREADS], p[2*FACE_THREADS], p[3*FACE_THREADS], NV > 4 ? p[4*FACE_THREADS] : 0.0, w);
 }
 
 // rows of dW/dq (W = rho,u,v,p) and of dz/dq (z = u,v,T,mu,mut,nut,rn) applied to a coefficient vector:
@@ -157,26 +169,30 @@ struct CellRef { int r, c; };
 
 template <int NV, int ORDER, int FLUX, bool VISC, int NL>
 __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const double* __restrict__ q, const FaceGeom& fg, double eps,
-                                            const CellRef* cr, bool Lint, bool Rint, double* __restrict__ S, size_t fo) {
+                                            const CellRef* cr, bool Lint, bool Rint, double* __restrict__ S, size_t fo, double* sq) {
     constexpr bool SA = NV > 4;
     const size_t stride = v.plane;
-    // the eight stencil cells are each loaded twice below (aggregates, then blocks): pull their lines into L1 now so
-    // that the later dependent loads cost an L1 hit instead of an exposed L2/HBM round trip
+    // the eight stencil cells are each used twice below (aggregates, then blocks) inside rolled loops: all 8*nv words
+    // are requested at once with cp.async into this thread's shared-memory column (no registers, full memory-level
+    // parallelism), so the dependent loads further down cost a shared-memory hit instead of an L2/HBM round trip
 #pragma unroll
     for (int n = 0; n < 8; n++) {
         const size_t o = v.at(cr[n].r, cr[n].c);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sq + (size_t)n*NV*FACE_THREADS);
 #pragma unroll
-        for (int k = 0; k < NV; k++) asm volatile("prefetch.global.L1 [%0];" :: "l"(q + k*stride + o));
+        for (int k = 0; k < NV; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + k*FACE_THREADS*8), "l"(q + k*stride + o));
     }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // ---- 1. primitives of the line cells, reconstruction and its derivative scalars
     double W[4][4];                               // [LL,L,R,RR][rho,u,v,p]
 #pragma unroll
     for (int n = 0; n < 4; n++) {
         const bool need = (n == 1 || n == 2) || (ORDER == 2 && ((n == 0 && Lint) || (n == 3 && Rint)));
         if (need) {
-            const size_t o = v.at(cr[n].r, cr[n].c);
+            const double* p = sq + (size_t)n*NV*FACE_THREADS;
             double T;
-            cons_to_prim<double>(g, q[o], q[stride + o], q[2*stride + o], q[3*stride + o], W[n][0], W[n][1], W[n][2], W[n][3], T);
+            cons_to_prim<double>(g, p[0], p[FACE_THREADS], p[2*FACE_THREADS], p[3*FACE_THREADS], W[n][0], W[n][1], W[n][2], W[n][3], T);
         } else { W[n][0] = W[n][1] = W[n][2] = W[n][3] = 1.0; }
     }
     double ql[4], qr[4], dl[4][3], dr[4][3];      // dl[k] = d ql_k / d(LL_k, L_k, R_k); dr[k] = d qr_k / d(L_k, R_k, RR_k)
@@ -237,7 +253,7 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
         for (int n = 1; n < 8; n++) {
             if (n == 3) continue;
             if (!VISC && n > 2) break;
-            CellD<NV> w; load_cell<NV, VISC>(v, g, q, cr[n].r, cr[n].c, w);
+            CellD<NV> w; load_cell_staged<NV, VISC>(g, sq, n, w);
             const double z[7] = {w.u, w.v, w.T, w.mu, w.mut, w.nut, w.rn};
             double* dst = n == 1 ? sD0 : (n == 2 ? sD1 : (n < 6 ? sP : sM));
 #pragma unroll
@@ -278,7 +294,7 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
     const double nut_up = SA ? (upL ? nutL : nutR) : 0.0;
     // ---- 4. one block per stencil cell: inviscid part (line cells) + viscous part (dual-cell cells)
     const double qx = 0.25*(fg.tx - fg.bx), qy = 0.25*(fg.ty - fg.by);
-#pragma unroll 1
+#pragma unroll
     for (int n = 0; n < 8; n++) {
         const bool line = n < 4, dual = VISC && (n == 1 || n == 2 || n >= 4);
         const bool used = (line && ((n == 1 || n == 2) || (ORDER == 2 && ((n == 0 && Lint) || (n == 3 && Rint))))) || dual;
@@ -286,7 +302,7 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
 #pragma unroll
         for (int e = 0; e < NV*NV; e++) blk[e] = 0.0;
         if (used) {
-            CellD<NV> cs; load_cell<NV, VISC>(v, g, q, cr[n].r, cr[n].c, cs);
+            CellD<NV> cs; load_cell_staged<NV, VISC>(g, sq, n, cs);
             const int il = n == 0 ? 0 : (n == 1 ? 1 : (n == 2 ? 2 : -1));      // which dl[k][.] belongs to this cell
             const int ir = n == 1 ? 0 : (n == 2 ? 1 : (n == 3 ? 2 : -1));      // which dr[k][.]
             double wx = 0, wy = 0, wb = 0;
@@ -343,8 +359,10 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
 
 // DIR = 0: chi faces (i in [0, nic], owned rows); DIR = 1: eta faces (rows j0 .. j1)
 template <int NV, int ORDER, int FLUX, bool VISC, int DIR>
-__global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
+__global__ void __launch_bounds__(FACE_THREADS) jac_face_kernel(const JacParams prm) {
     constexpr int NL = 2;
+    __shared__ double s_stage[8*NV*FACE_THREADS];                 // q of the eight stencil cells, one column per thread
+    double* sq = s_stage + threadIdx.x;
     const View& v = prm.v; const Metrics& m = prm.m;
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     const int jl = blockIdx.y;
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
         cr[0] = {r, imax(cL0 - 1, 0)}; cr[1] = {r, cL0}; cr[2] = {r, cL0 + 1}; cr[3] = {r, imin(cL0 + 2, v.pitch - 1)};
         cr[4] = {r + 1, cL0}; cr[5] = {r + 1, cL0 + 1}; cr[6] = {r - 1, cL0}; cr[7] = {r - 1, cL0 + 1};
         const bool Lint = i - 1 >= 0, Rint = i <= v.nic - 1;
-        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_chi, cr, Lint, Rint, prm.Schi, v.at(r, cf));
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_chi, cr, Lint, Rint, prm.Schi, v.at(r, cf), sq);
     } else {
         if (i >= v.nic || jl > v.njl) return;
         const int fj = v.j0 + jl;                                  // global eta-face index; L = cell row fj-1, R = cell row fj
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(128) jac_face_kernel(const JacParams prm) {
         cr[0] = {imax(rL - 1, 0), c}; cr[1] = {rL, c}; cr[2] = {rL + 1, c}; cr[3] = {imin(rL + 2, v.rows - 1), c};
         cr[4] = {rL, c + 1}; cr[5] = {rL + 1, c + 1}; cr[6] = {rL, c - 1}; cr[7] = {rL + 1, c - 1};
         const bool Lint = fj - 1 >= 0, Rint = fj <= v.njc - 1;
-        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_eta, cr, Lint, Rint, prm.Seta, v.at(rf, c));
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_eta, cr, Lint, Rint, prm.Seta, v.at(rf, c), sq);
     }
 }
 
