@@ -79,7 +79,9 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
         CK(c, cudaMalloc(&c->jac.blocks, need*sizeof(double)));
         c->jac.cap = need;
     }
-    const size_t need_s = (size_t)2*8*v.nv*v.nv*v.plane;           // per-face scratch: chi and eta, 8 stencil cells each
+    const int stiles = (v.pitch + STILE - 1)/STILE;
+    const size_t dir_s = (size_t)(v.rows + 1)*stiles*STILE*8*v.nv*v.nv;   // per-face scratch of one direction: 8 stencil cells each
+    const size_t need_s = 2*dir_s;
     if (need_s > c->jac_scratch_cap) {
         if (c->jac_scratch) CK(c, cudaFree(c->jac_scratch));
         c->jac_scratch = nullptr; c->jac_scratch_cap = 0;
@@ -92,7 +94,7 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
     JacParams p;
     p.v = v; p.g = c->g; p.m = metrics_of(c); p.gt = ghost_table_of(c);
     p.q = c->q[0]; p.J = c->jac.blocks; p.wdist = c->wdist; p.beta = c->beta;
-    p.Schi = c->jac_scratch; p.Seta = c->jac_scratch + (size_t)8*v.nv*v.nv*v.plane;
+    p.Schi = c->jac_scratch; p.Seta = c->jac_scratch + dir_s; p.stiles = stiles;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.nslots = nslots; p.err = c->jac_err;
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));

@@ -152,7 +152,8 @@ __device__ __forceinline__ void chain_Z(const CellD<NV>& w, double cu, double cv
 struct JacParams {
     View v; Gas g; Metrics m; GhostTable gt;
     const double* q; double* J;
-    double* Schi; double* Seta;          // per-face scratch: S[cellidx(8)][r][c][face plane]
+    double* Schi; double* Seta;          // per-face scratch, tiled: S[row][tile of 32 faces][cell(8)*nv*nv + e][32]
+    int stiles;                          // tiles per row
     const double* wdist; const double* beta;
     double eps_chi, eps_eta;
     int nslots;
@@ -166,6 +167,15 @@ struct JacParams {
 //                vertex averages                          (src/utils/mesh.cpp:44-53, 93-98)
 // fg.t*/b* are the doubled normals of the plus/minus sides, fg.r*/l* those of D1/D0.
 struct CellRef { int r, c; };
+
+// Scratch layout: the whole record set of 32 adjacent faces of a row (8 blocks x nv*nv entries) is ONE contiguous
+// 8*nv*nv*256-byte run, so a warp of the face kernel writes -- and a warp of the gather kernel reads -- long
+// sequential DRAM bursts instead of 200 chunks of 256 bytes that lie a whole plane apart.
+constexpr int STILE = 32;
+template <int NV>
+__device__ __forceinline__ size_t scratch_off(int stiles, int row, int col) {
+    return ((size_t)row*stiles + (col >> 5))*(size_t)(8*NV*NV*STILE) + (col & 31);
+}
 
 template <int NV, int ORDER, int FLUX, bool VISC, int NL>
 __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const double* __restrict__ q, const FaceGeom& fg, double eps,
@@ -351,9 +361,9 @@ __device__ __forceinline__ void face_blocks(const View& v, const Gas& g, const d
                 for (int c2 = 0; c2 < NV; c2++) blk[r*NV + c2] = out[c2];
             }
         }
-        double* p = S + ((size_t)n*NV*NV)*stride + fo;
+        double* p = S + (size_t)n*NV*NV*STILE + fo;
 #pragma unroll
-        for (int e = 0; e < NV*NV; e++) p[e*stride] = blk[e];
+        for (int e = 0; e < NV*NV; e++) p[e*STILE] = blk[e];
     }
 }
 
@@ -384,7 +394,7 @@ __global__ void __launch_bounds__(FACE_THREADS) jac_face_kernel(const JacParams 
         cr[0] = {r, imax(cL0 - 1, 0)}; cr[1] = {r, cL0}; cr[2] = {r, cL0 + 1}; cr[3] = {r, imin(cL0 + 2, v.pitch - 1)};
         cr[4] = {r + 1, cL0}; cr[5] = {r + 1, cL0 + 1}; cr[6] = {r - 1, cL0}; cr[7] = {r - 1, cL0 + 1};
         const bool Lint = i - 1 >= 0, Rint = i <= v.nic - 1;
-        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_chi, cr, Lint, Rint, prm.Schi, v.at(r, cf), sq);
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_chi, cr, Lint, Rint, prm.Schi, scratch_off<NV>(prm.stiles, r, cf), sq);
     } else {
         if (i >= v.nic || jl > v.njl) return;
         const int fj = v.j0 + jl;                                  // global eta-face index; L = cell row fj-1, R = cell row fj
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(FACE_THREADS) jac_face_kernel(const JacParams 
         cr[0] = {imax(rL - 1, 0), c}; cr[1] = {rL, c}; cr[2] = {rL + 1, c}; cr[3] = {imin(rL + 2, v.rows - 1), c};
         cr[4] = {rL, c + 1}; cr[5] = {rL + 1, c + 1}; cr[6] = {rL, c - 1}; cr[7] = {rL + 1, c - 1};
         const bool Lint = fj - 1 >= 0, Rint = fj <= v.njc - 1;
-        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_eta, cr, Lint, Rint, prm.Seta, v.at(rf, c), sq);
+        face_blocks<NV, ORDER, FLUX, VISC, NL>(v, prm.g, prm.q, fg, prm.eps_eta, cr, Lint, Rint, prm.Seta, scratch_off<NV>(prm.stiles, rf, c), sq);
     }
 }
 
@@ -494,7 +504,8 @@ __global__ void __launch_bounds__(128) jac_gather_kernel(const JacParams prm) {
     const int gj = v.j0 + jl;
     const size_t o = v.at(r, c), pl = v.plane;
     const double V = m.vol[o], Vi = 1.0/V;
-    const size_t fo[4] = {o, v.at(r, c + 1), o, v.at(r + 1, c)};
+    const size_t fo[4] = {scratch_off<NV>(prm.stiles, r, c), scratch_off<NV>(prm.stiles, r, c + 1),
+                          scratch_off<NV>(prm.stiles, r, c), scratch_off<NV>(prm.stiles, r + 1, c)};
 
     // SA source sensitivities (3x3 block, row 4 only)
     double Wx[3][3], Wy[3][3], Sd[6] = {0, 0, 0, 0, 0, 0}, sgn = 1.0;
@@ -566,7 +577,7 @@ __global__ void __launch_bounds__(128) jac_gather_kernel(const JacParams prm) {
                 if (ORDER == 1 && (n == 0 || n == 3)) continue;
                 if (!VISC && n >= 4) continue;
 #pragma unroll
-                for (int e = 0; e < NV*NV; e++) blk[e] += sc*S[((size_t)n*NV*NV + e)*pl];
+                for (int e = 0; e < NV*NV; e++) blk[e] += sc*S[(n*NV*NV + e)*STILE];
             }
         }
         if (SA && s < 9) {                                         // rhs[4] += S*V then /V  ->  d rhs4 = dS
