@@ -286,6 +286,7 @@ def run_ours(args):
         rh = torch.empty((nic, njc_per, nv), dtype=torch.float64).pin_memory()
         rn = rh.numpy()
         k_e2e = max(2, min(args.steps, 5))
+        dev_rhs = eq.get_rhs() if world == 1 else None      # device-resident path's result, before the host path overwrites it
 
         def e2e_step():
             # host q (pinned) -> device, residual, owned rhs rows -> host: the call-site form of calc_residual
@@ -307,7 +308,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e = float(t.item())
         rows_in = njc_per + (0 if world == 1 else (2 if rank in (0, world - 1) else 4))
-        e2e = {"value": round(cells_total / (ms_e / k_e2e * 1e-3) / 1e6, 3), "unit": "Mcell-evals/s",
+        # the host-buffer path and the device-resident path must produce the same rhs (they run the same kernel on
+        # chunks): compare the last e2e result with the device rhs of the timed loop
+        chk = None
+        if dev_rhs is not None:
+            chk = float(np.abs(rn - dev_rhs).max() / max(np.abs(dev_rhs).max(), 1e-300))
+            dev_rhs = None
+        e2e = {"value": round(cells_total / (ms_e / k_e2e * 1e-3) / 1e6, 3), "unit": "Mcell-evals/s", "rel_diff_vs_device_path": chk,
                "h2d_bytes_per_step": int(nic * rows_in * nv * 8) * 1, "d2h_bytes_per_step": int(nic * njc_per * nv * 8),
                "steps": k_e2e, "note": "per-GPU bytes; sgpu_residual_host(q_host, rhs_host) from pinned host arrays"}
 

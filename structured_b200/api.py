@@ -65,7 +65,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstructured_gpu.so")
+    # SGPU_LIB: load another build of the same library (A/B timing of kernel variants)
+    return os.environ.get("SGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstructured_gpu.so")
 
 
 def load_library():

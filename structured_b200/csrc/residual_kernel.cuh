@@ -2,8 +2,11 @@
 // sm_100a kernel -- primitives, MUSCL/first-order reconstruction, Roe/AUSM flux, Green-Gauss viscous
 // flux, SA transport + source, accumulation, /V and the partial sums of the residual norms.
 //
-// Decomposition ("j-marching strips"): a CTA of RW = 128 threads owns a strip of 128 plane
-// columns (124 cells + 2 halo columns each side) and walks a chunk of rows upward.  Thread t owns column
+// Decomposition ("j-marching strips"): a CTA of RW = 64 threads owns a strip of 64 plane
+// columns (60 cells + 2 halo columns each side) and walks a chunk of rows upward; six CTAs are resident per SM
+// (168 registers, 37 KB shared memory each).  Measured at 4096^2 SA: RW = 128 x 3 CTAs 1.53 ms, 96 x 4 1.45 ms,
+// 64 x 6 1.41 ms -- the same 12 warps per SM, but more independent CTAs de-synchronise the row barriers and the
+// fp64-dense / memory-dense phases, which pays for the 3 % more halo columns.  Thread t owns column
 // i0-2+t.  Per row it
 //   phase 1  converts the prefetched q of row jl+2 to primitives and stores them and the row's metrics into
 //            shared-memory rings (every HBM byte is loaded once, coalesced, one iteration ahead of its use);
@@ -21,7 +24,13 @@
 
 namespace sg {
 
-constexpr int RW = 128;                 // threads per CTA = plane columns per strip
+#ifndef SG_RW
+#define SG_RW 64
+#endif
+#ifndef SG_RES_MINB
+#define SG_RES_MINB 6
+#endif
+constexpr int RW = SG_RW;               // threads per CTA = plane columns per strip
 constexpr int RCELLS = RW - 4;          // cells per strip (threads 2 .. RW-3)
 
 struct ResParams {
@@ -96,7 +105,7 @@ __device__ __forceinline__ void face_net_flux(const Gas& g, const FaceGeom& fg, 
 }
 
 template <int NV, int ORDER, int FLUX, bool VISC>
-__global__ void __launch_bounds__(RW, 3) residual_kernel(const ResParams prm) {
+__global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResParams prm) {
     using Cfg = ResCfg<NV, VISC>;
     constexpr bool SA = Cfg::SA;
     constexpr int NB = Cfg::NB, NVA = Cfg::NVA;

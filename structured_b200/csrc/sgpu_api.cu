@@ -529,7 +529,10 @@ static int residual_host_pipelined_cols(sgpu_ctx* c, const double* q, int qj0, i
         CK(c, cudaEventRecord(c->pipe_up[ch], s_in));
         CK(c, cudaStreamWaitEvent(s_cmp, c->pipe_up[ch], 0));
         c->stream = s_cmp;
-        rc = apply_bcs(c, SGPU_STATE_Q, -(1 << 30), (1 << 30), a, b + 1);              // padded columns a .. b+1 (cells a-1 .. b)
+        // the left ghost column copies cells nic-1 INCLUDING their bottom/top ghosts (the corner ghosts of cell 0 are
+        // "whatever the last BC wrote", src/model/bc.cpp:430-433): give the wrap source its own ghosts first
+        if (vert_periodic && ch == 0) rc = apply_bcs(c, SGPU_STATE_Q, -(1 << 30), (1 << 30), std::max(v.nic - 1, 1), v.nic);
+        if (rc == SGPU_OK) rc = apply_bcs(c, SGPU_STATE_Q, -(1 << 30), (1 << 30), a, b + 1);   // padded columns a .. b+1 (cells a-1 .. b)
         if (rc == SGPU_OK) rc = launch_residual(c, SGPU_STATE_Q, lhs, false, 0, -1, s0, s1 - s0);
         c->stream = user;
         if (rc != SGPU_OK) break;
