@@ -1,4 +1,6 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the reference's golden outputs and the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -171,7 +173,7 @@ def test_windowed_slab_inputs_equal_global_inputs():
     one.close()
 
 
-@pytest.mark.parametrize("nic,njc", [(2, 2), (3, 5), (124, 9), (125, 7), (249, 3)])
+@pytest.mark.parametrize("nic,njc", [(2, 2), (3, 5), (60, 9), (61, 7), (121, 3), (124, 9), (125, 7), (249, 3)])
 def test_ragged_and_minimum_sizes(nic, njc):
     """edge sizes: the smallest grid the ABI accepts, strips that end exactly at / one past a strip seam, few rows"""
     from oracle.bindings import PortOracle
@@ -236,3 +238,23 @@ def test_full_size_4096_properties():
         assert np.array_equal(part[::511], sample[:, j0:j1, :])
         s.close()
     assert np.array_equal(got_sum, col_sum)
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("ntrans", [0, 1])
+def test_host_column_pipeline_equals_device_path_bitwise(ntrans, periodic):
+    """sgpu_residual_host pipelines column chunks (H2D | BCs + kernel | D2H); every chunking must give the bits of the
+    device-resident path, including the corner ghosts a periodic side copies from the wrap-around column"""
+    case = turbulent_channel_case(430, 52, ntrans=ntrans, reynolds=2e4, periodic=periodic)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q)
+    eq.residual_device()
+    dev = eq.get_rhs()
+    for chunks in ("2", "3", "7"):
+        os.environ["SGPU_PIPE_CHUNKS"] = chunks
+        try:
+            assert np.array_equal(eq.calc_residual(q), dev), chunks
+        finally:
+            del os.environ["SGPU_PIPE_CHUNKS"]
+    eq.close()
