@@ -191,6 +191,15 @@ typedef struct sgpu_linsolve {
  * b: host [nic][njc][nv], or NULL for the device rhs of the last sgpu_residual (what set_rhs receives).
  * x: host [nic][njc][nv] or NULL (the solution also stays on the device for sgpu_implicit_step). */
 int sgpu_linear_solve(sgpu_ctx* ctx, int matrix, const double* b, double* x, sgpu_linsolve* io);
+/* Steady adjoint of the discrete residual (no reference code -- "parity unpinned", checked against a
+ * sparse LU of the transposed COO matrix):  J^T psi = -g  with J = d rhs / d q of the last Jacobian build and
+ * g = d objective / d q, host [nic][njc][nv].  Solved by pseudo-time continuation, each step one GMRES solve with the
+ * transposed LHS matrix:  (delta/dt - J^T) dpsi = g + J^T psi,  psi += dpsi,  dt = calc_dt(cfl), until
+ * |g + J^T psi| <= tol |g| or max_steps.  io: GMRES controls for the inner solves; on return io->iterations is the
+ * total over all steps and io->rel_residual the outer residual.  The field-inversion gradient is then
+ * d objective / d beta = psi[..., 4] * sgpu_dres_dbeta (+ the explicit part). */
+int sgpu_adjoint_solve(sgpu_ctx* ctx, const double* g, double* psi, double cfl, int max_steps, double tol, sgpu_linsolve* io,
+                       int* steps, double* rel_residual);
 /* The whole ENABLE_ADOLC branch of Solver::step on the device (src/solver/solver.cpp:66-101,154-175):
  * calc_dt(cfl); rhs = residual(q) with solver.order; J = d residual(lhs_order)/dq; solve (-J + 1/dt) dq = rhs;
  * q += under_relaxation * dq (ls_eigen.cpp:66-70).  l2sq as in sgpu_residual. */

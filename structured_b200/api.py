@@ -24,7 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
-    "sgpu_linear_solve", "sgpu_implicit_step",
+    "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
@@ -323,6 +323,20 @@ class GpuEulerEquation:
         l2 = np.zeros(self.nv)
         self._ck(self.L.sgpu_implicit_step(self.h, ctypes.c_double(cfl), ctypes.c_double(under_relaxation), ctypes.byref(io), _dp(l2)))
         return np.sqrt(l2), self._linsolve_info(io)
+
+    def adjoint_solve(self, g: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
+                      restart: int = 40, max_iter: int = 400, rtol: float = 1e-3, reorthogonalize: bool = False):
+        """Steady adjoint J^T psi = -g (g = d objective / d q) by pseudo-time continuation with transposed-LHS GMRES solves;
+        needs jacobian_device() at the converged state.  Returns (psi, info)."""
+        io = self._linsolve(precond, restart, max_iter, rtol, reorthogonalize)
+        gg = np.ascontiguousarray(g, dtype=np.float64)
+        psi = self._state_array()
+        steps = ctypes.c_int(); rel = ctypes.c_double()
+        self._ck(self.L.sgpu_adjoint_solve(self.h, _dp(gg), _dp(psi), ctypes.c_double(cfl), max_steps, ctypes.c_double(tol), ctypes.byref(io),
+                                           ctypes.byref(steps), ctypes.byref(rel)))
+        info = self._linsolve_info(io)
+        info.update({"steps": steps.value, "rel_residual": rel.value})
+        return psi, info
 
     def dres_dbeta(self) -> np.ndarray:
         """d rhs4 / d beta per cell at the device state (SA extension; field-inversion gradient building block)"""

@@ -10,6 +10,7 @@ struct LinWork {
     int m = 0;                     // basis capacity (restart length)
     double* V = nullptr;           // (m+1) basis vectors
     double *w = nullptr, *z = nullptr, *x = nullptr, *b = nullptr, *u = nullptr;
+    double *psi = nullptr, *g = nullptr;   // adjoint continuation: current psi, objective gradient (allocated on first use)
     double* Dinv = nullptr;        // block-Jacobi inverse (nv*nv planes) or the line factors Dinv, DA, DC (3*nv*nv planes)
     double* partial = nullptr;     // [blocks][ldp]
     double* hdev = nullptr;        // ldp doubles: projections, then norm^2 in the last used column
@@ -22,6 +23,7 @@ struct LinWork {
 static void lin_free(LinWork*& L) {
     if (!L) return;
     cudaFree(L->V); cudaFree(L->w); cudaFree(L->z); cudaFree(L->x); cudaFree(L->b); cudaFree(L->u);
+    cudaFree(L->psi); cudaFree(L->g);
     cudaFree(L->Dinv); cudaFree(L->partial); cudaFree(L->hdev); cudaFree(L->ydev); cudaFree(L->err);
     if (L->hhost) cudaFreeHost(L->hhost);
     delete L; L = nullptr;
@@ -149,7 +151,7 @@ static int lin_norm(sgpu_ctx* c, const double* a, double* out) {
 }
 
 // Solves A x = b with b in L->b; the solution is left in L->x.
-static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io) {
+static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io, bool refactor = true) {
     LinWork* L = c->lin;
     const size_t n = L->n, vb = n*sizeof(double);
     const int m = std::min(io->restart > 0 ? io->restart : 30, L->m), G = L->blocks;   // L->m is the allocated capacity
@@ -162,7 +164,7 @@ static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io) {
     bool timed = false;
     io->matvec_ms = io->precond_ms = 0.0f;
     CK(c, cudaEventRecord(e0, c->stream));
-    if (int rc = lin_factor(c, matrix, precond)) return rc;
+    if (refactor) { if (int rc = lin_factor(c, matrix, precond)) return rc; }
     CK(c, cudaEventRecord(e1, c->stream));
     CK(c, cudaMemsetAsync(L->x, 0, vb, c->stream));
     double bnorm = 0.0;
@@ -288,6 +290,47 @@ int sgpu_linear_solve(sgpu_ctx* c, int matrix, const double* b, double* x, sgpu_
     if (int rc = lin_gmres(c, matrix, io)) return rc;
     if (x) return download_planes(c, c->lin->x, v.nv, x);
     return SGPU_OK;
+}
+
+int sgpu_adjoint_solve(sgpu_ctx* c, const double* g, double* psi, double cfl, int max_steps, double tol, sgpu_linsolve* io,
+                       int* steps_out, double* rel_out) {
+    if (!c || !g || !psi || !io) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = sgpu_calc_dt(c, cfl)) return rc;
+    if (int rc = lin_check(c, SGPU_MAT_LHS_T, io)) return rc;
+    if (int rc = lin_prepare(c, io->restart > 0 ? io->restart : 30)) return rc;
+    LinWork* L = c->lin;
+    const size_t n = L->n, vb = n*sizeof(double);
+    if (!L->psi) { CK(c, cudaMalloc(&L->psi, vb)); CK(c, cudaMalloc(&L->g, vb)); }
+    if (int rc = upload_planes(c, g, L->g)) return rc;
+    CK(c, cudaMemsetAsync(L->psi, 0, vb, c->stream));
+    double gnorm = 0.0;
+    if (int rc = lin_norm(c, L->g, &gnorm)) return rc;
+    int steps = 0, total_iters = 0; double rel = gnorm > 0.0 ? 1.0 : 0.0;
+    float setup = 0.0f, solve = 0.0f;
+    const int nmax = max_steps > 0 ? max_steps : 50;
+    const double stop = tol > 0.0 ? tol : 1e-8;
+    while (gnorm > 0.0) {
+        // rho = g + J^T psi (the negated adjoint residual) into L->b
+        if (steps == 0) CK(c, cudaMemcpyAsync(L->b, L->g, vb, cudaMemcpyDeviceToDevice, c->stream));
+        else {
+            if (int rc = lin_apply_op(c, SGPU_MAT_JT, L->psi, L->b)) return rc;
+            axpby_kernel<<<L->blocks, 256, 0, c->stream>>>(L->b, L->g, n, 1.0, 1.0); CKL(c); c->launches++;
+            double rn = 0.0;
+            if (int rc = lin_norm(c, L->b, &rn)) return rc;
+            rel = rn/gnorm;
+        }
+        if (rel <= stop || steps >= nmax) break;
+        // (delta/dt - J^T) dpsi = rho, psi += dpsi: backward Euler on d psi/d tau = J^T psi + g
+        if (int rc = lin_gmres(c, SGPU_MAT_LHS_T, io, steps == 0)) return rc;
+        total_iters += io->iterations; setup += io->setup_ms; solve += io->solve_ms;
+        axpby_kernel<<<L->blocks, 256, 0, c->stream>>>(L->psi, L->x, n, 1.0, 1.0); CKL(c); c->launches++;
+        steps++;
+    }
+    io->iterations = total_iters; io->setup_ms = setup; io->solve_ms = solve; io->rel_residual = rel; io->converged = rel <= stop;
+    if (steps_out) *steps_out = steps;
+    if (rel_out) *rel_out = rel;
+    return download_planes(c, L->psi, c->v.nv, psi);
 }
 
 int sgpu_implicit_step(sgpu_ctx* c, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq) {
