@@ -50,3 +50,38 @@ def test_create_fails_loudly_without_gpu_or_with_bad_args():
             raise AssertionError("expected SgpuError")
         except api.SgpuError:
             pass
+
+
+def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
+    """the ctypes mirrors of sgpu_bc / sgpu_desc / sgpu_linsolve have the C compiler's sizes and field offsets, and the
+    enum values the Python side hard-codes are the header's"""
+    import subprocess
+    structs = {"sgpu_bc": api.SgpuBc, "sgpu_desc": api.SgpuDesc, "sgpu_linsolve": api.SgpuLinsolve}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "structured_gpu.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    for e in ("SGPU_MAT_LHS", "SGPU_MAT_J", "SGPU_MAT_JT", "SGPU_MAT_LHS_T", "SGPU_PC_BLOCK_JACOBI", "SGPU_PC_LINE_J",
+              "SGPU_FLUX_ROE", "SGPU_FLUX_AUSM", "SGPU_STATE_Q", "SGPU_STATE_Q_TMP"):
+        lines.append('printf("enum %s %%d\\n", (int)%s);' % (e, e))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    enums = {}
+    for ln in out:
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "enum":
+            enums[t[1]] = int(t[2])
+        elif t[1] == "sizeof":
+            assert ctypes.sizeof(structs[t[0]]) == int(t[2]), ln
+        else:
+            assert getattr(structs[t[0]], t[1]).offset == int(t[2]), ln
+    assert [enums[k] for k in ("SGPU_MAT_LHS", "SGPU_MAT_J", "SGPU_MAT_JT", "SGPU_MAT_LHS_T")] == [api.MATRICES[k] for k in ("lhs", "J", "JT", "lhsT")]
+    assert [enums["SGPU_PC_BLOCK_JACOBI"], enums["SGPU_PC_LINE_J"]] == [api.PRECONDS["block_jacobi"], api.PRECONDS["line_j"]]
+    assert [enums["SGPU_FLUX_ROE"], enums["SGPU_FLUX_AUSM"]] == [api.FLUXES["roe"], api.FLUXES["ausm"]]
