@@ -205,6 +205,19 @@ int sgpu_adjoint_solve(sgpu_ctx* ctx, const double* g, double* psi, double cfl, 
  * q += under_relaxation * dq (ls_eigen.cpp:66-70).  l2sq as in sgpu_residual. */
 int sgpu_implicit_step(sgpu_ctx* ctx, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq);
 
+/* Building blocks on DEVICE vectors for a slab-partitioned Krylov solve (one process per GPU; the iteration itself is
+ * host logic over torch.distributed, structured_b200/slab.py: dot products are all-reduced, the two ghost rows of the
+ * operand are exchanged before every product).  A vector = nv state planes of this slab, sgpu_vec_size doubles, zero
+ * outside the owned cells except for halo rows filled by sgpu_vec_halo_unpack.  SGPU_MAT_LHS and SGPU_MAT_J only. */
+int sgpu_vec_size(const sgpu_ctx* ctx, long long* n);
+int sgpu_vec_from_rhs(sgpu_ctx* ctx, double* vec_dev);                                  /* what set_rhs receives */
+int sgpu_vec_add_to_state(sgpu_ctx* ctx, int which, const double* vec_dev, double omega);  /* q += omega*x, ls_eigen.cpp:66-70 */
+int sgpu_vec_halo_pack(sgpu_ctx* ctx, const double* vec_dev, int side, double* buf_dev);   /* layout of sgpu_halo_pack */
+int sgpu_vec_halo_unpack(sgpu_ctx* ctx, double* vec_dev, int side, const double* buf_dev);
+int sgpu_op_apply(sgpu_ctx* ctx, int matrix, const double* x_dev, double* y_dev);       /* y = A x on the owned rows */
+int sgpu_precond_setup(sgpu_ctx* ctx, int matrix, int precond);                         /* slab-local factors */
+int sgpu_precond_apply(sgpu_ctx* ctx, int matrix, int precond, const double* r_dev, double* z_dev);
+
 /* ---- multi-GPU j-slabs ---------------------------------------------------------------------- */
 /* Two ghost rows of q per interior slab edge.  side: 0 = low-j neighbour, 1 = high-j neighbour.
  * pack writes this slab's two boundary rows into a contiguous DEVICE buffer of sgpu_halo_count()

@@ -25,6 +25,8 @@ SYMBOLS = [
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
+    "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
+    "sgpu_precond_setup", "sgpu_precond_apply",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
@@ -323,6 +325,33 @@ class GpuEulerEquation:
         l2 = np.zeros(self.nv)
         self._ck(self.L.sgpu_implicit_step(self.h, ctypes.c_double(cfl), ctypes.c_double(under_relaxation), ctypes.byref(io), _dp(l2)))
         return np.sqrt(l2), self._linsolve_info(io)
+
+    # ---- device-vector building blocks of the slab-partitioned solve (driven by structured_b200/slab.py)
+    def vec_size(self) -> int:
+        n = ctypes.c_longlong()
+        self._ck(self.L.sgpu_vec_size(self.h, ctypes.byref(n)))
+        return n.value
+
+    def vec_from_rhs(self, vec_ptr: int):
+        self._ck(self.L.sgpu_vec_from_rhs(self.h, ctypes.c_void_p(vec_ptr)))
+
+    def vec_add_to_state(self, vec_ptr: int, omega: float = 1.0, which: int = 0):
+        self._ck(self.L.sgpu_vec_add_to_state(self.h, which, ctypes.c_void_p(vec_ptr), ctypes.c_double(omega)))
+
+    def vec_halo_pack(self, vec_ptr: int, side: int, buf_ptr: int):
+        self._ck(self.L.sgpu_vec_halo_pack(self.h, ctypes.c_void_p(vec_ptr), side, ctypes.c_void_p(buf_ptr)))
+
+    def vec_halo_unpack(self, vec_ptr: int, side: int, buf_ptr: int):
+        self._ck(self.L.sgpu_vec_halo_unpack(self.h, ctypes.c_void_p(vec_ptr), side, ctypes.c_void_p(buf_ptr)))
+
+    def op_apply(self, matrix: str, x_ptr: int, y_ptr: int):
+        self._ck(self.L.sgpu_op_apply(self.h, MATRICES[matrix], ctypes.c_void_p(x_ptr), ctypes.c_void_p(y_ptr)))
+
+    def precond_setup(self, matrix: str, precond: str):
+        self._ck(self.L.sgpu_precond_setup(self.h, MATRICES[matrix], PRECONDS[precond]))
+
+    def precond_apply(self, matrix: str, precond: str, r_ptr: int, z_ptr: int):
+        self._ck(self.L.sgpu_precond_apply(self.h, MATRICES[matrix], PRECONDS[precond], ctypes.c_void_p(r_ptr), ctypes.c_void_p(z_ptr)))
 
     def adjoint_solve(self, g: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
                       restart: int = 40, max_iter: int = 400, rtol: float = 1e-3, reorthogonalize: bool = False):

@@ -333,6 +333,74 @@ int sgpu_adjoint_solve(sgpu_ctx* c, const double* g, double* psi, double cfl, in
     return download_planes(c, L->psi, c->v.nv, psi);
 }
 
+// ---- building blocks on DEVICE vectors for a slab-partitioned Krylov solve (one process per GPU; the iteration is
+//      driven by the host over torch.distributed: structured_b200/slab.py).  A vector is nv state planes of this slab
+//      (sgpu_vec_size doubles); owned cells carry the data, the two ghost rows per interior slab edge are filled by
+//      sgpu_vec_halo_pack -> transport -> sgpu_vec_halo_unpack before every operator application.
+static int vec_check(sgpu_ctx* c, int matrix) {
+    if (matrix != SGPU_MAT_LHS && matrix != SGPU_MAT_J) FAIL(c, SGPU_ERR_ARG, "slab vector operations support SGPU_MAT_LHS and SGPU_MAT_J (the transposed products scatter across slab edges)");
+    if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
+    if (matrix == SGPU_MAT_LHS && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS matrix needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
+    return SGPU_OK;
+}
+int sgpu_vec_size(const sgpu_ctx* c, long long* n) {
+    if (!c || !n) return SGPU_ERR_ARG;
+    *n = (long long)(c->v.plane*c->v.nv);
+    return SGPU_OK;
+}
+int sgpu_vec_from_rhs(sgpu_ctx* c, double* vec) {
+    if (!c || !vec) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    masked_copy_kernel<<<dim3((v.pitch + 127)/128, v.rows), 128, 0, c->stream>>>(v, c->rhs, vec);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_vec_add_to_state(sgpu_ctx* c, int which, const double* vec, double omega) {
+    if (!c || !vec || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    masked_axpy_kernel<<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->q[which], vec, omega);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_vec_halo_pack(sgpu_ctx* c, const double* vec, int side, double* buf) {
+    if (!c || !vec || !buf || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_pack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, vec, buf, halo_rows(c, side, false));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_vec_halo_unpack(sgpu_ctx* c, double* vec, int side, const double* buf) {
+    if (!c || !vec || !buf || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_unpack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, vec, buf, halo_rows(c, side, true));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_op_apply(sgpu_ctx* c, int matrix, const double* x, double* y) {
+    if (!c || !x || !y) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = vec_check(c, matrix)) return rc;
+    return lin_apply_op(c, matrix, x, y);
+}
+int sgpu_precond_setup(sgpu_ctx* c, int matrix, int precond) {
+    if (!c) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = vec_check(c, matrix)) return rc;
+    if (precond != SGPU_PC_BLOCK_JACOBI && precond != SGPU_PC_LINE_J) FAIL(c, SGPU_ERR_ARG, "unknown preconditioner");
+    if (int rc = lin_prepare(c, 1)) return rc;
+    return lin_factor(c, matrix, precond);
+}
+int sgpu_precond_apply(sgpu_ctx* c, int matrix, int precond, const double* r, double* z) {
+    if (!c || !r || !z) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (!c->lin) FAIL(c, SGPU_ERR_STATE, "sgpu_precond_setup has not been called");
+    return lin_apply_pc(c, matrix, precond, r, z);
+}
+
 int sgpu_implicit_step(sgpu_ctx* c, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq) {
     if (!c || !io) return SGPU_ERR_ARG;
     if (int rc = sgpu_calc_dt(c, cfl)) return rc;                                   // solver.cpp:66

@@ -103,6 +103,16 @@ __global__ void masked_copy_kernel(View v, const double* __restrict__ src, doubl
     for (int k = 0; k < v.nv; k++) dst[k*v.plane + o] = own ? src[k*v.plane + o] : 0.0;
 }
 
+// q += omega * x on the owned cells (the update of src/linearsolver/ls_eigen.cpp:66-70 for a slab vector whose ghost
+// rows hold halo data)
+__global__ void masked_axpy_kernel(View v, double* __restrict__ q, const double* __restrict__ x, double omega) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    for (int k = 0; k < v.nv; k++) q[k*v.plane + o] += omega*x[k*v.plane + o];
+}
+
 // ------------------------------------------------------------------------------------------------
 // nv x nv inverse in registers: Gauss-Jordan with partial pivoting, every index a compile-time constant.
 // Returns false when a pivot is exactly zero.

@@ -85,3 +85,136 @@ class HaloExchanger:
         t = torch.as_tensor(values, dtype=torch.float64, device=device).clone()
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Slab-partitioned Krylov solve (SURVEY.md 8(f) N1 across GPUs).  Host logic only: the operator and the
+# preconditioner are the CUDA kernels behind sgpu_op_apply / sgpu_precond_apply; what is distributed is
+#   * the operand's two ghost rows per interior slab edge (HaloExchanger, before every product), and
+#   * every inner product (one all-reduce of k+1 doubles per Gram-Schmidt pass).
+# The same restarted, right-preconditioned GMRES as sgpu_linear_solve (csrc/linsolve_api.inl), written on torch
+# tensors so that the CPU tests run it over gloo with a numpy-defined operator.
+# ---------------------------------------------------------------------------------------------------
+def distributed_gmres(apply_op: Callable, apply_pc: Callable, b, restart: int = 30, max_iter: int = 500, rtol: float = 1e-10,
+                      allreduce: Callable = None):
+    """Solve A x = b for the row block this rank owns.
+
+    apply_op(x, out) / apply_pc(r, out) act on this rank's block (apply_op may exchange halos inside);
+    allreduce(t) sums a small tensor over the ranks in place (None: single rank).
+    Returns (x, info) with info = {iterations, converged, rel_residual}; rel_residual is the TRUE residual.
+    """
+    import math
+
+    import torch
+    n, m = b.numel(), int(restart)
+    V = torch.zeros((m + 1, n), dtype=b.dtype, device=b.device)
+    x = torch.zeros_like(b); w = torch.zeros_like(b); z = torch.zeros_like(b); u = torch.zeros_like(b)
+
+    def gsum(t):
+        if allreduce is not None:
+            allreduce(t)
+        return t
+
+    def norm(a):
+        return math.sqrt(float(gsum(torch.dot(a, a).reshape(1))[0]))
+
+    bnorm = norm(b)
+    info = {"iterations": 0, "converged": True, "rel_residual": 0.0}
+    if bnorm == 0.0:
+        return x, info
+    iters, beta, first = 0, bnorm, True
+    while True:
+        if first:
+            w.copy_(b); first = False
+        else:
+            apply_op(x, w)
+            torch.sub(b, w, out=w)
+            beta = norm(w)
+        info["rel_residual"] = beta / bnorm
+        if beta <= rtol * bnorm or iters >= max_iter:
+            break
+        V[0].copy_(w).div_(beta)
+        H = np.zeros((m + 1, m)); cs = np.zeros(m); sn = np.zeros(m); g = np.zeros(m + 1); g[0] = beta
+        k, done = 0, False
+        while k < m and iters < max_iter and not done:
+            apply_pc(V[k], z)
+            apply_op(z, w)
+            h = gsum(torch.mv(V[:k + 1], w))                       # classical Gram-Schmidt, one all-reduce
+            w.addmv_(V[:k + 1].t(), h, alpha=-1.0)
+            hk1 = norm(w)
+            hh = np.concatenate([h.cpu().numpy(), [hk1]])
+            if hk1 > 0.0:
+                V[k + 1].copy_(w).div_(hk1)
+            for j in range(k):                                     # Givens rotations
+                t = cs[j] * hh[j] + sn[j] * hh[j + 1]
+                hh[j + 1] = -sn[j] * hh[j] + cs[j] * hh[j + 1]
+                hh[j] = t
+            den = math.hypot(hh[k], hh[k + 1])
+            cs[k], sn[k] = (1.0, 0.0) if den == 0.0 else (hh[k] / den, hh[k + 1] / den)
+            hh[k] = cs[k] * hh[k] + sn[k] * hh[k + 1]
+            g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k]
+            H[:k + 1, k] = hh[:k + 1]
+            if abs(g[k + 1]) <= rtol * bnorm or hk1 == 0.0:
+                done = True
+            k += 1; iters += 1
+        if k == 0:
+            break
+        y = np.zeros(k)
+        for j in range(k - 1, -1, -1):
+            s = g[j] - H[j, j + 1:k] @ y[j + 1:k]
+            y[j] = s / H[j, j] if H[j, j] != 0.0 else 0.0
+        torch.mv(V[:k].t(), torch.as_tensor(y, dtype=b.dtype, device=b.device), out=u)
+        apply_pc(u, z)
+        x.add_(z)
+    info["iterations"] = iters
+    info["converged"] = info["rel_residual"] <= rtol
+    return x, info
+
+
+class SlabLinearSolver:
+    """linearsolver->set_lhs / set_rhs / solve_and_update (src/solver/solver.cpp:172-175) for ONE j-slab of a grid:
+    every rank holds a GpuEulerEquation built with (j_begin, j_end) and runs the same calls."""
+
+    def __init__(self, eq, rank: int, world: int, dist_module=None, device=None):
+        import torch
+        self.eq, self.rank, self.world, self.dist = eq, rank, world, dist_module
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.halo = HaloExchanger(rank, world, eq.halo_count(), self.device, dist_module)
+        self.n = eq.vec_size()
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+
+    def solve(self, matrix: str = "lhs", precond: str = "line_j", restart: int = 30, max_iter: int = 500, rtol: float = 1e-10):
+        """A x = rhs with the device rhs of the last residual and the Jacobian of the last jacobian_device();
+        returns (x as a device tensor laid out as state planes, info)."""
+        import torch
+        eq = self.eq
+        b = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+        eq.vec_from_rhs(b.data_ptr())
+        eq.precond_setup(matrix, precond)
+
+        def apply_op(x, out):
+            self.halo.exchange(lambda side, t: eq.vec_halo_pack(x.data_ptr(), side, t.data_ptr()),
+                               lambda side, t: eq.vec_halo_unpack(x.data_ptr(), side, t.data_ptr()))
+            eq.op_apply(matrix, x.data_ptr(), out.data_ptr())
+
+        def apply_pc(r, out):
+            eq.precond_apply(matrix, precond, r.data_ptr(), out.data_ptr())
+
+        return distributed_gmres(apply_op, apply_pc, b, restart, max_iter, rtol, self._allreduce if self.world > 1 else None)
+
+    def implicit_step(self, cfl: float, under_relaxation: float = 1.0, exchange_state: Callable = None, **kw):
+        """The implicit branch of Solver::step on a slab partition: dt, residual, Jacobian, distributed GMRES, update.
+        exchange_state() must refresh the ghost rows of q (the caller's residual halo exchange) before the residual."""
+        eq = self.eq
+        if exchange_state is not None:
+            exchange_state()
+        eq.calc_dt(cfl)
+        l2 = eq.residual_device(0, norms=True)
+        l2 = self.halo.allreduce_sum(np.asarray(l2), self.device)
+        eq.jacobian_device()
+        x, info = self.solve("lhs", **kw)
+        eq.vec_add_to_state(x.data_ptr(), under_relaxation)
+        return np.sqrt(l2), info

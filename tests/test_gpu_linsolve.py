@@ -217,3 +217,56 @@ def test_transposed_solve_field_inversion_size_2048x1024():
     r = g - (x / eq.get_dt() - eq.jacobian_apply(x, transpose=True))
     assert np.linalg.norm(r) <= 2e-8 * np.linalg.norm(g), info
     eq.close()
+
+
+@pytest.mark.parametrize("ntrans,precond", [(0, "block_jacobi"), (1, "line_j")])
+def test_slab_partitioned_solve_equals_single_slab_solve(ntrans, precond):
+    """two j-slab contexts (as two ranks would hold them) + the host GMRES of structured_b200/slab.py: halo rows of the
+    operand exchanged before every product, slab-local preconditioners -- same solution as the one-context solve"""
+    import torch
+    from structured_b200.slab import HIGH, LOW, SlabLinearSolver, distributed_gmres
+    nic, njc, split = 96, 64, 30
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4)
+    q = case.perturbed_q(0.02)
+    one = gpu_eq(case)
+    one.set_state(q); one.calc_dt(8.0); one.residual_device(); one.jacobian_device()
+    want, winfo = one.linear_solve("lhs", precond=precond, restart=50, max_iter=1500, rtol=1e-12)
+    assert winfo["converged"]
+    # world = 1 through the slab wrapper: exercises vec_from_rhs / op_apply / precond_* / vec_add_to_state
+    solo = SlabLinearSolver(one, 0, 1)
+    x1, info1 = solo.solve("lhs", precond=precond, restart=50, max_iter=1500, rtol=1e-12)
+    assert info1["converged"]
+    q_before = one.get_state()
+    one.vec_add_to_state(x1.data_ptr(), 0.5)
+    assert np.abs((one.get_state() - q_before) - 0.5 * want).max() <= 1e-8 * np.abs(want).max()
+    # two slabs in one process: the pair acts as one "rank" whose operator exchanges the halo rows between the halves
+    slabs = [gpu_eq(case, j_begin=0, j_end=split), gpu_eq(case, j_begin=split, j_end=njc)]
+    for s in slabs:
+        s.set_state(q); s.calc_dt(8.0); s.residual_device(); s.jacobian_device(); s.precond_setup("lhs", precond)
+    ns = [s.vec_size() for s in slabs]
+    b = torch.zeros(sum(ns), dtype=torch.float64, device="cuda")
+    parts = lambda t: (t[:ns[0]], t[ns[0]:])
+    for s, bp in zip(slabs, parts(b)):
+        s.vec_from_rhs(bp.data_ptr())
+    buf = torch.empty(slabs[0].halo_count(), dtype=torch.float64, device="cuda")
+
+    def apply_op(x, out):
+        xl, xh = parts(x); ol, oh = parts(out)
+        slabs[0].vec_halo_pack(xl.data_ptr(), HIGH, buf.data_ptr()); slabs[1].vec_halo_unpack(xh.data_ptr(), LOW, buf.data_ptr())
+        slabs[1].vec_halo_pack(xh.data_ptr(), LOW, buf.data_ptr()); slabs[0].vec_halo_unpack(xl.data_ptr(), HIGH, buf.data_ptr())
+        slabs[0].op_apply("lhs", xl.data_ptr(), ol.data_ptr()); slabs[1].op_apply("lhs", xh.data_ptr(), oh.data_ptr())
+
+    def apply_pc(r, out):
+        for s, rp, op in zip(slabs, parts(r), parts(out)):
+            s.precond_apply("lhs", precond, rp.data_ptr(), op.data_ptr())
+
+    x2, info2 = distributed_gmres(apply_op, apply_pc, b, restart=50, max_iter=1500, rtol=1e-12)
+    assert info2["converged"], info2
+    got = np.zeros_like(want)
+    for s, xp in zip(slabs, parts(x2)):
+        s.set_state(np.zeros_like(q))                      # q := 0, then q += x: read the solution back through the state
+        s.vec_add_to_state(xp.data_ptr(), 1.0)
+        got[:, s.j_begin:s.j_end, :] = s.get_state()[:, s.j_begin:s.j_end, :]
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+    for s in slabs + [one]:
+        s.close()

@@ -47,3 +47,70 @@ def test_two_gpus_peer_memory_halo_bit_for_bit(ntrans):
         assert np.array_equal(got, want), rep
     for s in (one, lo, hi):
         s.close()
+
+
+def _implicit_worker(rank, world, port, nic, njc, ntrans, cfl, out):
+    import os
+
+    import torch
+    import torch.distributed as dist
+    from structured_b200.api import GpuEulerEquation
+    from structured_b200.slab import HaloExchanger, SlabLinearSolver, partition_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4)
+        q = case.perturbed_q(0.02)
+        j0, j1 = partition_rows(njc, world)[rank]
+        eq = GpuEulerEquation(case, device=rank, j_begin=j0, j_end=j1)
+        eq.set_state_window(np.ascontiguousarray(q[:, j0:j1, :]), j0)        # own rows only: ghosts must come from the exchange
+        dev = torch.device("cuda", rank)
+        qhalo = HaloExchanger(rank, world, eq.halo_count(), dev, dist)
+        solver = SlabLinearSolver(eq, rank, world, dist, dev)
+
+        def exchange_state():
+            qhalo.exchange(lambda s, t: eq.halo_pack(0, s, t.data_ptr()), lambda s, t: eq.halo_unpack(0, s, t.data_ptr()))
+
+        l2, info = solver.implicit_step(cfl, 1.0, exchange_state=exchange_state, precond="line_j", restart=50, max_iter=1500, rtol=1e-12)
+        rows = eq.get_state()[:, j0:j1, :]
+        out.put((rank, j0, j1, rows, l2, info["converged"], info["iterations"]))
+        eq.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("ntrans", [0, 1])
+def test_two_gpu_implicit_step_over_nccl_equals_one_gpu(ntrans):
+    """one implicit Solver::step on two j-slabs, two processes, NCCL: ghost rows of q and of every Krylov operand
+    exchanged, inner products all-reduced -- same new state as sgpu_implicit_step on one GPU"""
+    import socket
+
+    import torch.multiprocessing as mp
+    from structured_b200.api import GpuEulerEquation
+    nic, njc, cfl = 128, 80, 8.0
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4)
+    q = case.perturbed_q(0.02)
+    one = GpuEulerEquation(case, device=0)
+    one.set_state(q)
+    l2_one, info = one.implicit_step(cfl, 1.0, precond="line_j", restart=50, max_iter=1500, rtol=1e-12)
+    assert info["converged"]
+    want = one.get_state()
+    one.close()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_implicit_worker, args=(r, 2, port, nic, njc, ntrans, cfl, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    got = np.zeros_like(want)
+    for rank, j0, j1, rows, l2, conv, iters in res:
+        assert conv
+        got[:, j0:j1, :] = rows
+        assert np.abs(l2 - l2_one).max() <= 1e-10 * np.abs(l2_one).max()
+    dq = want - q
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(dq).max(), np.abs(got - want).max() / np.abs(dq).max()
