@@ -65,9 +65,12 @@ static int lin_apply_op(sgpu_ctx* c, int matrix, const double* x, double* y) {
     const bool order2 = c->d.lhs_order == 2;
     const int op = mat_op(matrix);
     if (mat_transposed(matrix)) {
-        CK(c, cudaMemsetAsync(y, 0, v.plane*v.nv*sizeof(double), c->stream));
-        if (v.nv == 5) jac_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, 1);
-        else jac_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, 1);
+        // gather form for the inner row cells (writes every owned y once), then the boundary band's atomic scatter
+        if (v.nv == 5) op_apply_t_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
+        else op_apply_t_kernel<4><<<grd, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
+        CKL(c); c->launches++;
+        if (v.nv == 5) op_apply_t_band_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
+        else op_apply_t_band_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
         if (op == OP_LHS) {
             CKL(c); c->launches++;
             if (v.nv == 5) lhs_fixup_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->dt, x, y);

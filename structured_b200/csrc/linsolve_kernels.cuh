@@ -82,6 +82,69 @@ __global__ void __launch_bounds__(128) op_apply_kernel(View v, GhostTable gt, in
     for (int r = 0; r < NV; r++) y[r*pl + o] = yr[r];
 }
 
+// y = J^T x in GATHER form for the contributions of "inner" row cells (whole stencil interior, natural columns):
+//     (J^T x)[c] = sum_s J_s[c - off_s]^T x[c - off_s]
+// -- the blocks of the neighbouring ROW cells are read at a shifted offset, still coalesced, and every y is written
+// once (deterministic, no atomics).  Row cells in the boundary band (remapped / folded columns) are added afterwards by
+// jac_apply_kernel's atomic scatter restricted to the band (op_apply_t_band_kernel below).
+template <int NV>
+__global__ void __launch_bounds__(128) op_apply_t_kernel(View v, int nslots, bool viscous, bool order2,
+                                                         const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const int gj = v.j0 + jl;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    const size_t pl = v.plane;
+    double yr[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) yr[r] = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < nslots; s++) {
+        if (!viscous && s >= 5 && s <= 8) continue;
+        if (!order2 && s >= 9) continue;
+        const int ri = i - c_slot_dx[s], rj = gj - c_slot_dy[s];          // the row cell whose slot s points at this cell
+        if (!(ri >= 2 && ri < v.nic - 2 && rj >= 2 && rj < v.njc - 2)) continue;   // band rows: scattered separately
+        const int rl = rj - v.j0;
+        if (rl < 0 || rl >= v.njl) continue;                       // row cell owned by another slab
+        const size_t orow = v.at(rl + JOFF, ri + IOFF);
+        double xs[NV];
+#pragma unroll
+        for (int r = 0; r < NV; r++) xs[r] = x[r*pl + orow];
+        const double* Js = J + (size_t)s*NV*NV*pl + orow;
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) yr[c2] += ld_stream(Js + (size_t)(r*NV + c2)*pl)*xs[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NV; r++) y[r*pl + o] = yr[r];
+}
+
+// the band rows' share of J^T x: atomic scatter, but only from row cells within 2 of a physical boundary
+template <int NV>
+__global__ void op_apply_t_band_kernel(View v, GhostTable gt, int nslots, bool viscous, bool order2, const double* __restrict__ J,
+                                       const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const int gj = v.j0 + jl;
+    if (i >= 2 && i < v.nic - 2 && gj >= 2 && gj < v.njc - 2) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    SlotCols sc; resolve_slots(gt, nslots, i, gj, viscous, order2, sc);
+    for (int s = 0; s < nslots; s++) {
+        if (sc.col[s] < 0) continue;
+        const int ci = sc.col[s]/v.njc, cj = sc.col[s] - ci*v.njc;
+        const int rr = cj - v.j0 + JOFF;
+        if (rr < 0 || rr >= v.rows) continue;
+        const size_t oc = v.at(rr, ci + IOFF);
+        for (int r = 0; r < NV; r++) {
+            const double xr = x[r*v.plane + o];
+            for (int c2 = 0; c2 < NV; c2++) atomicAdd(&y[c2*v.plane + oc], J[((size_t)s*NV*NV + r*NV + c2)*v.plane + o]*xr);
+        }
+    }
+}
+
 // after the scattered J^T x accumulation: y = -y + x/dt on the owned cells
 template <int NV>
 __global__ void lhs_fixup_kernel(View v, const double* __restrict__ dt, const double* __restrict__ x, double* __restrict__ y) {
