@@ -156,6 +156,21 @@ int sgpu_jacobian_apply(sgpu_ctx* ctx, int transpose, const double* x, double* y
  * (owned rows written).  Gradient of an objective w.r.t. the correction field = psi^T dR/dbeta. */
 int sgpu_dres_dbeta(sgpu_ctx* ctx, double* out);
 
+/* ---- surface output ------------------------------------------------------- */
+/* What IOManager::write_surface (src/utils/io.cpp:182-255) reads: grad_u_eta[i][0][0..1], grad_v_eta[i][0][0..1] as
+ * the last residual evaluation left them in EulerEquation's work arrays (Mesh::calc_gradient on the j = 0 faces,
+ * src/utils/mesh.cpp:88-128) and Solution::p[i][0], p[i][1] of the final state (IOManager::write, io.cpp:41).
+ * which_res = the state the last calc_residual saw (BCs are applied to it here); which_q = the final state.
+ * Only the slab that owns j = 0 may call this.  Host outputs: grad_u, grad_v [nic][2]; p_row0, p_row1 [nic];
+ * any may be NULL. */
+int sgpu_wall_data(sgpu_ctx* ctx, int which_res, int which_q, double* grad_u, double* grad_v, double* p_row0, double* p_row1);
+/* The loop of IOManager::write_surface over cell columns i in [i_first, i_first + count) (the reference uses
+ * i_first = mesh->j1 - 1, count = mesh->nb, src/utils/io.cpp:219, src/utils/mesh.cpp:349-350): per column
+ * xw = xc[i][0], cp, cf (each may be NULL), and coeffs[6] = {cl_pressure, cd_pressure, cl_viscous, cd_viscous, cl, cd}
+ * with the angle of attack aoa in radians (config->freestream->aoa), summed in the reference's order. */
+int sgpu_surface(sgpu_ctx* ctx, int which_res, int which_q, int i_first, int count, double aoa,
+                 double* xw, double* cp, double* cf, double* coeffs);
+
 /* ---- device linear solve ---------------------------------------------------- */
 /* Replaces, for a Jacobian that stays on the device, the reference's linear-solver plug-in
  *     linearsolver->set_lhs(nnz, rind, cind, values); set_rhs(rhs); solve_and_update(q, UNDER_RELAXATION)

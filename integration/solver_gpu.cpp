@@ -134,7 +134,17 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
     }
 #endif
     for (size_t k = 0; k < nv; k++) l2norm[k] = sqrt(l2sq[k]);
-    auto sync_host = [&]() { gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state"); };
+    // what IOManager::write reads: Solution::q, and -- in write_surface (src/utils/io.cpp:215-216,224-234) -- the wall-face
+    // rows grad_u_eta[i][0], grad_v_eta[i][0] of EulerEquation's work arrays, which the host no longer computes
+    auto sync_host = [&]() {
+        gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state");
+        const size_t nic = mesh->nic;
+        std::vector<double> gu(2*nic), gv(2*nic);
+        gpu_check(sgpu_wall_data(ctx, SGPU_STATE_Q, SGPU_STATE_Q, gu.data(), gv.data(), nullptr, nullptr), ctx, "sgpu_wall_data");
+        auto eq = mesh->equation;
+        for (size_t i = 0; i < nic; i++)
+            for (size_t k = 0; k < 2; k++) { eq->grad_u_eta[i][0][k] = gu[2*i + k]; eq->grad_v_eta[i][0][k] = gv[2*i + k]; }
+    };
     if (counter > config->solver->iteration_max) {
         logger->info("Max iteration reached!");
         sync_host();

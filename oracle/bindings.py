@@ -88,7 +88,7 @@ class RefOracle:
         L.ref_time_residual.restype = ctypes.c_double
         L.ref_time_jacobian.restype = ctypes.c_double
         for name in ("ref_destroy", "ref_dims", "ref_get_grid", "ref_get_metrics", "ref_get_q", "ref_residual",
-                     "ref_get_primitives", "ref_calc_dt", "ref_time_residual", "ref_jacobian", "ref_time_jacobian", "ref_free"):
+                     "ref_get_primitives", "ref_calc_dt", "ref_time_residual", "ref_jacobian", "ref_time_jacobian", "ref_free", "ref_surface"):
             getattr(L, name).argtypes = None
         self._tmp = None
         if config_path is None:
@@ -96,6 +96,7 @@ class RefOracle:
             assert case.ntrans == 0, "the reference has no transport equation (ntrans = 0, src/solver/solution.cpp:9)"
             self._tmp = tempfile.TemporaryDirectory(prefix="sref_")
             config_path = write_case(case, self._tmp.name)
+        self.dir = os.path.dirname(os.path.abspath(config_path))
         self.h = ctypes.c_void_p(L.ref_create(os.path.abspath(config_path).encode()))
         ni, nj, nv = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         L.ref_dims(self.h, ctypes.byref(ni), ctypes.byref(nj), ctypes.byref(nv))
@@ -138,6 +139,20 @@ class RefOracle:
         dt = np.empty_like(q)
         self.L.ref_calc_dt(self.h, _dp(q), ctypes.c_double(cfl), _dp(dt))
         return dt
+
+    def surface(self, q_res, q_fin=None):
+        """IOManager::write_surface run by the reference (src/utils/io.cpp:182-255): returns (rows of the text file
+        [n][3] = xw cp cf at 6 significant digits, wall[6][nic] = the full-precision arrays the routine reads)."""
+        q_res = np.ascontiguousarray(q_res, dtype=np.float64)
+        q_fin = q_res if q_fin is None else np.ascontiguousarray(q_fin, dtype=np.float64)
+        wall = np.empty((6, self.nic))
+        label = ctypes.create_string_buffer(256)
+        self.L.ref_surface(self.h, _dp(q_res), _dp(q_fin), _dp(wall), label, 256)
+        path = os.path.join(self.dir, label.value.decode() + ".surface")
+        text = open(path).read()
+        os.remove(path)
+        rows = np.array([[float(t) for t in line.split()] for line in text.splitlines() if line.strip()]).reshape(-1, 3)
+        return rows, wall
 
     def time_residual(self, q, reps, lhs=False):
         q = np.ascontiguousarray(q, dtype=np.float64)
@@ -206,6 +221,19 @@ class PortOracle:
         dt = np.empty_like(q)
         self.L.port_calc_dt(self.h, _dp(q), ctypes.c_double(cfl), _dp(dt))
         return dt
+
+    def surface(self, q_res, q_fin=None, i_first=None, count=None, aoa=None):
+        """IOManager::write_surface restated (port_surface): dict(xw, cp, cf, coeffs[6], wall[6][nic]).  Defaults are the
+        reference's range j1 - 1 .. j1 - 1 + nb with j1 = geometry.tail, nb = ni - 2 j1 + 1 (src/utils/mesh.cpp:349-350)."""
+        q_res = np.ascontiguousarray(q_res, dtype=np.float64)
+        q_fin = q_res if q_fin is None else np.ascontiguousarray(q_fin, dtype=np.float64)
+        if i_first is None:
+            i_first, count = self.case.tail - 1, self.case.ni - 2*self.case.tail + 1
+        aoa = self.case.aoa if aoa is None else aoa
+        xw, cp, cf = np.empty(count), np.empty(count), np.empty(count)
+        coeffs, wall = np.empty(6), np.empty((6, self.nic))
+        self.L.port_surface(self.h, _dp(q_res), _dp(q_fin), int(i_first), int(count), ctypes.c_double(aoa), _dp(xw), _dp(cp), _dp(cf), _dp(coeffs), _dp(wall))
+        return dict(xw=xw, cp=cp, cf=cf, coeffs=coeffs, wall=wall)
 
     def time_residual(self, q, reps, lhs=False):
         q = np.ascontiguousarray(q, dtype=np.float64)

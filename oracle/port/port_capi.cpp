@@ -67,6 +67,55 @@ void port_get_primitives(void* hv, double* rho, double* u, double* v, double* p,
     if (nut) std::memcpy(nut, h->wd.nut.data(), n);
 }
 
+// IOManager::write_surface, src/utils/io.cpp:182-255.  The reference reads grad_{u,v}_eta[i][0] as the last
+// calc_residual left them (state q_res) and Solution::p[i][0..1] recomputed from the final q (io.cpp:41, unpadded,
+// shift 0): per cell column i in [i_first, i_first + count) (reference: j1 - 1 .. j1 - 1 + nb) xw, cp, cf and
+// coeffs[6] = {cl_p, cd_p, cl_v, cd_v, cl, cd}.  wall[6][nic] (may be NULL) = gu_x, gu_y, gv_x, gv_y, p0, p1.
+void port_surface(void* hv, const double* q_res, const double* q_fin, int i_first, int count, double aoa,
+                  double* xw, double* cp_out, double* cf_out, double* coeffs, double* wall) {
+    auto h = (PortHandle*)hv;
+    const sport::Case& c = h->c;
+    std::vector<double> rhs((size_t)c.nic*c.njc*c.nv);
+    sport::calc_residual<double>(c, h->wd, q_res, rhs.data(), false);
+    auto pcell = [&](int i, int j) {                                             // fluid.cpp:50-67 with shift 0
+        const double* Q = q_fin + ((size_t)i*c.njc + j)*c.nv;
+        double r = Q[0], uu = Q[1]/r, vv = Q[2]/r;
+        return (Q[3] - 0.5*r*(uu*uu + vv*vv))*(sport::GAMMA - 1.0);
+    };
+    auto X = [&](const std::vector<double>& a, int i, int j) { return a[(size_t)i*c.nj + j]; };
+    const sport::Work<double>& w = h->wd;
+    if (wall) for (int i = 0; i < c.nic; i++) {
+        wall[i] = w.gu_eta[w.E(i, 0)*2]; wall[c.nic + i] = w.gu_eta[w.E(i, 0)*2 + 1];
+        wall[2*c.nic + i] = w.gv_eta[w.E(i, 0)*2]; wall[3*c.nic + i] = w.gv_eta[w.E(i, 0)*2 + 1];
+        wall[4*c.nic + i] = pcell(i, 0); wall[5*c.nic + i] = pcell(i, 1);
+    }
+    double Fn_pressure = 0.0, Fc_pressure = 0.0, Fn_viscous = 0.0, Fc_viscous = 0.0;
+    for (int i = i_first; i < i_first + count; i++) {                            // :219-238
+        const double gux = w.gu_eta[w.E(i, 0)*2], guy = w.gu_eta[w.E(i, 0)*2 + 1];
+        const double gvx = w.gv_eta[w.E(i, 0)*2], gvy = w.gv_eta[w.E(i, 0)*2 + 1];
+        double qinf = 0.5*c.rho_inf*(c.u_inf*c.u_inf + c.v_inf*c.v_inf);
+        double cp = (0.5*(pcell(i, 0) + pcell(i, 1)) - c.p_inf)/qinf;
+        double tau = c.mu_inf*(guy - gvx)/qinf;
+        if (xw) xw[i - i_first] = 0.25*(X(c.xv, i, 0) + X(c.xv, i+1, 0) + X(c.xv, i, 1) + X(c.xv, i+1, 1));   // mesh.cpp:199
+        if (cp_out) cp_out[i - i_first] = cp;
+        if (cf_out) cf_out[i - i_first] = tau;
+        double dx = X(c.xv, i+1, 0) - X(c.xv, i, 0), dy = X(c.yv, i+1, 0) - X(c.yv, i, 0);
+        Fn_pressure = Fn_pressure - cp*dx;
+        Fc_pressure = Fc_pressure + cp*dy;
+        double sfdiv = 2.0/3.0*(gux + gvy);
+        double sxx = c.mu_inf*(2.0*gux - sfdiv)/qinf;
+        double syy = c.mu_inf*(2.0*gvy - sfdiv)/qinf;
+        Fn_viscous = Fn_viscous - tau*dy + syy*dx;
+        Fc_viscous = Fc_viscous + tau*dx - sxx*dy;
+    }
+    if (coeffs) {                                                                // :240-249
+        double ca = std::cos(aoa), sa = std::sin(aoa);
+        coeffs[0] = -Fc_pressure*sa + Fn_pressure*ca; coeffs[1] = Fc_pressure*ca + Fn_pressure*sa;
+        coeffs[2] = -Fc_viscous*sa + Fn_viscous*ca; coeffs[3] = Fc_viscous*ca + Fn_viscous*sa;
+        coeffs[4] = coeffs[2] + coeffs[0]; coeffs[5] = coeffs[3] + coeffs[1];
+    }
+}
+
 void port_calc_dt(void* hv, const double* q, double cfl, double* dt) {
     auto h = (PortHandle*)hv;
     sport::calc_dt(h->c, q, cfl, dt);

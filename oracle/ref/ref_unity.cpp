@@ -170,6 +170,36 @@ void ref_get_primitives(void* hv, double* rho, double* u, double* v, double* p, 
     std::memcpy(T, e->T.data(), sizeof(double)*n);
 }
 
+// IOManager::write_surface (src/utils/io.cpp:182-255) run by the reference itself: calc_residual at q_res (fills
+// EulerEquation::grad_{u,v}_eta), Solution::q = q_fin, then IOManager::write's own first statement (primvars into
+// Solution::p, io.cpp:41) and write_surface(), which writes "<label>.surface" (text, 6 significant digits: xw cp cf per
+// line) into the config's directory.  wall[6][nic] receives, in full precision, the reference's own arrays the routine
+// reads: grad_u_eta[i][0][0..1], grad_v_eta[i][0][0..1], Solution::p[i][0], p[i][1].  Returns the label length written
+// into label_out (the caller reads the file).
+int ref_surface(void* hv, const double* q_res, const double* q_fin, double* wall, char* label_out, int label_cap) {
+    auto h = (RefHandle*)hv;
+    auto m = h->d.mesh;
+    auto sol = m->solution;
+    std::memcpy(sol->q.data(), q_res, sizeof(double)*sol->nt);
+    m->equation->calc_residual(sol->q.const_ref(), sol->rhs, false);
+    std::memcpy(sol->q.data(), q_fin, sizeof(double)*sol->nt);
+    m->fluid_model->primvars(sol->q.const_ref(), sol->rho, sol->u, sol->v, sol->p, sol->T);
+    {
+        CwdGuard g(h->dir);
+        m->iomanager->write_surface();
+    }
+    const size_t nic = h->nic;
+    auto e = m->equation;
+    if (wall) for (size_t i = 0; i < nic; i++) {
+        wall[i] = e->grad_u_eta[i][0][0]; wall[nic + i] = e->grad_u_eta[i][0][1];
+        wall[2*nic + i] = e->grad_v_eta[i][0][0]; wall[3*nic + i] = e->grad_v_eta[i][0][1];
+        wall[4*nic + i] = sol->p[i][0]; wall[5*nic + i] = sol->p[i][1];
+    }
+    const std::string& lab = m->iomanager->label;
+    if (label_out && label_cap > 0) { std::strncpy(label_out, lab.c_str(), label_cap - 1); label_out[label_cap - 1] = 0; }
+    return (int)lab.size();
+}
+
 // dt[nic][njc][nv] = calc_dt(cfl) at state q (entries k >= nq are never written by the reference)
 void ref_calc_dt(void* hv, const double* q, double cfl, double* dt) {
     auto h = (RefHandle*)hv;

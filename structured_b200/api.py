@@ -24,6 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
+    "sgpu_wall_data", "sgpu_surface",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
@@ -366,6 +367,36 @@ class GpuEulerEquation:
         info = self._linsolve_info(io)
         info.update({"steps": steps.value, "rel_residual": rel.value})
         return psi, info
+
+    def wall_data(self, which_res: int = 0, which_q: int = 0):
+        """(grad_u [nic][2], grad_v [nic][2], p_row0 [nic], p_row1 [nic]): what IOManager::write_surface reads
+        (src/utils/io.cpp:182-255) -- eta-face gradients on the j = 0 faces of state which_res, pressure of the two lowest cell
+        rows of state which_q."""
+        gu, gv = np.empty((self.nic, 2)), np.empty((self.nic, 2))
+        p0, p1 = np.empty(self.nic), np.empty(self.nic)
+        self._ck(self.L.sgpu_wall_data(self.h, int(which_res), int(which_q), _dp(gu), _dp(gv), _dp(p0), _dp(p1)))
+        return gu, gv, p0, p1
+
+    def surface(self, which_res: int = 0, which_q: int = 0, i_first: Optional[int] = None, count: Optional[int] = None,
+                aoa: Optional[float] = None) -> dict:
+        """IOManager::write_surface (src/utils/io.cpp:182-255): xw, cp, cf per wall column and
+        coeffs = [cl_pressure, cd_pressure, cl_viscous, cd_viscous, cl, cd].  Default range = the reference's
+        j1 - 1 .. j1 - 1 + nb with j1 = geometry.tail, nb = ni - 2 j1 + 1 (src/utils/mesh.cpp:349-350)."""
+        if i_first is None:
+            i_first, count = self.case.tail - 1, self.case.ni - 2*self.case.tail + 1
+        aoa = self.case.aoa if aoa is None else aoa
+        xw, cp, cf, coeffs = np.empty(count), np.empty(count), np.empty(count), np.empty(6)
+        self._ck(self.L.sgpu_surface(self.h, int(which_res), int(which_q), int(i_first), int(count), ctypes.c_double(aoa),
+                                     _dp(xw), _dp(cp), _dp(cf), _dp(coeffs)))
+        return dict(xw=xw, cp=cp, cf=cf, coeffs=coeffs)
+
+    def write_surface(self, path: str, **kw) -> dict:
+        """the `<label>.surface` text file of the reference: `xw cp cf` per line, ostream default precision (io.cpp:225)"""
+        s = self.surface(**kw)
+        with open(path, "w") as f:
+            for a, b, c in zip(s["xw"], s["cp"], s["cf"]):
+                f.write("%g %g %g\n" % (a, b, c))
+        return s
 
     def dres_dbeta(self) -> np.ndarray:
         """d rhs4 / d beta per cell at the device state (SA extension; field-inversion gradient building block)"""

@@ -313,6 +313,48 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wall data of IOManager::write_surface (src/utils/io.cpp:182-255): the eta-face gradients of u and v on the
+// j = 0 faces as the last residual evaluation left them in EulerEquation's work arrays (Mesh::calc_gradient
+// with its j == 0 variant, src/utils/mesh.cpp:88-107,127-128) and the pressure of the two lowest cell rows of
+// the final state (Solution::p, unpadded, filled by IOManager::write, io.cpp:41).  One thread per cell column.
+//   q_res: state whose ghosts/gradients are used (BCs already applied); q_fin: the final state
+// out = gu[nic][2] | gv[nic][2] | p0[nic] | p1[nic] | xc0[nic] | dx[nic] | dy[nic]
+// ------------------------------------------------------------------------------------------------
+__global__ void wall_data_kernel(View v, Metrics m, const double* __restrict__ q_res, const double* __restrict__ q_fin,
+                                 const double* __restrict__ xv, const double* __restrict__ yv, double* __restrict__ out) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= v.nic) return;
+    const int nic = v.nic;
+    const size_t pl = v.plane;
+    const int r0 = JOFF, rg = JOFF - 1;                 // cell row j = 0 and the bottom ghost row
+    auto prim = [&](const double* q, int r, int c, double& u, double& vv, double& p) {      // fluid.cpp:50-67
+        const size_t o = v.at(r, c);
+        const double rho = q[o];
+        u = q[pl + o]/rho; vv = q[2*pl + o]/rho;
+        p = (q[3*pl + o] - 0.5*rho*(u*u + vv*vv))*(GAMMA - 1.0);
+    };
+    double* gu = out; double* gv = gu + 2*(size_t)nic; double* p0 = gv + 2*(size_t)nic; double* p1 = p0 + nic;
+    double* xc0 = p1 + nic; double* dx = xc0 + nic; double* dy = dx + nic;
+    const int c = i + IOFF;
+    double ut, vt, ub, vb, ua, va, ud, vd, pp;
+    prim(q_fin, r0, c, ua, va, pp); p0[i] = pp;
+    prim(q_fin, r0 + 1, c, ua, va, pp); p1[i] = pp;
+    prim(q_res, r0, c, ut, vt, pp); prim(q_res, rg, c, ub, vb, pp);
+    prim(q_res, r0, c - 1, ua, va, pp); prim(q_res, rg, c - 1, ud, vd, pp);
+    const double ul = 0.25*(ut + ub + ua + ud), vl = 0.25*(vt + vb + va + vd);           // mesh.cpp:96
+    prim(q_res, r0, c + 1, ua, va, pp); prim(q_res, rg, c + 1, ud, vd, pp);
+    const double ur = 0.25*(ut + ub + ua + ud), vr = 0.25*(vt + vb + va + vd);           // mesh.cpp:97
+    const size_t o = v.at(r0, c), o1 = v.at(r0 + 1, c), oc1 = v.at(r0, c + 1);
+    const double vol = m.vol[o];
+    const double tx = 0.5*(m.nex[o] + m.nex[o1]), ty = 0.5*(m.ney[o] + m.ney[o1]);       // mesh.cpp:99-107
+    const double bx = m.nex[o], by = m.ney[o], lx = m.ncx[o], ly = m.ncy[o], rx = m.ncx[oc1], ry = m.ncy[oc1];
+    gu[2*i] = (tx*ut - bx*ub + rx*ur - lx*ul)/vol; gu[2*i + 1] = (ty*ut - by*ub + ry*ur - ly*ul)/vol;   // :127-128
+    gv[2*i] = (tx*vt - bx*vb + rx*vr - lx*vl)/vol; gv[2*i + 1] = (ty*vt - by*vb + ry*vr - ly*vl)/vol;
+    xc0[i] = 0.25*(xv[o] + xv[oc1] + xv[o1] + xv[v.at(r0 + 1, c + 1)]);                  // mesh.cpp:199
+    dx[i] = xv[oc1] - xv[o]; dy[i] = yv[oc1] - yv[o];
+}
+
 __global__ void fill_kernel(double* __restrict__ p, size_t n, double val) {
     size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x*blockDim.x;

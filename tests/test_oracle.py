@@ -1,9 +1,11 @@
 """CPU suite: the oracle against the reference's own outputs (golden fixtures) and, where oracle/_ref
 exists (build container), against the reference compiled as a library."""
+import os
+
 import numpy as np
 import pytest
 
-from helpers import TOL, field_rel_err, golden, golden_state, jac_rel_err
+from helpers import GOLDEN, TOL, field_rel_err, golden, golden_state, jac_rel_err
 from oracle.bindings import PortOracle, RefOracle, have_ref, rk4_step_cpu
 from structured_b200.cases import ZOO, zoo_case
 
@@ -99,3 +101,43 @@ def test_sa_port_properties():
     fd = (ps.residual(q + h * v) - ps.residual(q - h * v)).reshape(-1) / (2 * h)
     assert np.abs(Jv - fd).max() / np.abs(fd).max() < 1e-6
     ps.close(); pl.close()
+
+
+def test_port_surface_matches_reference_golden():
+    """IOManager::write_surface (src/utils/io.cpp:182-255): the arrays it reads are bit-identical to the reference's,
+    the text rows agree to the 6 significant digits the reference prints."""
+    case, _ = golden("naca0012")
+    z = np.load(os.path.join(GOLDEN, "naca0012_surface.npz"))
+    port = PortOracle(case)
+    s = port.surface(case.perturbed_q(float(z["amp_res"])), case.perturbed_q(float(z["amp_fin"])))
+    assert np.array_equal(s["wall"], z["wall"])
+    rows = np.stack([s["xw"], s["cp"], s["cf"]], axis=1)
+    assert rows.shape == z["rows"].shape == (case.ni - 2*case.tail + 1, 3)
+    assert (np.abs(rows - z["rows"]) <= 5.1e-6*np.abs(rows) + 1e-300).all()
+    # coefficient sums: independent numpy restatement of io.cpp:226-249
+    gux, guy, gvx, gvy, p0, p1 = s["wall"][:, case.tail - 1:case.tail - 1 + len(rows)]
+    qinf = 0.5*case.rho_inf*(case.u_inf**2 + case.v_inf**2)
+    i0 = case.tail - 1
+    dx = np.diff(case.xv[i0:i0 + len(rows) + 1, 0]); dy = np.diff(case.yv[i0:i0 + len(rows) + 1, 0])
+    tau = case.mu_inf*(guy - gvx)/qinf; sf = 2.0/3.0*(gux + gvy)
+    sxx = case.mu_inf*(2*gux - sf)/qinf; syy = case.mu_inf*(2*gvy - sf)/qinf
+    fn_p, fc_p = -(s["cp"]*dx).sum(), (s["cp"]*dy).sum()
+    fn_v, fc_v = (-tau*dy + syy*dx).sum(), (tau*dx - sxx*dy).sum()
+    ca, sa = np.cos(case.aoa), np.sin(case.aoa)
+    want = np.array([-fc_p*sa + fn_p*ca, fc_p*ca + fn_p*sa, -fc_v*sa + fn_v*ca, fc_v*ca + fn_v*sa])
+    scale = np.abs(np.array([fn_p, fc_p, fn_v, fc_v])).max()
+    assert np.abs(s["coeffs"][:4] - want).max() <= 1e-12*scale
+    assert np.allclose(s["coeffs"][4:], [want[0] + want[2], want[1] + want[3]], rtol=1e-13)
+    port.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_surface_matches_reference_library_channel():
+    case, _ = golden("channel")
+    ref = RefOracle(case); port = PortOracle(case)
+    q = case.perturbed_q(0.02)
+    rows, wall = ref.surface(q)
+    s = port.surface(q)
+    assert np.array_equal(s["wall"], wall)
+    assert len(rows) == len(s["xw"])
+    ref.close(); port.close()
