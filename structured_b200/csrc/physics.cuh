@@ -45,16 +45,14 @@ __device__ __forceinline__ double s_sqrt(double x) { return x > 0.0 ? x*rsqrt_fa
 __device__ __forceinline__ double s_abs(double x) { return fabs(x); }
 __device__ __forceinline__ double s_val(double x) { return x; }
 // x^(2/3): FluidModel::get_laminar_viscosity uses pow(T/T_ref, 2.0/3.0) (src/model/fluid.cpp:38-40).  libdevice's
-// cbrt costs ~80 issue slots; here a float seed (MUFU.LG2/EX2, ~1e-6), one Halley step on s^3 = x^2 (cubic) and one
-// Newton correction with the stale slope: 16 fp64 instructions, measured max relative error 4.4e-16 on [1e-3, 1e3].
+// cbrt costs ~80 issue slots; here x^(2/3) = x y with y = x^(-1/3) from a float seed (MUFU.LG2/EX2, ~1e-6) and ONE
+// division-free third-order step, y = y0 (1 + e/3 + 2 e^2/9), e = 1 - x y0^3 (truncation 0.17 e^3 ~ 5e-18): 7 fp64
+// instructions, no reciprocal in the dependency chain; measured max relative error 4.4e-16 on [1e-3, 1e3].
 __device__ __forceinline__ double s_pow23(double x) {
-    const double s0 = (double)__powf((float)x, 0.666666667f);
-    const double a = x*x;
-    const double s3 = s0*s0*s0;
-    const double rd = rcp_fast(fma(2.0, s3, a));
-    const double s1 = s0*(fma(2.0, a, s3)*rd);
-    const double res = fma(s1*s1, s1, -a);
-    return fma(-res, s0*rd, s1);
+    const double y0 = (double)__powf((float)x, -0.333333333f);
+    const double e = fma(-x, y0*y0*y0, 1.0);
+    const double pe = fma(2.0/9.0, e, 1.0/3.0)*e;
+    return x*fma(y0, pe, y0);
 }
 // x^(1/6) for the SA f_w function: float seed + two Newton steps on y^6 = x (measured 8.9e-16 on [1e-33, 1e3])
 __device__ __forceinline__ double s_pow16(double x) {
@@ -222,6 +220,44 @@ __device__ __forceinline__ S sa_source(S rho, S nut, S mul, S om, S dndx, S dndy
     S g2 = gg*gg, g6 = g2*g2*g2;
     S fw = gg*s_pow16((1.0 + cw36)*s_rcp(g6 + cw36));
     S nd = nut*id;
+    return rho*(beta*SA_CB1*st*nut - cw1*fw*nd*nd) + (SA_CB2/SA_SIGMA)*rho*(dndx*dndx + dndy*dndy);
+}
+
+// double-only form of sa_source for the residual kernel, given mu_t = rho nu~ f_v1 (already in the kernel's ring):
+// X f_v1 = mu_t/mu, so f_v2 = 1 - X/(1 + X f_v1) needs one reciprocal of mu instead of re-deriving f_v1 (two), and
+// the sixth root is taken division-free (see below).
+// Same formulas as the template above; differs from it by rounding only.
+__device__ __forceinline__ double sa_source_mut(double rho, double nut, double mul, double mut, double om, double dndx, double dndy,
+                                                double d, double beta) {
+    const double k2 = SA_KAPPA*SA_KAPPA;
+    const double cw1 = SA_CB1/k2 + (1.0 + SA_CB2)/SA_SIGMA;
+    const double cw36 = 64.0;   // cw3^6
+    const double imul = rcp_fast(mul);
+    const double chi = rho*nut*imul;
+    const double fv2 = fma(-chi, rcp_fast(fma(mut, imul, 1.0)), 1.0);
+    const double k2d2 = k2*d*d;
+    const double id = rcp_fast(d);
+    const double sbar = nut*fv2*(id*id*(1.0/k2));
+    double st = om + sbar;
+    const double st_min = 0.3*om;
+    if (st < st_min) st = st_min;
+    double den = st*k2d2;
+    if (den < 1e-30) den = 1e-30;
+    double r = nut*rcp_fast(den);
+    if (r > 10.0) r = 10.0;
+    const double r2 = r*r, r6 = r2*r2*r2;
+    const double gg = r + SA_CW2*(r6 - r);
+    const double g2 = gg*gg, g6 = g2*g2*g2;
+    // fw = g ((1 + cw3^6)/z)^(1/6), z = g^6 + cw3^6 in [64, 1e33]: y = z^(-1/6) from a float seed and one division-free
+    // third-order step y0 (1 + e/6 + 7 e^2/72), e = 1 - z y0^6 (truncation 0.07 e^3 ~ 1e-17) -- no reciprocal in the chain
+    const double z = g6 + cw36;
+    const double y0 = (double)__powf((float)z, -0.166666667f);
+    const double y02 = y0*y0;
+    const double e = fma(-z, y02*y02*y02, 1.0);
+    const double pe = fma(7.0/72.0, e, 1.0/6.0)*e;
+    const double y = 2.0051747451504216*fma(y0, pe, y0);       // 65^(1/6)
+    const double fw = gg*y;
+    const double nd = nut*id;
     return rho*(beta*SA_CB1*st*nut - cw1*fw*nd*nd) + (SA_CB2/SA_SIGMA)*rho*(dndx*dndx + dndy*dndy);
 }
 

@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         if (SA) {
             const double rn = pq[NV - 1];
             B[BN*RW + t] = rn*rcp_fast(rho);
-            if (VISC) B[BMT*RW + t] = rn*sa_fv1<double>(rn*rcp_fast(mul));
+            if (VISC) {                                  // mu_t = rho nu~ f_v1, f_v1 = X^3/(X^3 + c_v1^3), X = rho nu~/mu: one reciprocal
+                const double r3 = rn*rn*rn, m3 = mul*mul*mul;
+                B[BMT*RW + t] = rn*(r3*rcp_fast(fma(SA_CV1*SA_CV1*SA_CV1, m3, r3)));
+            }
         }
     };
     auto store_row_direct = [&](int jl) {                // prologue: straight from HBM
@@ -221,12 +224,13 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
     };
 
     // ---- eta face between local cell rows jl and jl+1 (global face row gj = j0+jl+1), column i
-    auto eta_face = [&](int jl, const double* ql, const double* qr, const double* vown, double* D, double* bars) {
+    // own = cell_vars(jl, t): loaded once per row by the caller and shared with the chi face
+    auto eta_face = [&](int jl, const double* ql, const double* qr, const double* vown, const double* own, double* D, double* bars) {
         const int gj = v.j0 + jl + 1;
         FaceGeom fg;
         const double* Mf = Mrow(jl + 1);
         fg.nx = Mf[MEX*RW + t]; fg.ny = Mf[MEY*RW + t];
-        double qt[NVA ? NVA : 1], qb[NVA ? NVA : 1], qrr[NVA ? NVA : 1];
+        double qt[NVA ? NVA : 1], qrr[NVA ? NVA : 1];
         if (VISC) {                                      // mesh.cpp:99-126 with clamped indices
             const int la = imax(gj - 1, 0) - v.j0, lb = imin(gj, v.njc - 1) - v.j0;     // local rows of the two cells
             const int lT = imin(gj + 1, v.nj - 1) - v.j0, lBo = imax(gj - 1, 0) - v.j0;
@@ -236,22 +240,22 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
             fg.lx = MA[MCX*RW + t] + MB[MCX*RW + t]; fg.ly = MA[MCY*RW + t] + MB[MCY*RW + t];
             fg.rx = MA[MCX*RW + t + 1] + MB[MCX*RW + t + 1]; fg.ry = MA[MCY*RW + t + 1] + MB[MCY*RW + t + 1];
             fg.ivol2 = rcp_fast(MA[MVOL*RW + t] + MB[MVOL*RW + t]);
-            cell_vars(jl + 1, t, qt); cell_vars(jl, t, qb);
+            cell_vars(jl + 1, t, qt);
 #pragma unroll
             for (int n = 0; n < NVA; n++) qrr[n] = sVX[n*RW + t + 1];
         }
-        const double nutL = SA ? Brow(jl)[BN*RW + t] : 0.0, nutR = SA ? Brow(jl + 1)[BN*RW + t] : 0.0;
-        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, qt, qb, qrr, vown, D, bars);
+        const double nutL = SA ? (VISC ? own[VN] : Brow(jl)[BN*RW + t]) : 0.0, nutR = SA ? (VISC ? qt[VN] : Brow(jl + 1)[BN*RW + t]) : 0.0;
+        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, qt, own, qrr, vown, D, bars);
     };
     // ---- chi face between cells (i-1, jl) and (i, jl)
-    auto chi_face = [&](int jl, const double* qr, const double* vtop, const double* vbot, double* D, double* bars) {
+    auto chi_face = [&](int jl, const double* qr, const double* vtop, const double* vbot, const double* own, double* D, double* bars) {
         double ql[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) ql[k] = sMX[k*RW + t - 1];
         FaceGeom fg;
         const double* M0 = Mrow(jl); const double* M1 = Mrow(jl + 1);
         fg.nx = M0[MCX*RW + t]; fg.ny = M0[MCY*RW + t];
-        double qrr[NVA ? NVA : 1], qll[NVA ? NVA : 1];
+        double qll[NVA ? NVA : 1];
         if (VISC) {                                      // mesh.cpp:54-82 with clamped indices
             const int ta = t - 1 + (i == 0 ? 1 : 0), tb = t - (i == v.nic ? 1 : 0);
             const int tR = t + (i + 1 <= v.ni - 1 ? 1 : 0), tL = t - (i - 1 >= 0 ? 1 : 0);
@@ -260,10 +264,10 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
             fg.rx = fg.nx + M0[MCX*RW + tR]; fg.ry = fg.ny + M0[MCY*RW + tR];
             fg.lx = fg.nx + M0[MCX*RW + tL]; fg.ly = fg.ny + M0[MCY*RW + tL];
             fg.ivol2 = rcp_fast(M0[MVOL*RW + ta] + M0[MVOL*RW + tb]);
-            cell_vars(jl, t, qrr); cell_vars(jl, t - 1, qll);
+            cell_vars(jl, t - 1, qll);
         }
-        const double nutL = SA ? Brow(jl)[BN*RW + t - 1] : 0.0, nutR = SA ? Brow(jl)[BN*RW + t] : 0.0;
-        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, vtop, vbot, qrr, qll, D, bars);
+        const double nutL = SA ? (VISC ? qll[VN] : Brow(jl)[BN*RW + t - 1]) : 0.0, nutR = SA ? (VISC ? own[VN] : Brow(jl)[BN*RW + t]) : 0.0;
+        face_net_flux<NV, FLUX, VISC>(g, fg, ql, qr, nutL, nutR, vtop, vbot, own, qll, D, bars);
     };
 
     // ---- prologue: rows ra-2 .. ra+1 into the rings; limiter of cells ra-1 and ra along j; vertex row ra;
@@ -286,7 +290,9 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         eta_limiter(ra - 1, qlo /*to_high of cell ra-1*/, dummy);
         eta_limiter(ra, ehi, elo);
         __syncthreads();
-        if (cell_ok) eta_face(ra - 1, qlo, elo, vbot, Dbot, bbot);
+        double own0[NVA ? NVA : 1];
+        if (VISC) cell_vars(ra - 1, t, own0);
+        if (cell_ok) eta_face(ra - 1, qlo, elo, vbot, own0, Dbot, bbot);
         else {
 #pragma unroll
             for (int k = 0; k < NV; k++) Dbot[k] = 0.0;
@@ -318,8 +324,10 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         // both faces unconditionally, in one basic block: the halo lanes of a warp execute the face code anyway, and
         // without the two divergent regions the scheduler interleaves the independent eta / chi chains (A/B: 1.365 ->
         // 1.358 ms).  Halo lanes compute on in-range shared memory and never store.
-        eta_face(jl, ehi, elo, vtop, Dtop, btop);
-        chi_face(jl, cqr, vtop, vbot, Dchi, bchi);
+        double own[NVA ? NVA : 1];
+        if (VISC) cell_vars(jl, t, own);
+        eta_face(jl, ehi, elo, vtop, own, Dtop, btop);
+        chi_face(jl, cqr, vtop, vbot, own, Dchi, bchi);
         if (face_ok) {
 #pragma unroll
             for (int k = 0; k < NV; k++) sFC[k*RW + t] = Dchi[k];
@@ -349,7 +357,9 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
                     om = fabs(dvdx - dudy);
                 }
                 const double mul = VISC ? Brow(jl)[BM*RW + t] : g.mu_ref;
-                const double src = sa_source<double>(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, om, dndx, dndy, wd, beta);
+                // the double-only SA source reuses mu_t from the ring (one reciprocal fewer, division-free sixth root)
+                const double src = VISC ? sa_source_mut(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, Brow(jl)[BMT*RW + t], om, dndx, dndy, wd, beta)
+                                        : sa_source<double>(Arow(jl)[t], Brow(jl)[BN*RW + t], mul, om, dndx, dndy, wd, beta);
                 res[NV - 1] += src*V;
             }
 #pragma unroll
