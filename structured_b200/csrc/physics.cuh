@@ -120,15 +120,15 @@ __device__ __forceinline__ void muscl_cell(double qm, double q0, double qp, doub
 template <class S>
 __device__ __forceinline__ void roe_flux(double nx, double ny, S rlft, S ulft, S vlft, S plft,
                                          S rrht, S urht, S vrht, S prht, S* f) {
-    // one reciprocal for both densities; reciprocal square roots give (rat), (cav, 1/c^2) and (|n|, n/|n|)
-    S pi = s_rcp(rlft*rrht);
+    // ONE reciprocal square root of rho_L rho_R gives 1/(rho_L rho_R) (both 1/rho) and sqrt(rho_L rho_R) (the Roe density and,
+    // times 1/rho_L, the Roe weight): dependency depth rsqrt -> rcp instead of rcp -> rsqrt -> rcp
+    S rr_ = rlft*rrht, yrr = s_rsqrt(rr_), pi = yrr*yrr;
     S rlfti = rrht*pi, rrhti = rlft*pi;
     S rulft = rlft*ulft, rvlft = rlft*vlft;
     S uvl = 0.5*(ulft*ulft + vlft*vlft), elft = plft*OGM1 + rlft*uvl, hlft = (elft + plft)*rlfti;
     S rurht = rrht*urht, rvrht = rrht*vrht;
     S uvr = 0.5*(urht*urht + vrht*vrht), erht = prht*OGM1 + rrht*uvr, hrht = (erht + prht)*rrhti;
-    S t = rrht*rlfti;
-    S rat = t*s_rsqrt(t), rati = s_rcp(rat + 1.0), rav = rat*rlft;
+    S rav = rr_*yrr, rat = rav*rlfti, rati = s_rcp(rat + 1.0);
     S uav = (rat*urht + ulft)*rati, vav = (rat*vrht + vlft)*rati, hav = (rat*hrht + hlft)*rati;
     S uv = 0.5*(uav*uav + vav*vav);
     S c2 = GM1*(hav - uv);
@@ -224,7 +224,7 @@ __device__ __forceinline__ S sa_source(S rho, S nut, S mul, S om, S dndx, S dndy
 }
 
 // double-only form of sa_source for the residual kernel, given mu_t = rho nu~ f_v1 (already in the kernel's ring):
-// X f_v1 = mu_t/mu, so f_v2 = 1 - X/(1 + X f_v1) needs one reciprocal of mu instead of re-deriving f_v1 (two), and
+// X f_v1 = mu_t/mu, so f_v2 = 1 - X/(1 + X f_v1) = 1 - rho nu~/(mu + mu_t) needs one reciprocal instead of three, and
 // the sixth root is taken division-free (see below).
 // Same formulas as the template above; differs from it by rounding only.
 __device__ __forceinline__ double sa_source_mut(double rho, double nut, double mul, double mut, double om, double dndx, double dndy,
@@ -232,9 +232,7 @@ __device__ __forceinline__ double sa_source_mut(double rho, double nut, double m
     const double k2 = SA_KAPPA*SA_KAPPA;
     const double cw1 = SA_CB1/k2 + (1.0 + SA_CB2)/SA_SIGMA;
     const double cw36 = 64.0;   // cw3^6
-    const double imul = rcp_fast(mul);
-    const double chi = rho*nut*imul;
-    const double fv2 = fma(-chi, rcp_fast(fma(mut, imul, 1.0)), 1.0);
+    const double fv2 = fma(-rho*nut, rcp_fast(mul + mut), 1.0);     // X/(1 + X f_v1) = rho nu~/(mu + mu_t)
     const double k2d2 = k2*d*d;
     const double id = rcp_fast(d);
     const double sbar = nut*fv2*(id*id*(1.0/k2));
