@@ -171,6 +171,13 @@ int sgpu_wall_data(sgpu_ctx* ctx, int which_res, int which_q, double* grad_u, do
 int sgpu_surface(sgpu_ctx* ctx, int which_res, int which_q, int i_first, int count, double aoa,
                  double* xw, double* cp, double* cf, double* coeffs);
 
+/* d F / d q of the surface functional F = sum_k weights[k] coeffs[k], k = cl_pressure, cd_pressure, cl_viscous, cd_viscous
+ * (the first four coefficients of sgpu_surface, evaluated with which_res = which_q = which): the right-hand side g of the
+ * adjoint system (d rhs/d q)^T psi = -g for sgpu_adjoint_solve (no reference counterpart -- the
+ * reference never differentiates its surface loop).  Ghost cells are chained through the boundary conditions that wrote
+ * them.  dFdq: GLOBAL host [nic][njc][nv], fully written (zeros away from the wall). */
+int sgpu_surface_gradient(sgpu_ctx* ctx, int which, int i_first, int count, double aoa, const double* weights, double* dFdq);
+
 /* ---- device linear solve ---------------------------------------------------- */
 /* Replaces, for a Jacobian that stays on the device, the reference's linear-solver plug-in
  *     linearsolver->set_lhs(nnz, rind, cind, values); set_rhs(rhs); solve_and_update(q, UNDER_RELAXATION)

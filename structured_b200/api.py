@@ -24,7 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
-    "sgpu_wall_data", "sgpu_surface",
+    "sgpu_wall_data", "sgpu_surface", "sgpu_surface_gradient",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
@@ -389,6 +389,19 @@ class GpuEulerEquation:
         self._ck(self.L.sgpu_surface(self.h, int(which_res), int(which_q), int(i_first), int(count), ctypes.c_double(aoa),
                                      _dp(xw), _dp(cp), _dp(cf), _dp(coeffs)))
         return dict(xw=xw, cp=cp, cf=cf, coeffs=coeffs)
+
+    def surface_gradient(self, weights, which: int = 0, i_first: Optional[int] = None, count: Optional[int] = None,
+                         aoa: Optional[float] = None) -> np.ndarray:
+        """d/dq [nic][njc][nv] of sum_k weights[k]*coeffs[k], k = cl_pressure, cd_pressure, cl_viscous, cd_viscous of
+        `surface(which, which)`: the adjoint right-hand side of a force objective."""
+        if i_first is None:
+            i_first, count = self.case.tail - 1, self.case.ni - 2*self.case.tail + 1
+        aoa = self.case.aoa if aoa is None else aoa
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (4,)
+        out = self._state_array()
+        self._ck(self.L.sgpu_surface_gradient(self.h, int(which), int(i_first), int(count), ctypes.c_double(aoa), _dp(w), _dp(out)))
+        return out
 
     def write_surface(self, path: str, **kw) -> dict:
         """the `<label>.surface` text file of the reference: `xw cp cf` per line, ostream default precision (io.cpp:225)"""

@@ -204,6 +204,35 @@ int sgpu_dres_dbeta(sgpu_ctx* c, double* out) {
     return SGPU_OK;
 }
 
+int sgpu_surface_gradient(sgpu_ctx* c, int which, int i_first, int count, double aoa, const double* weights, double* dFdq) {
+    if (!c || !weights || !dFdq || which < 0 || which > 1) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    const View& v = c->v;
+    if (v.j0 != 0 || v.j1 != v.njc) FAIL(c, SGPU_ERR_STATE, "sgpu_surface_gradient needs the whole grid on one context (boundary-condition chains cross slabs)");
+    if (i_first < 0 || count < 0 || i_first + count > v.nic) FAIL(c, SGPU_ERR_ARG, "surface range [%d, %d) outside the %d cell columns", i_first, i_first + count, v.nic);
+    CK(c, cudaSetDevice(c->device));
+    if (!c->ghost_tab) if (int rc = build_ghost_table(c)) return rc;
+    if (int rc = apply_bcs(c, which)) return rc;
+    double* g = nullptr;
+    CK(c, cudaMalloc(&g, v.plane*v.nv*sizeof(double)));
+    CK(c, cudaMemsetAsync(g, 0, v.plane*v.nv*sizeof(double), c->stream));
+    // cl = -Fc sin(aoa) + Fn cos(aoa), cd = Fc cos(aoa) + Fn sin(aoa)   (io.cpp:240-246)
+    const double ca = cos(aoa), sa = sin(aoa);
+    const double a_np = weights[0]*ca + weights[1]*sa, a_cp = -weights[0]*sa + weights[1]*ca;
+    const double a_nv = weights[2]*ca + weights[3]*sa, a_cv = -weights[2]*sa + weights[3]*ca;
+    const double qinf = 0.5*c->d.rho_inf*(c->d.u_inf*c->d.u_inf + c->d.v_inf*c->d.v_inf);
+    if (count > 0) {
+        const GhostTable gt = ghost_table_of(c);
+        const Metrics m = metrics_of(c);
+        if (v.nv == 5) surface_grad_kernel<5><<<(count + 63)/64, 64, 0, c->stream>>>(v, c->g, m, gt, c->q[which], c->xv, c->yv, i_first, count, a_np, a_cp, a_nv, a_cv, c->d.mu_inf, qinf, g);
+        else surface_grad_kernel<4><<<(count + 63)/64, 64, 0, c->stream>>>(v, c->g, m, gt, c->q[which], c->xv, c->yv, i_first, count, a_np, a_cp, a_nv, a_cv, c->d.mu_inf, qinf, g);
+        CKL(c); c->launches++;
+    }
+    int rc = download_planes(c, g, v.nv, dFdq);
+    cudaFree(g);
+    return rc;
+}
+
 int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) {
     if (!c || !x || !y) return SGPU_ERR_ARG;
     if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");

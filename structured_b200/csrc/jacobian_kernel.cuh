@@ -726,6 +726,116 @@ __global__ void sa_dbeta_kernel(View v, Gas g, Metrics m, const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// d(surface functional)/dq: the adjoint right-hand side of an objective built from IOManager::write_surface's
+// force coefficients (src/utils/io.cpp:219-249), F = a_np Fn_pressure + a_cp Fc_pressure + a_nv Fn_viscous + a_cv Fc_viscous.
+// One thread per wall column i: F's partial derivatives with respect to p(i,0), p(i,1) and the four wall-face gradient
+// components are constants of the column's geometry; the gradients are linear in (u, v) of the six cells of the j = 0
+// dual cell (mesh.cpp:88-128), three of which are ghosts.  Each cell's share is chained to its conservative variables and
+// scattered: interior cells directly, ghost cells through the BC that wrote them last (copy-type ghosts to the cell they
+// duplicate, functional ghosts through bc_ghost_jacobian -- the same maps the Jacobian fold uses), to depth 3.
+// out: nv planes, zeroed by the caller; columns overlap, so contributions are added atomically.
+// ---------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void surface_grad_kernel(View v, Gas g, Metrics m, GhostTable gt, const double* __restrict__ q,
+                                    const double* __restrict__ xv, const double* __restrict__ yv, int i_first, int count,
+                                    double a_np, double a_cp, double a_nv, double a_cv, double mu_inf, double qinf,
+                                    double* __restrict__ out) {
+    const int n = blockIdx.x*blockDim.x + threadIdx.x;
+    if (n >= count) return;
+    const int i = i_first + n, c = i + IOFF, r0 = JOFF;
+    const size_t pl = v.plane;
+    const size_t o = v.at(r0, c), o1 = v.at(r0 + 1, c), oc1 = v.at(r0, c + 1);
+    const double dx = xv[oc1] - xv[o], dy = yv[oc1] - yv[o];
+    const double ivol = 1.0/m.vol[o];
+    const double tx = 0.5*(m.nex[o] + m.nex[o1]), ty = 0.5*(m.ney[o] + m.ney[o1]);
+    const double bx = m.nex[o], by = m.ney[o], lx = m.ncx[o], ly = m.ncy[o], rx = m.ncx[oc1], ry = m.ncy[oc1];
+    // weights of the six cells in d/dx and d/dy of the face gradient: [column i-1, i, i+1][row: 0 = cell row j = 0, 1 = ghost row]
+    double wx[3][2], wy[3][2];
+    wx[1][0] = (tx + 0.25*(rx - lx))*ivol; wx[1][1] = (-bx + 0.25*(rx - lx))*ivol;
+    wx[2][0] = wx[2][1] = 0.25*rx*ivol;     wx[0][0] = wx[0][1] = -0.25*lx*ivol;
+    wy[1][0] = (ty + 0.25*(ry - ly))*ivol; wy[1][1] = (-by + 0.25*(ry - ly))*ivol;
+    wy[2][0] = wy[2][1] = 0.25*ry*ivol;     wy[0][0] = wy[0][1] = -0.25*ly*ivol;
+    // F_i = Cp cp_i + T tau_i + Sxx sxx_i + Syy syy_i  (io.cpp:223-237)
+    const double k = mu_inf/qinf;
+    const double T = -a_nv*dy + a_cv*dx, Sxx = -a_cv*dy, Syy = a_nv*dx;
+    const double Gux = k*((4.0/3.0)*Sxx - (2.0/3.0)*Syy), Gvy = k*((4.0/3.0)*Syy - (2.0/3.0)*Sxx);
+    const double Guy = k*T, Gvx = -k*T;
+    const double Cp = (-a_np*dx + a_cp*dy)*0.5/qinf;                  // dF/dp(i,0) = dF/dp(i,1)
+
+    struct Item { int ip, jp, depth; double w[NV]; };
+    Item st[8]; int sp = 0;
+    auto push_cell = [&](int ip, int jp, double du, double dv, double dp) {   // chain (u, v, p) -> q of that cell
+        const size_t oc = v.at(jp - 1 + JOFF, ip - 1 + IOFF);
+        const double rho = q[oc], ri = 1.0/rho, uu = q[pl + oc]*ri, vv = q[2*pl + oc]*ri;
+        Item& it = st[sp++];
+        it.ip = ip; it.jp = jp; it.depth = 0;
+        const double gp = dp*(GAMMA - 1.0);
+        it.w[0] = -(uu*du + vv*dv)*ri + gp*0.5*(uu*uu + vv*vv);
+        it.w[1] = du*ri - gp*uu; it.w[2] = dv*ri - gp*vv; it.w[3] = gp;
+        if (NV > 4) it.w[4] = 0.0;
+    };
+    auto drain = [&]() {
+        while (sp > 0) {
+            const Item it = st[--sp];
+            const int ip = it.ip, jp = it.jp;
+            if (ip < 0 || ip > gt.nic + 1 || jp < 0 || jp > gt.njc + 1) continue;
+            if (!gt.is_ghost(ip, jp)) {
+                const size_t oc = v.at(jp - 1 + JOFF, ip - 1 + IOFF);
+#pragma unroll
+                for (int e = 0; e < NV; e++) if (it.w[e] != 0.0) atomicAdd(out + e*pl + oc, it.w[e]);
+                continue;
+            }
+            if (it.depth >= 3) continue;
+            const GhostDesc& gd = gt.at(ip, jp);
+            if (gd.type == SGPU_BC_PERIODIC || gd.type == SGPU_BC_WAKE) {
+                Item& nx_ = st[sp++]; nx_ = it; nx_.ip = gd.a_ip; nx_.jp = gd.a_jp; nx_.depth = it.depth + 1;
+                continue;
+            }
+            if (gd.type == SGPU_BC_FREESTREAM || gd.type < 0) continue;      // constants
+            const bool has_b = gd.type != SGPU_BC_OUTFLOW;
+            double qa[NV], qb[NV];
+            auto ldq = [&](int pip, int pjp, double* dst) {
+                const size_t oc = v.at(pjp - 1 + JOFF, pip - 1 + IOFF);
+#pragma unroll
+                for (int e = 0; e < NV; e++) dst[e] = q[e*pl + oc];
+            };
+            ldq(gd.a_ip, gd.a_jp, qa);
+            if (has_b) ldq(gd.b_ip, gd.b_jp, qb); else {
+#pragma unroll
+                for (int e = 0; e < NV; e++) qb[e] = qa[e];
+            }
+            double nx = 0.0, ny = 0.0;
+            if (gd.type == SGPU_BC_SLIPWALL) {
+                const size_t of = v.at((gd.face == SGPU_FACE_BOTTOM ? 0 : v.njc) - v.j0 + JOFF, ip - 1 + IOFF);
+                nx = m.nex[of]; ny = m.ney[of];
+            }
+            double Ma[NV*NV], Mb[NV*NV];
+            bc_ghost_jacobian<NV>(g, gd, nx, ny, qa, qb, Ma, Mb);
+            for (int tt = 0; tt < (has_b ? 2 : 1); tt++) {
+                const double* M = tt ? Mb : Ma;
+                Item& nx_ = st[sp++];
+                nx_.ip = tt ? gd.b_ip : gd.a_ip; nx_.jp = tt ? gd.b_jp : gd.a_jp; nx_.depth = it.depth + 1;
+#pragma unroll
+                for (int cc = 0; cc < NV; cc++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int rr = 0; rr < NV; rr++) acc += it.w[rr]*M[rr*NV + cc];
+                    nx_.w[cc] = acc;
+                }
+            }
+        }
+    };
+    for (int dc = -1; dc <= 1; dc++)
+        for (int row = 0; row < 2; row++) {
+            const double du = Gux*wx[dc + 1][row] + Guy*wy[dc + 1][row], dv = Gvx*wx[dc + 1][row] + Gvy*wy[dc + 1][row];
+            push_cell(i + 1 + dc, row == 0 ? 1 : 0, du, dv, (dc == 0 && row == 0) ? Cp : 0.0);
+            drain();
+        }
+    push_cell(i + 1, 2, 0.0, 0.0, Cp);                                  // p(i, 1)
+    drain();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Slot -> column cell, shared by the COO export and the matrix-vector products
 // ---------------------------------------------------------------------------------------------------
 struct SlotCols {

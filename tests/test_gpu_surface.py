@@ -92,3 +92,77 @@ def test_surface_file_and_errors(tmp_path):
     with pytest.raises(SgpuError):
         top.wall_data()
     top.close()
+
+
+@pytest.mark.parametrize("make", [lambda: golden("naca0012")[0], lambda: zoo_case("A"), lambda: zoo_case("B"), lambda: zoo_case("C"),
+                                  lambda: zoo_case("D"), lambda: zoo_case("E"), lambda: turbulent_channel_case(48, 40, ntrans=1)])
+def test_surface_gradient_matches_finite_differences(make):
+    """d(sum_k w_k coeff_k)/dq from the device (ghost cells chained through their boundary conditions) against central
+    differences of the oracle's write_surface restatement along random directions.  No reference counterpart: parity
+    unpinned beyond this check."""
+    from oracle.bindings import PortOracle
+    case = make()
+    port = PortOracle(case)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q, SGPU_STATE_Q)
+    aoa = case.aoa if case.aoa else 0.05
+    w = np.array([0.7, -1.3, 0.9, 1.1])
+    g = eq.surface_gradient(w, SGPU_STATE_Q, 0, case.nic, aoa)
+    assert g.shape == q.shape and np.isfinite(g).all() and np.abs(g).max() > 0
+    F = lambda qq: float(w @ port.surface(qq, qq, 0, case.nic, aoa)["coeffs"][:4])
+    rng = np.random.default_rng(11)
+    scale_q = np.abs(q).mean(axis=(0, 1))
+    for trial in range(4):
+        v = rng.standard_normal(q.shape)*scale_q
+        if trial >= 2:                                                          # concentrate on the rows the functional sees
+            v[:, 3:-1] = 0.0
+        h = 1e-6
+        fd = (F(q + h*v) - F(q - h*v))/(2*h)
+        an = float((g*v).sum())
+        assert abs(fd - an) <= 2e-6*np.abs(g*v).sum() + 1e-300, (trial, fd, an)
+    eq.close(); port.close()
+
+
+def test_surface_gradient_single_weight_is_linear():
+    """the gradient is linear in the weights and vanishes for zero weights"""
+    case, _ = golden("naca0012")
+    eq = gpu_eq(case)
+    eq.set_state(case.perturbed_q(), SGPU_STATE_Q)
+    g0 = eq.surface_gradient(np.zeros(4))
+    assert not g0.any()
+    parts = [eq.surface_gradient(np.eye(4)[k]) for k in range(4)]
+    w = np.array([0.3, 2.0, -1.0, 0.5])
+    full = eq.surface_gradient(w)
+    want = sum(w[k]*parts[k] for k in range(4))
+    assert np.abs(full - want).max() <= 1e-12*np.abs(want).max()
+    eq.close()
+
+
+def test_force_objective_adjoint_equals_direct_sensitivity():
+    """Field-inversion chain at a laminar state: g = d(drag coefficient)/dq from sgpu_surface_gradient, steady adjoint
+    J^T psi = -g on the device (sgpu_adjoint_solve), and the adjoint identity -- for any residual perturbation ds the
+    direct sensitivity g^T dq with J dq = -ds (sparse LU of the COO Jacobian) equals psi^T ds."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    case = turbulent_channel_case(40, 32, ntrans=0, reynolds=2e4, periodic=False)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.001)
+    eq.set_state(q)
+    g = eq.surface_gradient(np.array([0.0, 1.0, 0.0, 1.0]), 0, 0, case.nic, 0.0)      # total drag of the bottom wall
+    assert np.abs(g).max() > 0 and not g[:, 3:-1].any()                               # only the wall rows (and BC sources) carry it
+    rj, cj, vj = eq.jacobian_coo()
+    n = q.size
+    J = sp.csc_matrix((vj, (rj.astype(np.int64), cj.astype(np.int64))), shape=(n, n))
+    psi, info = eq.adjoint_solve(g, cfl=1e4, max_steps=200, tol=1e-10, rtol=1e-4, restart=60, max_iter=600)
+    assert info["converged"], info
+    r = g.reshape(-1) + J.T @ psi.reshape(-1)
+    assert np.linalg.norm(r) <= 2e-10*np.linalg.norm(g)
+    rng = np.random.default_rng(3)
+    lu = spla.splu(J)
+    for _ in range(3):
+        ds = rng.standard_normal(n)
+        dq = lu.solve(-ds)
+        direct, adjoint = float(g.reshape(-1) @ dq), float(psi.reshape(-1) @ ds)
+        assert abs(direct - adjoint) <= 1e-7*max(abs(direct), abs(adjoint)), (direct, adjoint)
+    eq.close()
