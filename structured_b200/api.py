@@ -411,6 +411,19 @@ class GpuEulerEquation:
                 f.write("%g %g %g\n" % (a, b, c))
         return s
 
+    # ---- the reference's solution files, fed from the device state (IOManager, src/utils/io.cpp:104-180)
+    def write_restart(self, path: str, which: int = 0) -> None:
+        from . import io as _io
+        _io.write_restart(path, self.get_state(which))
+
+    def read_restart(self, path: str, which: int = 0) -> None:
+        from . import io as _io
+        self.set_state(_io.read_restart(path, self.nic, self.njc, self.nv), which)
+
+    def write_npz(self, path: str, which: int = 0) -> None:
+        from . import io as _io
+        _io.write_npz(path, self.case, self.get_state(which))
+
     def dres_dbeta(self) -> np.ndarray:
         """d rhs4 / d beta per cell at the device state (SA extension; field-inversion gradient building block)"""
         out = np.zeros((self.nic, self.njc))

@@ -258,3 +258,23 @@ def test_host_column_pipeline_equals_device_path_bitwise(ntrans, periodic):
         finally:
             del os.environ["SGPU_PIPE_CHUNKS"]
     eq.close()
+
+
+def test_solution_files_roundtrip_through_device(tmp_path):
+    """`.out` / `.npz` (IOManager::write_restart, read_restart, write_npz, src/utils/io.cpp:104-180) fed from the device planes"""
+    from structured_b200 import io as sio
+    case = turbulent_channel_case(37, 21, ntrans=1)
+    q = case.perturbed_q(0.02)
+    eq = gpu_eq(case)
+    eq.set_state(q)
+    eq.write_restart(str(tmp_path / "a.out"))
+    assert (tmp_path / "a.out").read_bytes() == np.ascontiguousarray(q).tobytes()
+    eq.set_state(case.freestream_q())
+    eq.read_restart(str(tmp_path / "a.out"))
+    assert np.array_equal(eq.get_state(), q)
+    eq.write_npz(str(tmp_path / "a.npz"))
+    z = np.load(tmp_path / "a.npz")
+    rho, u, v, p, T = sio.primitives(case, q)
+    assert np.array_equal(z["q"], q) and np.array_equal(z["p"], p) and np.array_equal(z["T"], T)
+    assert z["xc"].shape == (case.nic, case.njc)
+    eq.close()
