@@ -45,7 +45,8 @@ enum sgpu_face { SGPU_FACE_BOTTOM = 0, SGPU_FACE_RIGHT = 1, SGPU_FACE_TOP = 2, S
 /* solver.flux strings, src/model/eulerequation.cpp:123-128 */
 enum sgpu_flux { SGPU_FLUX_ROE = 0, SGPU_FLUX_AUSM = 1 };
 /* which state array a residual is evaluated on / an update writes (src/solver/solver.cpp:104,110) */
-enum sgpu_state { SGPU_STATE_Q = 0, SGPU_STATE_Q_TMP = 1 };
+enum sgpu_state { SGPU_STATE_Q = 0, SGPU_STATE_Q_TMP = 1,
+                  SGPU_STATE_LAST_RESIDUAL = -1 /* sgpu_wall_data / sgpu_surface only: the state the last tracked sgpu_residual saw */ };
 
 /* One [[boundary]] table (src/model/bc.cpp:472-488). start/end index the PADDED arrays, inclusive;
  * a negative `end` is resolved as in BoundaryContainer::get_index (bc.cpp:436-457). */
@@ -164,6 +165,11 @@ int sgpu_dres_dbeta(sgpu_ctx* ctx, double* out);
  * Only the slab that owns j = 0 may call this.  Host outputs: grad_u, grad_v [nic][2]; p_row0, p_row1 [nic];
  * any may be NULL. */
 int sgpu_wall_data(sgpu_ctx* ctx, int which_res, int which_q, double* grad_u, double* grad_v, double* p_row0, double* p_row1);
+/* The reference's grad arrays are simply whatever its LAST calc_residual left behind -- in an RK4 step the stage-3 state,
+ * which no longer exists once the step has updated q.  While tracking is on, every sgpu_residual (also inside
+ * sgpu_explicit_step / sgpu_implicit_step) keeps its wall rows (one O(nic) kernel), and which_res =
+ * SGPU_STATE_LAST_RESIDUAL selects them: the `.surface` file then equals the stock binary's. */
+int sgpu_track_wall(sgpu_ctx* ctx, int on);
 /* The loop of IOManager::write_surface over cell columns i in [i_first, i_first + count) (the reference uses
  * i_first = mesh->j1 - 1, count = mesh->nb, src/utils/io.cpp:219, src/utils/mesh.cpp:349-350): per column
  * xw = xc[i][0], cp, cf (each may be NULL), and coeffs[6] = {cl_pressure, cd_pressure, cl_viscous, cd_viscous, cl, cd}

@@ -85,6 +85,9 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
     auto solution = mesh->solution;
     const size_t nv = solution->nq + solution->ntrans;
     double l2sq[8] = {0}, l2norm[8] = {0};
+    // steps that end in IOManager::write (src/solver/solver.cpp:136-141,192-194) keep the wall rows of their last residual evaluation
+    const bool will_write = counter > config->solver->iteration_max || counter % config->io->fileout_frequency == 0;
+    gpu_check(sgpu_track_wall(ctx, will_write ? 1 : 0), ctx, "sgpu_track_wall");
     config->profiler->reset_time_residual();
 #if defined(STRUCTURED_GPU_DEVICE_SOLVE)
     // The whole implicit branch on the device (src/solver/solver.cpp:66-101,154-175): no COO export, no host linear solver.
@@ -135,12 +138,13 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
 #endif
     for (size_t k = 0; k < nv; k++) l2norm[k] = sqrt(l2sq[k]);
     // what IOManager::write reads: Solution::q, and -- in write_surface (src/utils/io.cpp:215-216,224-234) -- the wall-face
-    // rows grad_u_eta[i][0], grad_v_eta[i][0] of EulerEquation's work arrays, which the host no longer computes
+    // rows grad_u_eta[i][0], grad_v_eta[i][0] of EulerEquation's work arrays as the LAST calc_residual of this step left them
+    // (tracked on the device for the steps that write, see below)
     auto sync_host = [&]() {
         gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state");
         const size_t nic = mesh->nic;
         std::vector<double> gu(2*nic), gv(2*nic);
-        gpu_check(sgpu_wall_data(ctx, SGPU_STATE_Q, SGPU_STATE_Q, gu.data(), gv.data(), nullptr, nullptr), ctx, "sgpu_wall_data");
+        gpu_check(sgpu_wall_data(ctx, SGPU_STATE_LAST_RESIDUAL, SGPU_STATE_Q, gu.data(), gv.data(), nullptr, nullptr), ctx, "sgpu_wall_data");
         auto eq = mesh->equation;
         for (size_t i = 0; i < nic; i++)
             for (size_t k = 0; k < 2; k++) { eq->grad_u_eta[i][0][k] = gu[2*i + k]; eq->grad_v_eta[i][0][k] = gv[2*i + k]; }

@@ -24,7 +24,7 @@ SYMBOLS = [
     "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
-    "sgpu_wall_data", "sgpu_surface", "sgpu_surface_gradient",
+    "sgpu_wall_data", "sgpu_track_wall", "sgpu_surface", "sgpu_surface_gradient",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
@@ -367,6 +367,10 @@ class GpuEulerEquation:
         info = self._linsolve_info(io)
         info.update({"steps": steps.value, "rel_residual": rel.value})
         return psi, info
+
+    def track_wall(self, on: bool = True):
+        """keep the wall rows of every later residual evaluation (which_res = -1 then selects the last one)"""
+        self._ck(self.L.sgpu_track_wall(self.h, int(on)))
 
     def wall_data(self, which_res: int = 0, which_q: int = 0):
         """(grad_u [nic][2], grad_v [nic][2], p_row0 [nic], p_row1 [nic]): what IOManager::write_surface reads

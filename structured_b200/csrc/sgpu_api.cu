@@ -57,6 +57,7 @@ struct sgpu_ctx {
     void* ghost_tab = nullptr;
     int* jac_err = nullptr;
     bool have_grid = false, have_dt = false;
+    double* wall_last = nullptr; bool wall_track = false, wall_valid = false;   // wall rows of the last residual evaluation (sgpu_track_wall)
     std::string err;
     long long launches = 0;
     // kernel timing
@@ -192,6 +193,7 @@ int sgpu_destroy(sgpu_ctx* c) {
         cudaEventDestroy(c->pipe_start);
     }
     if (c->ghost_tab) cudaFree(c->ghost_tab);
+    if (c->wall_last) cudaFree(c->wall_last);
     if (c->jac_err) cudaFree(c->jac_err);
     for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
@@ -466,6 +468,12 @@ int sgpu_residual(sgpu_ctx* c, int which, int lhs, double* l2sq) {
     CK(c, cudaSetDevice(c->device));
     if (int rc = apply_bcs(c, which)) return rc;
     if (int rc = launch_residual(c, which, lhs, l2sq != nullptr)) return rc;
+    if (c->wall_track && c->v.j0 == 0 && c->v.njl >= 2) {         // keep what this evaluation would have left in grad_{u,v}_eta[i][0]
+        if (!c->wall_last) CK(c, cudaMalloc(&c->wall_last, 9*(size_t)c->v.nic*sizeof(double)));
+        wall_data_kernel<<<(c->v.nic + 127)/128, 128, 0, c->stream>>>(c->v, metrics_of(c), c->q[which], c->q[which], c->xv, c->yv, c->wall_last);
+        CKL(c); c->launches++;
+        c->wall_valid = true;
+    }
     if (l2sq) {
         CK(c, cudaMemcpyAsync(l2sq, c->l2sq_dev, sizeof(double)*c->v.nv, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
@@ -688,19 +696,30 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
 // ---------------------------------------------------------------------------------------------- surface output
 // device part of sgpu_wall_data / sgpu_surface: BCs on which_res, one small kernel, one D2H of 9 nic doubles
 static int wall_data_host(sgpu_ctx* c, int which_res, int which_q, std::vector<double>& h) {
-    if (!c || which_res < 0 || which_res > 1 || which_q < 0 || which_q > 1) return SGPU_ERR_ARG;
+    if (!c || which_res < SGPU_STATE_LAST_RESIDUAL || which_res > 1 || which_q < 0 || which_q > 1) return SGPU_ERR_ARG;
+    const bool last = which_res == SGPU_STATE_LAST_RESIDUAL;
+    if (last && !c->wall_valid) FAIL(c, SGPU_ERR_STATE, "no tracked residual evaluation: call sgpu_track_wall(ctx, 1) before the evaluation whose wall gradients are wanted");
+    if (last) which_res = which_q;
     if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
     const View& v = c->v;
     if (v.j0 != 0 || v.njl < 2) FAIL(c, SGPU_ERR_STATE, "the wall data live on the slab that owns j = 0 (with at least two cell rows)");
     CK(c, cudaSetDevice(c->device));
-    if (int rc = apply_bcs(c, which_res)) return rc;
+    if (!last) if (int rc = apply_bcs(c, which_res)) return rc;
     const size_t n = 9*(size_t)v.nic;
     if (int rc = ensure_stage(c, n)) return rc;
     wall_data_kernel<<<(v.nic + 127)/128, 128, 0, c->stream>>>(v, metrics_of(c), c->q[which_res], c->q[which_q], c->xv, c->yv, c->stage);
     CKL(c); c->launches++;
+    if (last) CK(c, cudaMemcpyAsync(c->stage, c->wall_last, 4*(size_t)v.nic*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // gu | gv of the tracked evaluation
     h.resize(n);
     CK(c, cudaMemcpyAsync(h.data(), c->stage, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+
+extern "C" int sgpu_track_wall(sgpu_ctx* c, int on) {
+    if (!c) return SGPU_ERR_ARG;
+    c->wall_track = on != 0;
+    if (!on) c->wall_valid = false;
     return SGPU_OK;
 }
 

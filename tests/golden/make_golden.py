@@ -89,6 +89,28 @@ def surface_fixture():
     print("surface", rows.shape)
 
 
+def explicit_surface_fixture():
+    """`<label>.surface` of the stock binary after the short explicit runs stored in channel.npz / naca0012.npz (same inputs):
+    the text IOManager::write_surface produced (src/utils/io.cpp:182-255) -- final pressure, gradients of the last RK stage."""
+    out = {}
+    for name in ("channel", "naca0012"):
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        inp = str(z["explicit_inp"])
+        import tomllib
+        t = tomllib.loads(inp)
+        src = os.path.join(REF, "examples/laminar", "channel" if name == "channel" else "naca0012", os.path.basename(t["geometry"]["filename"]))
+        with tempfile.TemporaryDirectory() as wd:
+            shutil.copy(src, wd)
+            with open(os.path.join(wd, "run.inp"), "w") as f:
+                f.write(inp)
+            subprocess.run([REF_BIN, "-c", "run.inp"], cwd=wd, check=True, stdout=subprocess.DEVNULL)
+            q = np.load(os.path.join(wd, t["io"]["label"] + ".npz"))["q"]
+            assert np.array_equal(q, z["explicit_q"])
+            out[name] = np.array(open(os.path.join(wd, t["io"]["label"] + ".surface")).read())
+    np.savez_compressed(os.path.join(HERE, "explicit_surface.npz"), **out)
+    print("explicit surface", {k: len(str(v).splitlines()) for k, v in out.items()})
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("needs the reference tree at /root/reference")
@@ -107,6 +129,7 @@ def main():
     fixture_from_config("naca0012", os.path.join(na, "config.inp"), 0.5, "sample",
                         dict(inp=ex, grid_src=os.path.join(na, "grid.unf2"), grid_name="grid.unf2", label="implicit", steps=n_it + 2))
     surface_fixture()
+    explicit_surface_fixture()
     for z in ZOO:
         case = zoo_case(z, 14, 10)
         with tempfile.TemporaryDirectory() as wd:

@@ -166,3 +166,35 @@ def test_force_objective_adjoint_equals_direct_sensitivity():
         direct, adjoint = float(g.reshape(-1) @ dq), float(psi.reshape(-1) @ ds)
         assert abs(direct - adjoint) <= 1e-7*max(abs(direct), abs(adjoint)), (direct, adjoint)
     eq.close()
+
+
+def test_tracked_wall_rows_are_those_of_the_last_residual_evaluation():
+    """sgpu_track_wall: after an RK4 step the wall gradients of SGPU_STATE_LAST_RESIDUAL are those of the stage-3 state (what the
+    reference's stale work arrays hold, src/solver/solver.cpp:109-114), the pressure rows those of the final state"""
+    from oracle.bindings import PortOracle, rk4_step_cpu
+    from structured_b200.api import SgpuError
+    case = zoo_case("A")
+    port = PortOracle(case)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q, SGPU_STATE_Q); eq.set_state(q, SGPU_STATE_Q_TMP)
+    with pytest.raises(SgpuError):
+        eq.wall_data(which_res=-1)                                              # nothing tracked yet
+    eq.track_wall(True)
+    eq.explicit_step(0.5, "rk4_jameson")
+    # CPU emulation of the same step, keeping the state of the last residual evaluation
+    dt = port.calc_dt(q, 0.5)
+    q_tmp = q.copy()
+    for order in range(4):
+        last = q_tmp.copy()
+        q_tmp = q + port.residual(last)*dt/(4.0 - order)
+    want = port.surface(last, q_tmp, 0, case.nic, 0.05)
+    got = eq.surface(-1, SGPU_STATE_Q, 0, case.nic, 0.05)
+    assert rel(got["cp"], want["cp"]) <= 1e-10
+    assert np.abs(got["cf"] - want["cf"]).max() <= 1e-10*np.abs(want["cf"]).max()
+    mixed = eq.surface(SGPU_STATE_Q, SGPU_STATE_Q, 0, case.nic, 0.05)           # the final-state gradients differ measurably
+    assert np.abs(mixed["cf"] - want["cf"]).max() > 1e-8*np.abs(want["cf"]).max()
+    eq.track_wall(False)
+    with pytest.raises(SgpuError):
+        eq.wall_data(which_res=-1)
+    eq.close(); port.close()
