@@ -88,8 +88,11 @@ static int lin_factor(sgpu_ctx* c, int matrix, int precond) {
     CK(c, cudaMemsetAsync(L->err, 0, sizeof(int), c->stream));
     if (precond == SGPU_PC_LINE_J) {
         const int nb = (v.nic + 31)/32;
-        if (v.nv == 5) line_factor_kernel<5><<<nb, 32, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err);
-        else line_factor_kernel<4><<<nb, 32, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err);
+#define LINE_FACTOR(NV_) do { \
+        CK(c, cudaFuncSetAttribute(line_factor_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_ring_bytes<NV_>())); \
+        line_factor_kernel<NV_><<<nb, 32, fact_ring_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); } while (0)
+        if (v.nv == 5) LINE_FACTOR(5); else LINE_FACTOR(4);
+#undef LINE_FACTOR
     } else {
         const dim3 grd((v.nic + 127)/128, v.njl);
         if (v.nv == 5) bj_factor_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->jac.blocks, c->dt, op, L->Dinv, L->err);

@@ -290,27 +290,75 @@ __device__ __forceinline__ void matmul_block(const double (&a)[NV][NV], const do
         }
 }
 
+// The recurrence D'_j = D_j - A'_j DC_{j-1} is sequential in j and only nic/32 warps exist, so the kernel is pure latency:
+// with the row's five Jacobian blocks loaded when the loop reaches them, every row paid 3-4 dependent DRAM round trips
+// (35 ms at 4096^2).  As in line_apply_kernel below, each lane streams the words it will read itself -- the blocks of slots
+// 0, 3, 11, 4, 12 and 1/dt of the rows ahead -- through a FACT_STAGES-deep shared-memory ring with cp.async: no barrier,
+// coalesced 256-byte row segments per plane, and the loop body is arithmetic only.
+constexpr int FACT_STAGES = 6;
+template <int NV> constexpr int fact_ring_planes() { return 5*NV*NV + 1; }
+template <int NV> constexpr size_t fact_ring_bytes() { return (size_t)FACT_STAGES*fact_ring_planes<NV>()*32*sizeof(double); }
+
+__device__ __forceinline__ void fact_cp_async8(double* smem, const double* g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(g) : "memory");
+}
+
 template <int NV>
 __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, int nslots,
                                                          double* __restrict__ F, int* __restrict__ err) {
-    const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= v.nic) return;
+    extern __shared__ double fring[];
+    constexpr int B = NV*NV, NP = 5*NV*NV + 1, S = FACT_STAGES;
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x*32 + lane;
+    const bool live = i < v.nic;
+    const int ic = live ? i : v.nic - 1;                           // idle lanes shadow the last line and never store
     const size_t pl = v.plane;
     double* __restrict__ Dinv = F;
     double* __restrict__ DA = F + (size_t)NV*NV*pl;
     double* __restrict__ DC = F + (size_t)2*NV*NV*pl;
     const bool arms = nslots > 9;
+    auto slot = [&](int st, int p) -> double* { return fring + ((size_t)st*NP + p)*32 + lane; };
+    auto issue = [&](int jl) {                                     // ring group g = 0..4 <- Jacobian slots 0, 3, 11, 4, 12
+        if (jl < v.njl) {
+            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            const int st = jl % S;
+#pragma unroll
+            for (int g = 0; g < 5; g++) {
+                const int sl = g == 0 ? 0 : (g == 1 ? 3 : (g == 2 ? 11 : (g == 3 ? 4 : 12)));
+                if ((g == 2 || g == 4) && !arms) continue;
+#pragma unroll
+                for (int e = 0; e < B; e++) fact_cp_async8(slot(st, g*B + e), J + ((size_t)sl*B + e)*pl + o);
+            }
+            if (op == OP_LHS) fact_cp_async8(slot(st, 5*B), dt + o);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // the same transform load_block applies: A = -J + I/dt for OP_LHS, J otherwise
+    auto ring_block = [&](int st, int g, double idt, bool diag, double (&a)[NV][NV]) {
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                const double vj = *slot(st, g*B + r*NV + c);
+                a[r][c] = op == OP_LHS ? ((diag && r == c) ? idt - vj : -vj) : vj;
+            }
+    };
+    for (int jl = 0; jl < S - 1; jl++) issue(jl);
     double DCp[NV][NV];                                            // DC_{j-1}
     for (int jl = 0; jl < v.njl; jl++) {
+        issue(jl + S - 1);
+        asm volatile("cp.async.wait_group %0;" :: "n"(S - 1) : "memory");
+        const int st = jl % S;
         const int gj = v.j0 + jl;
-        const size_t o = v.at(jl + JOFF, i + IOFF);
+        const size_t o = v.at(jl + JOFF, ic + IOFF);
         double D[NV][NV], A[NV][NV], T[NV][NV], I[NV][NV];
-        load_block<NV>(J, pl, o, 0, op, op == OP_LHS ? 1.0/dt[o] : 0.0, true, D);
+        ring_block(st, 0, op == OP_LHS ? 1.0/(*slot(st, 5*B)) : 0.0, true, D);
         const bool lo = jl > 0, hi = jl + 1 < v.njl;
         if (lo) {
-            load_block<NV>(J, pl, o, 3, op, 0.0, false, A);
+            ring_block(st, 1, 0.0, false, A);
             if (arms && gj - 2 >= 0) {
-                load_block<NV>(J, pl, o, 11, op, 0.0, false, T);
+                ring_block(st, 2, 0.0, false, T);
 #pragma unroll
                 for (int r = 0; r < NV; r++)
 #pragma unroll
@@ -329,14 +377,16 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
         }
         if (!invert_block<NV>(D, I)) atomicExch(err, 1);
         matmul_block<NV>(I, A, T);
+        if (live) {
 #pragma unroll
-        for (int r = 0; r < NV; r++)
+            for (int r = 0; r < NV; r++)
 #pragma unroll
-            for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DA[(size_t)(r*NV + c)*pl + o] = T[r][c]; }
+                for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DA[(size_t)(r*NV + c)*pl + o] = T[r][c]; }
+        }
         if (hi) {
-            load_block<NV>(J, pl, o, 4, op, 0.0, false, A);
+            ring_block(st, 3, 0.0, false, A);
             if (arms && gj + 2 <= v.njc - 1) {
-                load_block<NV>(J, pl, o, 12, op, 0.0, false, T);
+                ring_block(st, 4, 0.0, false, T);
 #pragma unroll
                 for (int r = 0; r < NV; r++)
 #pragma unroll
@@ -349,10 +399,12 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
 #pragma unroll
                 for (int c = 0; c < NV; c++) DCp[r][c] = 0.0;
         }
+        if (live) {
 #pragma unroll
-        for (int r = 0; r < NV; r++)
+            for (int r = 0; r < NV; r++)
 #pragma unroll
-            for (int c = 0; c < NV; c++) DC[(size_t)(r*NV + c)*pl + o] = DCp[r][c];
+                for (int c = 0; c < NV; c++) DC[(size_t)(r*NV + c)*pl + o] = DCp[r][c];
+        }
     }
 }
 
