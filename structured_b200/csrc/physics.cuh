@@ -102,18 +102,26 @@ __device__ __forceinline__ void muscl_cell(S qm, S q0, S qp, double eps, S& to_h
     to_low = q0 - f3qt*(thp*f2a + thm*f2b);
 }
 
-// double overload: the same limiter with the products contracted by hand -- m = f2a f2b once,
-// 1/4 (a1 + eps) = fma(3/4, m, eps/4), a2 + eps = fma(2 d, d, fma(3, m, eps)) -- 6 fp64 instructions fewer per
-// variable and direction than the generic form; differs from it by rounding only (<= 4 ulp of q0 measured).
-__device__ __forceinline__ void muscl_cell(double qm, double q0, double qp, double eps, double& to_high, double& to_low) {
-    const double f2a = q0 - qm, f2b = qp - q0;
-    const double m = f2b*f2a, d = f2b - f2a;
-    const double num = fma(0.75, m, 0.25*eps);
-    const double den = fma(d + d, d, fma(3.0, m, eps));
-    const double f3qt = num*rcp_fast(den);
-    const double g = f3qt*K23;                          // thm = 2/3, thp = 2 thm
-    to_high = fma(g, fma(2.0, f2b, f2a), q0);
-    to_low = fma(-g, fma(2.0, f2a, f2b), q0);
+// double form for the residual kernel: the same limiter with the products contracted by hand -- m = f2a f2b once,
+// 1/4 (a1 + eps) = fma(3/4, m, eps/4), a2 + eps = fma(2 d, d, fma(3, m, eps)), thp = 2 thm -- and two variables sharing
+// ONE reciprocal: 1/den_a = den_b/(den_a den_b) (den >= eps ~ 1e-8, products stay far inside the fp64 range).  Differs from
+// the template above by rounding only (<= 4 ulp of q0 measured).
+__device__ __forceinline__ void muscl_cell2(const double* qm, const double* q0, const double* qp, double eps, double* to_high, double* to_low) {
+    double f2a[2], f2b[2], num[2], den[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        f2a[k] = q0[k] - qm[k]; f2b[k] = qp[k] - q0[k];
+        const double m = f2b[k]*f2a[k], d = f2b[k] - f2a[k];
+        num[k] = fma(0.75, m, 0.25*eps);
+        den[k] = fma(d + d, d, fma(3.0, m, eps));
+    }
+    const double r = rcp_fast(den[0]*den[1]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double g = num[k]*(den[1 - k]*r)*K23;
+        to_high[k] = fma(g, fma(2.0, f2b[k], f2a[k]), q0[k]);
+        to_low[k] = fma(-g, fma(2.0, f2a[k], f2b[k]), q0[k]);
+    }
 }
 
 // ---- ConvectiveFluxRoe::evaluate, src/model/flux.cpp:51-146 ------------------------------------------

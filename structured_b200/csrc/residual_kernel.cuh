@@ -202,14 +202,20 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
     auto chi_limiter = [&](int jl, double* to_low) {
         const double* A = Arow(jl);
         const int tm = imax(t - 1, 0), tp = imin(t + 1, RW - 1);
+        // all four variables in ONE region, no branch: the limiter runs for every lane (a ghost column's result is discarded by
+        // a select), two variables share a reciprocal.  Four separate `if (interior)` regions per limiter kept the scheduler
+        // from interleaving the four reciprocal chains (A/B: 1.258 -> 1.176 ms for both limiters)
+        double qm_[4], q0_[4], qp_[4], hi_[4], lo_[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const double q0 = A[k*RW + t];
-            double hi = q0, lo = q0;                     // ghost / first order: the cell value (reconstruction.cpp:29-35)
-            if (ORDER == 2 && col_int) muscl_cell(A[k*RW + tm], q0, A[k*RW + tp], prm.eps_chi, hi, lo);
-            to_low[k] = lo;
-            sMX[k*RW + t] = hi;
+        for (int k = 0; k < 4; k++) { q0_[k] = A[k*RW + t]; qm_[k] = A[k*RW + tm]; qp_[k] = A[k*RW + tp]; hi_[k] = lo_[k] = q0_[k]; }   // ghost / first order: the cell value (reconstruction.cpp:29-35)
+        if (ORDER == 2) {
+            double h2[4], l2[4];
+            muscl_cell2(qm_, q0_, qp_, prm.eps_chi, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps_chi, h2 + 2, l2 + 2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { hi_[k] = col_int ? h2[k] : q0_[k]; lo_[k] = col_int ? l2[k] : q0_[k]; }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { to_low[k] = lo_[k]; sMX[k*RW + t] = hi_[k]; }
     };
     // MUSCL limiter of cell (i, jl) along j: to_high (left state of face jl+1), to_low (right state of face jl)
     // qp_reg: the primitives of row jl+1 in registers (main loop), or nullptr to read them from the ring
@@ -217,12 +223,14 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         const double* Am = Arow(jl - 1); const double* A0 = Arow(jl); const double* Ap = Arow(jl + 1);
         const int gjc = v.j0 + jl;
         const bool row_int = gjc >= 0 && gjc <= v.njc - 1;
+        double qm_[4], q0_[4], qp_[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const double q0 = A0[k*RW + t];
-            double hi = q0, lo = q0;
-            if (ORDER == 2 && row_int) muscl_cell(Am[k*RW + t], q0, qp_reg ? qp_reg[k] : Ap[k*RW + t], prm.eps_eta, hi, lo);
-            to_high[k] = hi; to_low[k] = lo;
+        for (int k = 0; k < 4; k++) { q0_[k] = A0[k*RW + t]; qm_[k] = Am[k*RW + t]; qp_[k] = qp_reg ? qp_reg[k] : Ap[k*RW + t]; to_high[k] = to_low[k] = q0_[k]; }
+        if (ORDER == 2) {
+            double h2[4], l2[4];
+            muscl_cell2(qm_, q0_, qp_, prm.eps_eta, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps_eta, h2 + 2, l2 + 2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { to_high[k] = row_int ? h2[k] : q0_[k]; to_low[k] = row_int ? l2[k] : q0_[k]; }
         }
     };
 
