@@ -11,11 +11,13 @@
 //   phase 1  converts the prefetched q of row jl+2 to primitives and stores them and the row's metrics into
 //            shared-memory rings (every HBM byte is loaded once, coalesced, one iteration ahead of its use);
 //            evaluates the MUSCL limiter of its own cell along i ONCE (both face values) and the vertex
-//            average of its lower-left... upper-left vertex ONCE, publishing what the right neighbour needs;
-//   phase 2  evaluates the limiter of cell (i, jl+1) along j once (one value used now, one carried in
-//            registers), the eta face on top of its cell and the chi face on its left -- each face flux is
-//            computed exactly once; the bottom eta flux, the lower vertex average and the left state of the
-//            next eta face are carried in registers, the right chi flux comes from thread t+1 via smem;
+//            average of its upper-left vertex ONCE, publishing what the right neighbour needs; evaluates the
+//            limiter of cell (i, jl+1) along j once (own column only: no barrier needed; one value used in
+//            phase 2, one carried in registers).  Both limiters run branch-free for all four variables;
+//   phase 2  evaluates the eta face on top of its cell and the chi face on its left, unconditionally and in one
+//            basic block -- each face flux is computed exactly once; the bottom eta flux, the lower vertex
+//            average and the left state of the next eta face are carried in registers, the right chi flux
+//            comes from thread t+1 via smem;
 //   phase 3  accumulates, adds sources, divides by V, stores rhs (coalesced) and accumulates rhs^2.
 // Two __syncthreads per row.  Arithmetic per cell is independent of the strip/chunk/slab decomposition, so
 // one GPU and N slabs agree bit for bit.
