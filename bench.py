@@ -52,6 +52,12 @@ def workload_dims(args, n_gpus):
     return 16384, 1024 * n_gpus, 1024
 
 
+def workload_name(nic, njc_total, nv, n_gpus, njc_per):
+    """identical in both arms (the driver pairs the lines by config); sampling details go to cpu_baseline.sample"""
+    return "SA turbulent bump channel %dx%d cells, MUSCL+Roe+viscous, nv=%d, fp64%s" % (
+        nic, njc_total, nv, "" if n_gpus == 1 else ", j-slabs of %dx%d per GPU" % (nic, njc_per))
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,6 +115,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(local, world):
+    """Pin this rank to its GPU's CPU set (`nvidia-smi topo -m`, column "CPU Affinity"); when several ranks share one set
+    the set is split evenly between them.  Returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        sets = {}
+        for ln in out.splitlines():
+            f = ln.split()
+            if not f or not f[0].startswith("GPU") or not f[0][3:].isdigit():
+                continue
+            rng = [x for x in f[1:] if x[0].isdigit() and ("-" in x or "," in x or x.isdigit())]
+            if not rng:
+                continue
+            cpus = set()
+            for part in rng[0].split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            sets[int(f[0][3:])] = sorted(cpus)
+        mine = sets.get(local)
+        if not mine:
+            return "unbound (no CPU affinity reported)"
+        sharers = sorted(g for g, c in sets.items() if c == mine and g < world)
+        if len(sharers) > 1 and local in sharers:
+            k, n = sharers.index(local), len(sharers)
+            per = max(1, len(mine) // n)
+            mine = mine[k * per:(k + 1) * per] or mine
+        allowed = sorted(set(mine) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, allowed)
+        return "cpus %d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))
+    except Exception as ex:  # noqa: BLE001
+        return "unbound (%s)" % str(ex)[:60]
+
+
+def copy_ceiling(torch, dist, world, h2d_bytes, d2h_bytes, reps=3):
+    """What the PCIe / host-memory path allows with NO kernel in between: every rank copies its e2e step's bytes
+    host->device and device->host concurrently on two streams; returns ms per step (max over ranks)."""
+    hin = torch.empty(h2d_bytes // 8, dtype=torch.float64).pin_memory()
+    hout = torch.empty(d2h_bytes // 8, dtype=torch.float64).pin_memory()
+    din = torch.empty(h2d_bytes // 8, dtype=torch.float64, device="cuda")
+    dout = torch.empty(d2h_bytes // 8, dtype=torch.float64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def once():
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+    once(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
+    for _ in range(reps):
+        once()
+    torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def build_case(nic, njc_total, ntrans, cell_rows=None):
     from structured_b200.cases import turbulent_channel_case
     return turbulent_channel_case(nic, njc_total, ntrans=ntrans, order=2, flux="roe", mach=0.2, reynolds=5e6, periodic=True,
@@ -128,6 +201,23 @@ def _cpu_worker(args):
     orc.time_residual(q, 1)
     t = orc.time_residual(q, reps)
     return t
+
+
+def _cpu_jacobian_worker(args):
+    nic, njc, ntrans = args
+    sys.path.insert(0, ROOT)
+    from oracle.bindings import PortOracle
+    case = build_case(nic, njc, ntrans)
+    orc = PortOracle(case)
+    t, nnz = orc.time_jacobian(case.perturbed_q(), True)
+    return t, nnz, orc.ncolors if hasattr(orc, "ncolors") else None
+
+
+def cpu_jacobian(nic, njc, ntrans):
+    """the oracle's stand-in for trace_on .. sparse_jac (src/solver/solver.cpp:72-90,154-157) on a bounded sample, 1 core"""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(1) as pool:
+        return pool.map(_cpu_jacobian_worker, [(nic, njc, ntrans)])[0]
 
 
 def cpu_throughput(kind, nic, njc, ntrans, reps, procs):
@@ -163,7 +253,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "residual_mcell_evals_per_s", "value": round(val, 4), "unit": "Mcell-evals/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / reps, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "SA turbulent bump channel %dx%d cells (timed on a %dx%d sample per core), MUSCL+Roe+viscous, nv=%d" % (nic, njc_total, sn, sn, 4 + args.ntrans)},
+           "config": {"workload": workload_name(nic, njc_total, 4 + args.ntrans, args.gpus, workload_dims(args, args.gpus)[2])},
            "cpu_baseline": {"value": round(val, 4), "unit": "Mcell-evals/s", "cores": cores, "kind": "port", "sample": sample, **extra},
            "e2e": {"value": round(val, 4), "unit": "Mcell-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -184,6 +274,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the GPU path has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_cpus(local, world)            # before any pinned allocation (first-touch locality of the staging pages)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -231,6 +322,35 @@ def run_ours(args):
             eq.halo_pull(0)          # device-side wait on the neighbours' flags, then unpack into the ghost rows
         else:
             halo.exchange(lambda side, t: eq.halo_pack(0, side, t.data_ptr()), lambda side, t: eq.halo_unpack(0, side, t.data_ptr()))
+
+    # ---- N > 1 self-check (outside the timed region): after corrupting the ghost rows, ONE exchange must deliver the rows
+    #      the host generated for them bit for bit, and the slab's rhs must equal the rhs of the window-uploaded state
+    halo_check = None
+    if world > 1:
+        ok = True
+        want = {}
+        for side, rows in ((LOW, (j0 - 2, j0)), (HIGH, (j1, j1 + 2))):
+            if (side == LOW and rank > 0) or (side == HIGH and rank < world - 1):
+                want[side] = np.ascontiguousarray(np.transpose(q[:, rows[0] - jw0:rows[1] - jw0, :], (2, 1, 0))).reshape(-1)   # [nv][2][nic]
+        eq.residual_device(0)
+        rhs_ref = np.zeros((nic, j1 - j0, nv)); eq.get_rhs_window(rhs_ref)      # ghosts uploaded from the host window
+        junk = torch.full((eq.halo_count(),), 7.0, dtype=torch.float64, device="cuda")
+        for side in want:
+            eq.halo_unpack(0, side, junk.data_ptr())
+        torch.cuda.synchronize(); dist.barrier()
+        exchange()
+        got = torch.empty(eq.halo_count(), dtype=torch.float64, device="cuda")
+        for side, w in want.items():
+            eq.halo_pack_ghost(0, side, got.data_ptr())
+            torch.cuda.synchronize()
+            ok = ok and np.array_equal(got.cpu().numpy(), w)
+        eq.residual_device(0)
+        rhs_x = np.zeros_like(rhs_ref); eq.get_rhs_window(rhs_x)
+        ok = ok and np.array_equal(rhs_x, rhs_ref)
+        del rhs_x, rhs_ref
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        halo_check = "bit-exact" if t.item() >= 1.0 else "FAILED"
 
     l2 = np.zeros(nv)
 
@@ -314,9 +434,15 @@ def run_ours(args):
         if dev_rhs is not None:
             chk = float(np.abs(rn - dev_rhs).max() / max(np.abs(dev_rhs).max(), 1e-300))
             dev_rhs = None
+        h2d_b, d2h_b = int(nic * rows_in * nv * 8), int(nic * njc_per * nv * 8)
+        ms_copy = copy_ceiling(torch, dist, world, h2d_b, d2h_b)
         e2e = {"value": round(cells_total / (ms_e / k_e2e * 1e-3) / 1e6, 3), "unit": "Mcell-evals/s", "rel_diff_vs_device_path": chk,
-               "h2d_bytes_per_step": int(nic * rows_in * nv * 8) * 1, "d2h_bytes_per_step": int(nic * njc_per * nv * 8),
-               "steps": k_e2e, "note": "per-GPU bytes; sgpu_residual_host(q_host, rhs_host) from pinned host arrays"}
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "steps": k_e2e, "note": "per-GPU bytes; sgpu_residual_host(q_host, rhs_host) from pinned host arrays",
+               "copy_ceiling": {"value": round(cells_total / (ms_copy * 1e-3) / 1e6, 1), "unit": "Mcell-evals/s",
+                                "GBps_per_gpu_each_way": round(0.5 * (h2d_b + d2h_b) / (ms_copy * 1e-3) / 1e9, 1),
+                                "what": "the same bytes moved by bare concurrent cudaMemcpyAsync H2D + D2H on all ranks at once, no kernel: the PCIe / host-memory ceiling of this box"},
+               "cpu_affinity": affinity}
 
     if rank == 0:
         clocks = sampler.stop()                          # sampled across the timed residual loop and the e2e loop
@@ -347,6 +473,64 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             lin = {"unavailable": str(ex)[:120]}
 
+    # ---- N > 1: the same sample through the slab-partitioned solver (operand ghost rows exchanged per product, inner
+    #      products all-reduced; structured_b200/slab.py)
+    if jac and "build_ms" in jac and world > 1 and not args.no_linsolve:
+        try:
+            from structured_b200.slab import SlabLinearSolver
+            eq.calc_dt(20.0)
+            eq.residual_device(0)
+            sl = SlabLinearSolver(eq, rank, world, dist)
+            x = torch.zeros(sl.n, dtype=torch.float64, device="cuda"); y = torch.zeros_like(x)
+            eq.vec_from_rhs(x.data_ptr())
+
+            def matvec():
+                sl.halo.exchange(lambda side, t: eq.vec_halo_pack(x.data_ptr(), side, t.data_ptr()),
+                                 lambda side, t: eq.vec_halo_unpack(x.data_ptr(), side, t.data_ptr()))
+                eq.op_apply("J", x.data_ptr(), y.data_ptr())
+            matvec(); barrier()
+            e0.record()
+            for _ in range(5):
+                matvec()
+            e1.record(); barrier()
+            mv_ms = e0.elapsed_time(e1) / 5
+            barrier(); e0.record()
+            _, info = sl.solve("lhs", precond="line_j", restart=20, max_iter=20, rtol=1e-8)
+            e1.record(); barrier()
+            sv_ms = e0.elapsed_time(e1)
+            t = torch.tensor([mv_ms, sv_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mv_ms, sv_ms = float(t[0].item()), float(t[1].item())
+            mv_bytes = cells_local * (jac["slots"] * nv * nv + 2 * nv) * 8
+            lin = {"system": "(-J + 1/dt) dq = rhs at CFL 20 (src/solver/solver.cpp:162-175), j-slabs", "method": "GMRES(20) over torch.distributed, slab-local j-line preconditioner",
+                   "iterations": info["iterations"], "rel_residual": info["rel_residual"], "ms_per_iteration_incl_setup": round(sv_ms / max(info["iterations"], 1), 3),
+                   "jacobian_apply_ms": round(mv_ms, 4), "jacobian_apply_GBps_per_gpu": round(mv_bytes / (mv_ms * 1e-3) / 1e9, 1),
+                   "jacobian_apply_roofline_frac": round(mv_bytes / (mv_ms * 1e-3) / 1e9 / measured_peak()[0], 4)}
+            del x, y, sl
+        except Exception as ex:  # noqa: BLE001
+            lin = {"unavailable": str(ex)[:160]}
+
+    # ---- the laminar rows the reference itself has (nv = 4, 104 B/cell): same grid, device resident, beside the COMPILED
+    #      REFERENCE (oracle/_ref, kind "reference") on a bounded sample -- the one pairing against the reference's own code
+    laminar = None
+    if world == 1 and args.ntrans == 1 and not args.no_cpu_baseline:
+        try:
+            lcase = build_case(nic, njc_total, 0)
+            leq = GpuEulerEquation(lcase, device=local)
+            leq.set_state(lcase.perturbed_q())
+            for _ in range(3):
+                leq.residual_device(0)
+            leq.enable_kernel_timing(True)
+            for _ in range(10):
+                leq.residual_device(0)
+            lk = float(np.mean(leq.kernel_times()))
+            leq.close()
+            laminar = {"workload": "laminar bump channel %dx%d cells, MUSCL+Roe+viscous, nv=4, fp64" % (nic, njc_total),
+                       "kernel_ms": round(lk, 4), "value": round(cells_local / (lk * 1e-3) / 1e6, 1), "unit": "Mcell-evals/s",
+                       "roofline_frac": round(cells_local * B_PER_CELL[4] / (lk * 1e-3) / 1e9 / measured_peak()[0], 4), "bytes_per_cell": B_PER_CELL[4]}
+        except Exception as ex:  # noqa: BLE001
+            laminar = {"unavailable": str(ex)[:160]}
+
     peak, peak_src = measured_peak()
     kt = float(np.mean(ktimes)) if len(ktimes) else None
     achieved = cells_local * B_PER_CELL[nv] / (kt * 1e-3) / 1e9 if kt else None
@@ -359,8 +543,23 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 2) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                "traffic_source": "ncu --set full capture, committed (profiles/residual_traffic.json); not measured by this run" if traffic else None,
                 "kernel": "residual_kernel<nv=%d,order=2,roe,viscous>" % nv, "kernel_ms": round(kt, 4) if kt else None,
                 "bytes_per_cell": B_PER_CELL[nv], "peak_source": peak_src}
+    # the kernel is fp64-ISSUE bound, not HBM bound: the second roofline.  instr_per_cell = fp64 instructions of
+    # the SASS row loop per thread x (threads per strip / cells per strip), from the committed static count
+    roofline_fp64 = None
+    fp = os.path.join(ROOT, "profiles", "residual_fp64.json")
+    if kt and os.path.exists(fp) and nv == 5:
+        try:
+            ipc = float(json.load(open(fp))["fp64_instr_per_cell"])
+            sms, clk = torch.cuda.get_device_properties(local).multi_processor_count, (clocks or {}).get("sm_mhz") or 1965.0
+            floor_ms = ipc * cells_local / (sms * 64.0 * clk * 1e6) * 1e3          # 64 fp64 lanes per SM and clock
+            roofline_fp64 = {"instr_per_cell": ipc, "floor_ms": round(floor_ms, 4), "frac": round(floor_ms / kt, 4),
+                             "hbm_frac_at_floor": round(cells_local * B_PER_CELL[nv] / (floor_ms * 1e-3) / 1e9 / peak, 4),
+                             "source": "static SASS count, profiles/residual_fp64.json; 64 fp64 lanes/SM/clk at the sampled SM clock"}
+        except Exception:
+            roofline_fp64 = None
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -372,17 +571,30 @@ def run_ours(args):
         if have_ref():
             v2, _, _ = cpu_throughput("reference", sn, sn, 0, reps, 1)
             cpu["reference_laminar_1core"] = round(v2, 4)
+            if laminar and "value" in laminar:
+                laminar["cpu_baseline"] = {"value": round(v2, 4), "unit": "Mcell-evals/s", "cores": 1, "kind": "reference",
+                                           "sample": "%d reps of EulerEquation::calc_residual (oracle/_ref, the reference compiled unmodified) on a %dx%d-cell sample of the same laminar workload" % (reps, sn, sn)}
+        # Jacobian CPU baseline: the oracle's dual-number coloured Jacobian, 1 core, bounded sample
+        try:
+            jn = 160
+            tj, nnzj, ncol = cpu_jacobian(jn, jn, args.ntrans)
+            cpu["jacobian"] = {"ms_per_Mcell": round(tj * 1e3 / (jn * jn / 1e6), 1), "Mcell_per_s": round(jn * jn / tj / 1e6, 5), "cores": 1, "kind": "port",
+                               "what": "oracle stand-in for trace_on .. sparse_jac (src/solver/solver.cpp:72-90,154-157): index-domain pattern + greedy colouring (%s colours) + dual-number sweeps; NOT ADOL-C (un-vendored, absent from this image)" % ncol,
+                               "sample": "one build on a %dx%d-cell sample of the same workload (nv=%d), nnz %d, %.2f s" % (jn, jn, nv, nnzj, tj),
+                               "extrapolated_ms_at_workload": round(tj * 1e3 * cells_local / (jn * jn), 0)}
+        except Exception as ex:  # noqa: BLE001
+            cpu["jacobian"] = {"unavailable": str(ex)[:160]}
 
     if rank == 0:
         out = {"metric": "residual_mcell_evals_per_s", "value": round(value, 2), "unit": "Mcell-evals/s", "n_gpus": n_gpus,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "SA turbulent bump channel %dx%d cells, MUSCL+Roe+viscous, nv=%d, fp64%s" % (
-                              nic, njc_total, nv, "" if n_gpus == 1 else ", j-slabs of %dx%d per GPU" % (nic, njc_per)),
+               "config": {"workload": workload_name(nic, njc_total, nv, n_gpus, njc_per),
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "linear_solve": lin, "l2norm": [float(x) for x in np.sqrt(l2)]}
+               "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "halo_check": halo_check,
+               "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()
     if world > 1:

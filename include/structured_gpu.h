@@ -97,6 +97,14 @@ int sgpu_set_grid_window(sgpu_ctx* ctx, const double* xv, const double* yv, int 
 int sgpu_set_field_window(sgpu_ctx* ctx, const char* name, const double* field, int j_first, int j_count);
 /* SA extension inputs, GLOBAL [nic][njc]: name = "wall_distance" | "beta" (no reference counterpart) */
 int sgpu_set_field(sgpu_ctx* ctx, const char* name, const double* field);
+int sgpu_get_field(sgpu_ctx* ctx, const char* name, double* field);   /* GLOBAL [nic][njc]; owned rows written */
+/* Wall distance of the SA extension evaluated on the device (no reference counterpart; the reference has no turbulence
+ * model, src/solver/solution.cpp:9): distance from every cell centre (Mesh::xc, yc, src/utils/mesh.cpp:199-200) to the
+ * nearest point of the wall edges.  segments: host [nseg][4] = x0 y0 x1 y1; nseg = 0 sets d = 1e30.
+ * _from_bcs derives the edges from the `wall` / `isothermalwall` [[boundary]] tables (any face, ranges as in
+ * src/model/bc.cpp:436-457) and the GLOBAL host vertex arrays [ni][nj]. */
+int sgpu_compute_wall_distance(sgpu_ctx* ctx, const double* segments, int nseg);
+int sgpu_wall_distance_from_bcs(sgpu_ctx* ctx, const double* xv, const double* yv);
 /* metrics as Mesh::calc_metrics leaves them, for parity checks: normal_chi [ni][njc][2],
  * normal_eta [nic][nj][2], volume [nic][njc] (GLOBAL shapes; only owned rows are written) */
 int sgpu_get_metrics(sgpu_ctx* ctx, double* normal_chi, double* normal_eta, double* volume);
@@ -147,6 +155,11 @@ int sgpu_explicit_step(sgpu_ctx* ctx, int scheme, double cfl, double* l2sq);
  * values = -values, diagonal += 1/dt[row] (sgpu_calc_dt must have been called). */
 int sgpu_jacobian_coo(sgpu_ctx* ctx, int* nnz, unsigned int** rind, unsigned int** cind, double** values,
                       int apply_lhs_transform);
+/* The same export for the cell rows j in [j_first, j_first + j_count) only, from the Jacobian a previous
+ * sgpu_jacobian_device left on the device (no rebuild): large grids whose full COO would overflow `int nnz`, sampled
+ * parity checks.  Row / column numbers stay GLOBAL. */
+int sgpu_jacobian_coo_rows(sgpu_ctx* ctx, int j_first, int j_count, int* nnz, unsigned int** rind, unsigned int** cind,
+                           double** values, int apply_lhs_transform);
 /* Device-resident block-stencil form (no size limit): evaluates the Jacobian and leaves it on the device.
  * *slots = number of stencil slots per cell, block layout J[slot][r][c][cell]. build_ms (may be NULL)
  * receives the device time of the build. */
@@ -253,6 +266,8 @@ int sgpu_precond_apply(sgpu_ctx* ctx, int matrix, int precond, const double* r_d
 int sgpu_halo_count(const sgpu_ctx* ctx);
 int sgpu_halo_pack(sgpu_ctx* ctx, int which, int side, double* dev_buf);
 int sgpu_halo_unpack(sgpu_ctx* ctx, int which, int side, const double* dev_buf);
+/* verification aid: the two GHOST rows of a side, packed like sgpu_halo_pack (what the last exchange delivered) */
+int sgpu_halo_pack_ghost(sgpu_ctx* ctx, int which, int side, double* dev_buf);
 /* Peer-memory variant (NVLink P2P): each slab owns, per side, a receive buffer (two slots + a sequence flag).
  * After the neighbour's buffer has been registered -- same process: sgpu_halo_recv_buffer + sgpu_halo_enable_peer +
  * sgpu_halo_set_peer; one process per GPU: sgpu_halo_ipc_handle on the owner, sgpu_halo_open_peer on the writer --

@@ -189,9 +189,13 @@ class PortOracle:
         xv = np.ascontiguousarray(case.xv, dtype=np.float64)
         yv = np.ascontiguousarray(case.yv, dtype=np.float64)
         L.port_set_grid(self.h, _dp(xv), _dp(yv))
+        if getattr(case, "global_counts", None):     # cropped window of a larger grid (tests/helpers.py::crop_case)
+            L.port_set_global_counts(self.h, int(case.global_counts[0]), int(case.global_counts[1]))
         if case.ntrans:
             if case.wall_distance is not None:
                 L.port_set_field(self.h, b"wall_distance", _dp(np.ascontiguousarray(case.wall_distance)))
+            else:                                    # nearest wall edge, like sgpu_wall_distance_from_bcs
+                L.port_wall_distance(self.h, None)
             if case.beta is not None:
                 L.port_set_field(self.h, b"beta", _dp(np.ascontiguousarray(case.beta)))
 
@@ -252,6 +256,32 @@ class PortOracle:
         q = np.ascontiguousarray(q, dtype=np.float64)
         nnz = ctypes.c_int()
         return float(self.L.port_time_jacobian(self.h, _dp(q), int(lhs), ctypes.byref(nnz))), nnz.value
+
+    def wall_distance(self):
+        """nearest-wall-edge distance [nic][njc] from the case's wall / isothermalwall tables (also stored in the oracle)"""
+        out = np.empty((self.nic, self.njc))
+        self.L.port_wall_distance(self.h, _dp(out))
+        return out
+
+    def set_field(self, name, f):
+        self.L.port_set_field(self.h, name.encode(), _dp(np.ascontiguousarray(f, dtype=np.float64)))
+
+    def jacobian_rows(self, q, cells, lhs=True):
+        """Rows of the Jacobian for sampled row cells on LARGE grids (static 5x5 colouring, 25 nv / lanes dual sweeps):
+        cells [n][2] = (i, j), none within 2 cells of a periodic / wake boundary.  Returns COO (rind, cind, values) of the
+        non-zero entries with the reference's flat numbering (i*njc + j)*nv + k."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
+        m, nv = len(cells), self.nv
+        out = np.zeros((m, nv, 25, nv))
+        self.L.port_jacobian_rows(self.h, _dp(q), int(lhs), cells.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), m, _dp(out))
+        di, dj = np.meshgrid(np.arange(-2, 3), np.arange(-2, 3), indexing="ij")
+        ci = cells[:, 0][:, None] + di.reshape(-1)[None, :]; cj = cells[:, 1][:, None] + dj.reshape(-1)[None, :]      # [m][25]
+        rows = ((cells[:, 0].astype(np.int64)*self.njc + cells[:, 1])[:, None, None, None]*nv + np.arange(nv)[None, :, None, None])
+        cols = ((ci.astype(np.int64)*self.njc + cj)[:, None, :, None]*nv + np.arange(nv)[None, None, None, :])
+        rows, cols = np.broadcast_to(rows, out.shape), np.broadcast_to(cols, out.shape)
+        keep = out != 0.0
+        return rows[keep].astype(np.uint32), cols[keep].astype(np.uint32), out[keep]
 
 
 def rk4_step_cpu(oracle, q, q_tmp, cfl):

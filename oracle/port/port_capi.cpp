@@ -37,6 +37,12 @@ void port_set_grid(void* hv, const double* xv, const double* yv) {
     h->have_ad = false;
 }
 
+// a case that is a cropped window of a larger grid keeps that grid's limiter constants (reconstruction.cpp:62-63)
+void port_set_global_counts(void* hv, int nic_global, int njc_global) {
+    auto h = (PortHandle*)hv;
+    h->c.eps_nic = nic_global; h->c.eps_njc = njc_global;
+}
+
 int port_set_field(void* hv, const char* name, const double* f) {
     auto h = (PortHandle*)hv;
     size_t n = (size_t)h->c.nic*h->c.njc;
@@ -44,6 +50,45 @@ int port_set_field(void* hv, const char* name, const double* f) {
     else if (!std::strcmp(name, "beta")) h->c.beta.assign(f, f + n);
     else return -1;
     return 0;
+}
+
+// SA wall distance (extension; no reference counterpart): for every cell the distance from its centre (Mesh::xc, yc,
+// src/utils/mesh.cpp:199-200) to the nearest point of the boundary edges covered by a `wall` / `isothermalwall` table.
+// Brute force over all edges; stores the field in the case and copies it to out [nic][njc] (may be NULL).
+int port_wall_distance(void* hv, double* out) {
+    auto h = (PortHandle*)hv;
+    sport::Case& c = h->c;
+    struct Seg { double ax, ay, bx, by, il2; };
+    std::vector<Seg> segs;
+    auto X = [&](const std::vector<double>& a, int i, int j) { return a[(size_t)i*c.nj + j]; };
+    for (const sgpu_bc& b : c.bcs) {
+        if (b.type != SGPU_BC_WALL && b.type != SGPU_BC_ISOTHERMALWALL) continue;
+        const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
+        const int n = horiz ? c.nic : c.njc;
+        for (int p = std::max(b.start, 1); p <= std::min(b.end, n); p++) {
+            int i0, j0, i1, j1;
+            if (horiz) { i0 = p - 1; i1 = p; j0 = j1 = (b.face == SGPU_FACE_BOTTOM ? 0 : c.nj - 1); }
+            else { j0 = p - 1; j1 = p; i0 = i1 = (b.face == SGPU_FACE_LEFT ? 0 : c.ni - 1); }
+            Seg s; s.ax = X(c.xv, i0, j0); s.ay = X(c.yv, i0, j0); s.bx = X(c.xv, i1, j1) - s.ax; s.by = X(c.yv, i1, j1) - s.ay;
+            const double l2 = s.bx*s.bx + s.by*s.by; s.il2 = l2 > 0.0 ? 1.0/l2 : 0.0;
+            segs.push_back(s);
+        }
+    }
+    for (int i = 0; i < c.nic; i++) for (int j = 0; j < c.njc; j++) {
+        const double px = 0.25*(X(c.xv, i, j) + X(c.xv, i+1, j) + X(c.xv, i, j+1) + X(c.xv, i+1, j+1));
+        const double py = 0.25*(X(c.yv, i, j) + X(c.yv, i+1, j) + X(c.yv, i, j+1) + X(c.yv, i+1, j+1));
+        double best = 1e300;
+        for (const Seg& s : segs) {
+            const double dx = px - s.ax, dy = py - s.ay;
+            double t = (dx*s.bx + dy*s.by)*s.il2;
+            t = std::min(std::max(t, 0.0), 1.0);
+            const double ex = dx - t*s.bx, ey = dy - t*s.by;
+            best = std::min(best, ex*ex + ey*ey);
+        }
+        c.wall_dist[(size_t)i*c.njc + j] = segs.empty() ? 1e30 : std::sqrt(best);
+    }
+    if (out) std::memcpy(out, c.wall_dist.data(), sizeof(double)*c.wall_dist.size());
+    return (int)segs.size();
 }
 
 void port_get_metrics(void* hv, double* nchi, double* neta, double* vol) {
@@ -151,6 +196,49 @@ double port_time_jacobian(void* hv, const double* q, int lhs, int* nnz_out) {
     if (nnz_out) *nnz_out = nnz;
     free(r); free(c); free(v);
     return dt.count();
+}
+
+// Jacobian ROWS of sampled cells on grids too large for the full pattern + colouring pipeline above: static colouring
+// colour(i, j, k) = ((i mod 5)*5 + (j mod 5))*nv + k -- two cells of one colour are >= 5 apart in i or j, so they never
+// share a row (row stencil: |di|, |dj| <= 2; SURVEY.md Appendix B "Colouring").  ceil(25 nv / lanes) dual sweeps over the
+// whole grid, then for each sampled row cell the derivative w.r.t. the 25 cells of its 5x5 window is read off.
+// Valid for rows whose ghost cells depend on cells INSIDE that window only (walls, slipwall, outflow, freestream);
+// rows within 2 cells of a periodic or wake boundary must not be sampled (their wrap-around columns alias).
+// cells: [ncells][2] = (i, j);  out: [ncells][nv][25][nv] = d rhs[i][j][r] / d q[i+di][j+dj][c], window index (di+2)*5 + (dj+2),
+// zero for window cells outside the grid.
+int port_jacobian_rows(void* hv, const double* q, int lhs, const int* cells, int ncells, double* out) {
+    auto h = (PortHandle*)hv;
+    if (!h->have_ad) { h->wdual.init(h->c); h->wdep.init(h->c); h->have_ad = true; }
+    const sport::Case& c = h->c;
+    const int nv = c.nv, N = PORT_DUAL_LANES;
+    const size_t n = (size_t)c.nic*c.njc*nv;
+    const int ncolors = 25*nv;
+    std::vector<PDual> a_q(n), a_rhs(n);
+    std::memset(out, 0, sizeof(double)*(size_t)ncells*nv*25*nv);
+    auto color = [&](int i, int j, int k) { return ((i % 5)*5 + (j % 5))*nv + k; };
+    for (int c0 = 0; c0 < ncolors; c0 += N) {
+        for (int i = 0; i < c.nic; i++) for (int j = 0; j < c.njc; j++) for (int k = 0; k < nv; k++) {
+            const size_t id = ((size_t)i*c.njc + j)*nv + k;
+            a_q[id] = PDual(q[id]);
+            const int l = color(i, j, k) - c0;
+            if (l >= 0 && l < N) a_q[id].d[l] = 1.0;
+        }
+        sport::calc_residual<PDual>(c, h->wdual, a_q.data(), a_rhs.data(), lhs != 0);
+        for (int m = 0; m < ncells; m++) {
+            const int i = cells[2*m], j = cells[2*m + 1];
+            for (int di = -2; di <= 2; di++) for (int dj = -2; dj <= 2; dj++) {
+                const int ci = i + di, cj = j + dj;
+                if (ci < 0 || ci >= c.nic || cj < 0 || cj >= c.njc) continue;
+                for (int k = 0; k < nv; k++) {
+                    const int l = color(ci, cj, k) - c0;
+                    if (l < 0 || l >= N) continue;
+                    for (int r = 0; r < nv; r++)
+                        out[(((size_t)m*nv + r)*25 + (di + 2)*5 + (dj + 2))*nv + k] = a_rhs[((size_t)i*c.njc + j)*nv + r].d[l];
+                }
+            }
+        }
+    }
+    return 0;
 }
 
 void port_free(void* p) { free(p); }

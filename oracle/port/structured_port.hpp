@@ -41,9 +41,10 @@ struct Case {
     std::vector<double> xv, yv;                     // [ni][nj]
     std::vector<double> nchi, neta, vol, ds_chi, ds_eta;   // [ni][njc][2], [nic][nj][2], [nic][njc]
     std::vector<double> wall_dist, beta;            // [nic][njc]  (SA)
+    int eps_nic = 0, eps_njc = 0;                   // cell counts the limiter constants are taken from (= nic, njc)
 
     void init(const sgpu_desc& d) {
-        ni = d.ni; nj = d.nj; nic = ni - 1; njc = nj - 1;
+        ni = d.ni; nj = d.nj; nic = ni - 1; njc = nj - 1; eps_nic = nic; eps_njc = njc;
         ntrans = d.ntrans; nv = nq + ntrans;
         order = d.order; lhs_order = d.lhs_order; flux = d.flux;
         rho_inf = d.rho_inf; u_inf = d.u_inf; v_inf = d.v_inf; p_inf = d.p_inf; T_inf = d.T_inf;
@@ -241,7 +242,9 @@ void reconstruct(const Case& c, Work<T>& w, const std::vector<T>& q, int var, in
     for (int i = 0; i < nic; i++) for (int j = 0; j < nj; j++) { le[w.E(i,j)] = q[w.P(i+1, j)]; re[w.E(i,j)] = q[w.P(i+1, j+1)]; }
     if (order != 2) return;
     const double thm = 2.0/3.0, thp = 4.0/3.0;
-    const double eps_chi = std::pow(10.0/nic, 3), eps_eta = std::pow(10.0/njc, 3);   // :62-63
+    // :62-63.  eps_nic / eps_njc = nic / njc, except for a CROPPED window of a larger grid (tests/helpers.py::crop_case),
+    // which must use the limiter constants of the grid it was cut from
+    const double eps_chi = std::pow(10.0/c.eps_nic, 3), eps_eta = std::pow(10.0/c.eps_njc, 3);
     for (int i = 0; i < nic; i++) for (int j = 0; j < njc; j++) {                   // chi :94-111
         T f2a = q[w.P(i+1, j+1)] - q[w.P(i, j+1)];        // f2[i][j]
         T f2b = q[w.P(i+2, j+1)] - q[w.P(i+1, j+1)];      // f2[i+1][j]

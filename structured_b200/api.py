@@ -21,14 +21,15 @@ _U = ctypes.POINTER(ctypes.c_uint)
 
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
-    "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
+    "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_field", "sgpu_compute_wall_distance",
+    "sgpu_wall_distance_from_bcs", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
-    "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
+    "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_coo_rows", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
     "sgpu_wall_data", "sgpu_track_wall", "sgpu_surface", "sgpu_surface_gradient",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
-    "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
+    "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_pack_ghost", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
 
@@ -78,9 +79,10 @@ def load_library():
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if not os.path.exists(path):
+    if not os.environ.get("SGPU_LIB"):
         from . import build as _build
-        _build.build()
+        if _build.stale(path):          # missing, or older than any source under csrc/ / include/: never load a stale library
+            _build.build()
     L = ctypes.CDLL(path)
     L.sgpu_last_error.restype = ctypes.c_char_p
     L.sgpu_last_error.argtypes = [ctypes.c_void_p]
@@ -133,6 +135,8 @@ class GpuEulerEquation:
             if case.ntrans:
                 if case.wall_distance is not None:
                     self.set_field("wall_distance", case.wall_distance)
+                else:                                    # [turbulence] wall_distance = "compute": nearest wall edge, on the device
+                    self.compute_wall_distance()
                 if case.beta is not None:
                     self.set_field("beta", case.beta)
         else:
@@ -175,6 +179,23 @@ class GpuEulerEquation:
     # ---- static inputs
     def set_field(self, name: str, field: np.ndarray):
         self._ck(self.L.sgpu_set_field(self.h, name.encode(), _dp(np.ascontiguousarray(field, dtype=np.float64))))
+
+    def get_field(self, name: str) -> np.ndarray:
+        out = np.zeros((self.nic, self.njc))
+        self._ck(self.L.sgpu_get_field(self.h, name.encode(), _dp(out)))
+        return out
+
+    def compute_wall_distance(self, segments: Optional[np.ndarray] = None):
+        """SA wall distance on the device: distance of every cell centre to the nearest wall edge.  segments [n][4] =
+        x0 y0 x1 y1, default: the edges covered by the case's `wall` / `isothermalwall` tables (needs the full grid)."""
+        if segments is None:
+            if self.case.window is not None:
+                raise SgpuError("wall edges from the [[boundary]] tables need the full vertex arrays; pass the segments")
+            xv = np.ascontiguousarray(self.case.xv, dtype=np.float64); yv = np.ascontiguousarray(self.case.yv, dtype=np.float64)
+            self._ck(self.L.sgpu_wall_distance_from_bcs(self.h, _dp(xv), _dp(yv)))
+        else:
+            seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 4)
+            self._ck(self.L.sgpu_compute_wall_distance(self.h, _dp(seg), int(seg.shape[0])))
 
     def metrics(self):
         nchi = np.zeros((self.case.ni, self.njc, 2)); neta = np.zeros((self.nic, self.case.nj, 2)); vol = np.zeros((self.nic, self.njc))
@@ -268,10 +289,15 @@ class GpuEulerEquation:
         return np.sqrt(l2)
 
     # ---- Jacobian
-    def jacobian_coo(self, apply_lhs_transform: bool = False):
-        """Replacement of sparse_jac (src/solver/solver.cpp:156): returns (rind, cind, values) numpy copies."""
+    def jacobian_coo(self, apply_lhs_transform: bool = False, rows: Optional[tuple] = None):
+        """Replacement of sparse_jac (src/solver/solver.cpp:156): returns (rind, cind, values) numpy copies.
+        rows = (j_first, j_count): only those cell rows, from the Jacobian jacobian_device() left on the device."""
         nnz = ctypes.c_int(); r, c, v = _U(), _U(), _P()
-        self._ck(self.L.sgpu_jacobian_coo(self.h, ctypes.byref(nnz), ctypes.byref(r), ctypes.byref(c), ctypes.byref(v), int(apply_lhs_transform)))
+        if rows is None:
+            self._ck(self.L.sgpu_jacobian_coo(self.h, ctypes.byref(nnz), ctypes.byref(r), ctypes.byref(c), ctypes.byref(v), int(apply_lhs_transform)))
+        else:
+            self._ck(self.L.sgpu_jacobian_coo_rows(self.h, int(rows[0]), int(rows[1]), ctypes.byref(nnz), ctypes.byref(r), ctypes.byref(c),
+                                                   ctypes.byref(v), int(apply_lhs_transform)))
         n = nnz.value
         libc = ctypes.CDLL(None)
         libc.free.argtypes = [ctypes.c_void_p]
@@ -440,6 +466,9 @@ class GpuEulerEquation:
 
     def halo_pack(self, which: int, side: int, dev_ptr: int):
         self._ck(self.L.sgpu_halo_pack(self.h, which, side, ctypes.c_void_p(dev_ptr)))
+
+    def halo_pack_ghost(self, which: int, side: int, dev_ptr: int):
+        self._ck(self.L.sgpu_halo_pack_ghost(self.h, which, side, ctypes.c_void_p(dev_ptr)))
 
     def halo_unpack(self, which: int, side: int, dev_ptr: int):
         self._ck(self.L.sgpu_halo_unpack(self.h, which, side, ctypes.c_void_p(dev_ptr)))

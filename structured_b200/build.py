@@ -23,11 +23,28 @@ def sources():
     return out
 
 
-def stale() -> bool:
-    if not os.path.exists(LIB):
+HASH = LIB + ".srchash"        # content hash of the sources the library was built from (mtimes do not survive a snapshot copy)
+
+
+def source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(sources()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def stale(lib: str = LIB) -> bool:
+    """True if the library is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in sources())
+    try:
+        with open(HASH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -41,6 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libstructured_gpu.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    with open(HASH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

@@ -295,7 +295,65 @@ def turbulent_channel_case(nic: int, njc: int, ntrans: int = 1, order: int = 2, 
     return c
 
 
-def zoo_case(name: str, nic: int = 24, njc: int = 16) -> Case:
+def wall_segments(case: "Case") -> np.ndarray:
+    """[n][4] = x0 y0 x1 y1 of every boundary edge covered by a `wall` / `isothermalwall` table (ranges as in
+    BoundaryContainer::get_index, src/model/bc.cpp:436-457: padded index p <-> cell p - 1).  Full grids only."""
+    assert case.window is None, "wall edges need the full vertex arrays"
+    nic, njc = case.nic, case.njc
+    out = []
+    for b in case.boundaries:
+        if b.type not in ("wall", "isothermalwall"):
+            continue
+        horiz = b.face in ("bottom", "top")
+        n = nic if horiz else njc
+        end = b.end if b.end >= 0 else n + 2 + b.end
+        for p in range(max(b.start, 1), min(end, n) + 1):
+            if horiz:
+                j = 0 if b.face == "bottom" else case.nj - 1
+                out.append((case.xv[p - 1, j], case.yv[p - 1, j], case.xv[p, j], case.yv[p, j]))
+            else:
+                i = 0 if b.face == "left" else case.ni - 1
+                out.append((case.xv[i, p - 1], case.yv[i, p - 1], case.xv[i, p], case.yv[i, p]))
+    return np.array(out, dtype=np.float64).reshape(-1, 4)
+
+
+def flat_plate_grid(nic: int, njc: int, L: float = 1.0, H: float = 0.25, s: float = 3.0, skew: float = 0.15):
+    """Flat-plate grid: x uniform, y clustered at the (flat) lower boundary, y_j = H [1 - tanh(s (1 - j/njc))/tanh(s)];
+    `skew` shears the interior grid lines (zero at j = 0 and j = njc) so that the chi normals are not axis aligned."""
+    i = np.arange(nic + 1, dtype=np.float64)[:, None]
+    j = np.arange(njc + 1, dtype=np.float64)[None, :]
+    y = H * (1.0 - np.tanh(s * (1.0 - j / njc)) / math.tanh(s)) + 0.0 * i
+    x = L * i / nic + skew * L / nic * np.sin(np.pi * y / H) * np.sin(2.0 * np.pi * i / nic)
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+def flat_plate_case(nic: int, njc: int, ntrans: int = 1, order: int = 2, lhs_order: Optional[int] = None, flux: str = "roe",
+                    mach: float = 0.2, reynolds: float = 5e6, leading_edge: float = 0.2) -> Case:
+    """BASELINE.json config 2: turbulent flat plate -- bottom boundary `slipwall` up to
+    x = leading_edge * L, adiabatic `wall` from there on, `freestream` on top and at the inflow, `outflow` on the right;
+    M = 0.2, Re_L = 5e6, MUSCL + Roe + viscous + SA.  The wall distance is left to the device
+    (`wall_distance = None` -> nearest edge of the wall segment, sgpu_wall_distance_from_bcs)."""
+    xv, yv = flat_plate_grid(nic, njc)
+    c = Case(ni=nic + 1, nj=njc + 1, xv=xv, yv=yv)
+    c.rho_inf, c.u_inf, c.v_inf, c.p_inf, c.T_inf = 1.0, mach, 0.0, 1.0 / 1.4, 1.0 / 1.4
+    c.mu_inf = c.rho_inf * c.u_inf * 1.0 / reynolds
+    c.order, c.lhs_order, c.flux, c.scheme = order, (order if lhs_order is None else lhs_order), flux, "rk4_jameson"
+    c.ntrans = ntrans
+    ile = max(1, min(nic - 1, int(round(leading_edge * nic))))        # cells 0 .. ile-1 slip, ile .. nic-1 wall
+    c.boundaries = [
+        Boundary("slipwall", "bottom", 1, ile),
+        Boundary("wall", "bottom", ile + 1, -2),
+        Boundary("freestream", "top", 0, -1),
+        Boundary("freestream", "left", 0, -1),
+        Boundary("outflow", "right", 0, -1),
+    ]
+    if ntrans:
+        c.beta = synthetic_beta(c)
+    c.label = "flatplate_%dx%d" % (nic, njc)
+    return c
+
+
+def zoo_case(name: str, nic: int = 24, njc: int = 16, ntrans: int = 0) -> Case:
     """Small synthetic cases that together exercise every BC type / face the reference implements,
     both fluxes, both reconstruction orders and the inviscid switch (parity-test cases, not bench lines)."""
     xv, yv = bump_channel_grid(nic, njc, L=1.0, H=0.5, s=1.2, bump=0.1, skew=0.3)
@@ -329,7 +387,13 @@ def zoo_case(name: str, nic: int = 24, njc: int = 16) -> Case:
                         Boundary("wall", "bottom", nw + 1, nic - nw)]
     else:
         raise ValueError(name)
+    if ntrans:                   # SA x BC matrix: nu~ ghost rules of every BC type (wall distance: nearest wall edge, if any)
+        assert c.viscous, "the SA extension needs a viscous case"
+        c.ntrans = ntrans
+        c.label += "_sa"
+        c.beta = synthetic_beta(c, L=1.0, H=0.5)
     return c
 
 
 ZOO = ("A", "B", "C", "D", "E")
+ZOO_SA = ("A", "B", "D", "E")    # C is inviscid

@@ -289,8 +289,15 @@ __global__ void halo_signal_kernel(unsigned long long* flag, unsigned long long 
     *(volatile unsigned long long*)flag = seq;
     __threadfence_system();
 }
-__global__ void halo_wait_kernel(const unsigned long long* flag, unsigned long long seq) {
-    while (*(volatile const unsigned long long*)flag < seq) { }
+// bounded spin: a neighbour that never pushes (mismatched call counts, a dead rank) must not hang the GPU -- after
+// `timeout_ns` the kernel gives up and raises *err, which the host reads at its next synchronising call
+__global__ void halo_wait_kernel(const unsigned long long* flag, unsigned long long seq, unsigned long long timeout_ns, int* err) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (*(volatile const unsigned long long*)flag < seq) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicAdd(err, 1); break; }
+    }
     __threadfence_system();
 }
 
@@ -353,6 +360,41 @@ __global__ void wall_data_kernel(View v, Metrics m, const double* __restrict__ q
     gv[2*i] = (tx*vt - bx*vb + rx*vr - lx*vl)/vol; gv[2*i + 1] = (ty*vt - by*vb + ry*vr - ly*vl)/vol;
     xc0[i] = 0.25*(xv[o] + xv[oc1] + xv[o1] + xv[v.at(r0 + 1, c + 1)]);                  // mesh.cpp:199
     dx[i] = xv[oc1] - xv[o]; dy[i] = yv[oc1] - yv[o];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wall distance of the SA extension (no reference counterpart; SURVEY.md Appendix C "wall distance d"): for every cell
+// the distance from its centre (xc, yc = 1/4 of its four vertices, src/utils/mesh.cpp:199-200) to the nearest point of
+// the wall -- the union of the boundary edges covered by a `wall` / `isothermalwall` table.  Brute force, exact
+// point-to-segment distance: segments are staged through shared memory in tiles, one thread per cell.
+// seg: [nseg][5] = ax, ay, abx, aby, 1/|ab|^2
+// ------------------------------------------------------------------------------------------------
+constexpr int WD_TILE = 256;
+__global__ void __launch_bounds__(128) wall_distance_kernel(View v, const double* __restrict__ xv, const double* __restrict__ yv,
+                                                            const double* __restrict__ seg, int nseg, double* __restrict__ wdist) {
+    __shared__ double s_seg[WD_TILE*5];
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int r = blockIdx.y + JOFF;
+    const bool ok = i < v.nic;
+    const int c = (ok ? i : 0) + IOFF;
+    const size_t o = v.at(r, c), o1 = v.at(r + 1, c);
+    const double px = 0.25*(xv[o] + xv[o + 1] + xv[o1] + xv[o1 + 1]), py = 0.25*(yv[o] + yv[o + 1] + yv[o1] + yv[o1 + 1]);
+    double best = 1e300;
+    for (int s0 = 0; s0 < nseg; s0 += WD_TILE) {
+        const int n = min(WD_TILE, nseg - s0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n*5; k += blockDim.x) s_seg[k] = seg[(size_t)s0*5 + k];
+        __syncthreads();
+        for (int k = 0; k < n; k++) {
+            const double ax = s_seg[5*k], ay = s_seg[5*k + 1], bx = s_seg[5*k + 2], by = s_seg[5*k + 3], il2 = s_seg[5*k + 4];
+            const double dx = px - ax, dy = py - ay;
+            double t = (dx*bx + dy*by)*il2;
+            t = fmin(fmax(t, 0.0), 1.0);
+            const double ex = dx - t*bx, ey = dy - t*by;
+            best = fmin(best, ex*ex + ey*ey);
+        }
+    }
+    if (ok) wdist[o] = sqrt(best);
 }
 
 __global__ void fill_kernel(double* __restrict__ p, size_t n, double val) {

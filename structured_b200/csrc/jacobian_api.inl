@@ -96,8 +96,9 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
     p.q = c->q[0]; p.J = c->jac.blocks; p.wdist = c->wdist; p.beta = c->beta;
     p.Schi = c->jac_scratch; p.Seta = c->jac_scratch + dir_s; p.stiles = stiles;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.nslots = nslots; p.err = c->jac_err;
-    cudaEvent_t e0, e1;
-    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1;
+    CK(c, cudaEventCreate(&ev0.e)); CK(c, cudaEventCreate(&ev1.e));
+    const cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     CK(c, cudaEventRecord(e0, c->stream));
     int rc = SGPU_ERR_ARG;
     const bool roe = c->d.flux == SGPU_FLUX_ROE;
@@ -121,48 +122,62 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
     CK(c, cudaMemcpyAsync(&herr, c->jac_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f; CK(c, cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (build_ms) *build_ms = ms;
     if (herr) FAIL(c, SGPU_ERR_ARG, "%d boundary couplings could not be represented in the block-stencil Jacobian", herr);
     c->jac.valid = true;
     return SGPU_OK;
 }
 
+// device / host temporaries that are released on every exit path (CK / FAIL return early)
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return (T*)p; }
+};
+struct HostCoo {                                                   // the caller's arrays: handed over only on success
+    unsigned int* r = nullptr; unsigned int* c = nullptr; double* v = nullptr;
+    ~HostCoo() { free(r); free(c); free(v); }
+};
+
+// COO export of the cell rows jl in [jl0, jl1) (local rows of this slab) of the resident block-stencil Jacobian
 template <int NV>
-static int jacobian_export_t(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int** cind, double** values, int lhs_transform) {
+static int jacobian_export_t(sgpu_ctx* c, int jl0, int jl1, int* nnz, unsigned int** rind, unsigned int** cind, double** values, int lhs_transform) {
     const View& v = c->v;
-    const size_t nrows = (size_t)v.nic*v.njl*NV;
+    *nnz = 0; *rind = nullptr; *cind = nullptr; *values = nullptr;
+    const int nrw = jl1 - jl0;
+    const size_t nrows = (size_t)v.nic*nrw*NV;
     const GhostTable gt = ghost_table_of(c);
     const bool order2 = c->d.lhs_order == 2;
-    int* counts = nullptr; long long* offs = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
-    CK(c, cudaMalloc(&counts, (nrows + 1)*sizeof(int)));
-    CK(c, cudaMalloc(&offs, (nrows + 1)*sizeof(long long)));
-    CK(c, cudaMemsetAsync(counts, 0, (nrows + 1)*sizeof(int), c->stream));
-    const dim3 grd((v.nic + 127)/128, v.njl);
-    jac_count_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, counts);
+    DevBuf counts, offs, tmp, dr, dc, dv; size_t tmp_bytes = 0;
+    CK(c, counts.alloc((nrows + 1)*sizeof(int)));
+    CK(c, offs.alloc((nrows + 1)*sizeof(long long)));
+    CK(c, cudaMemsetAsync(counts.p, 0, (nrows + 1)*sizeof(int), c->stream));
+    const dim3 grd((v.nic + 127)/128, nrw);
+    jac_count_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, jl0, nrw, counts.as<int>());
     CKL(c); c->launches++;
-    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offs, (int)(nrows + 1), c->stream));
-    CK(c, cudaMalloc(&tmp, tmp_bytes));
-    CK(c, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offs, (int)(nrows + 1), c->stream));
+    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int>(), offs.as<long long>(), (int)(nrows + 1), c->stream));
+    CK(c, tmp.alloc(tmp_bytes));
+    CK(c, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int>(), offs.as<long long>(), (int)(nrows + 1), c->stream));
     c->launches++;
     long long total = 0;
-    CK(c, cudaMemcpyAsync(&total, offs + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&total, offs.as<long long>() + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(tmp);
-    if (total > 2147483647LL) { cudaFree(counts); cudaFree(offs); FAIL(c, SGPU_ERR_OVERFLOW, "nnz = %lld does not fit the reference's `int nnz` (src/solver/solution.h:16); use sgpu_jacobian_device", total); }
-    unsigned int *dr = nullptr, *dc = nullptr; double* dv = nullptr;
+    if (total > 2147483647LL) FAIL(c, SGPU_ERR_OVERFLOW, "nnz = %lld does not fit the reference's `int nnz` (src/solver/solution.h:16); use sgpu_jacobian_device", total);
     const size_t n = (size_t)std::max<long long>(total, 1);
-    CK(c, cudaMalloc(&dr, n*sizeof(unsigned int))); CK(c, cudaMalloc(&dc, n*sizeof(unsigned int))); CK(c, cudaMalloc(&dv, n*sizeof(double)));
-    jac_fill_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, offs, c->dt, lhs_transform, dr, dc, dv);
+    CK(c, dr.alloc(n*sizeof(unsigned int))); CK(c, dc.alloc(n*sizeof(unsigned int))); CK(c, dv.alloc(n*sizeof(double)));
+    jac_fill_kernel<NV><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, offs.as<long long>(), c->dt, lhs_transform,
+                                                    jl0, nrw, dr.as<unsigned int>(), dc.as<unsigned int>(), dv.as<double>());
     CKL(c); c->launches++;
     // malloc: ownership passes to the caller, who free()s the three arrays as after sparse_jac (src/solver/solver.cpp:181-183)
-    *rind = (unsigned int*)malloc(n*sizeof(unsigned int)); *cind = (unsigned int*)malloc(n*sizeof(unsigned int)); *values = (double*)malloc(n*sizeof(double));
-    if (!*rind || !*cind || !*values) { cudaFree(counts); cudaFree(offs); cudaFree(dr); cudaFree(dc); cudaFree(dv); FAIL(c, SGPU_ERR_ARG, "malloc of the COO arrays failed"); }
-    CK(c, cudaMemcpyAsync(*rind, dr, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(*cind, dc, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(*values, dv, (size_t)total*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HostCoo h;
+    h.r = (unsigned int*)malloc(n*sizeof(unsigned int)); h.c = (unsigned int*)malloc(n*sizeof(unsigned int)); h.v = (double*)malloc(n*sizeof(double));
+    if (!h.r || !h.c || !h.v) FAIL(c, SGPU_ERR_ARG, "malloc of the COO arrays failed");
+    CK(c, cudaMemcpyAsync(h.r, dr.p, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(h.c, dc.p, (size_t)total*sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(h.v, dv.p, (size_t)total*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(counts); cudaFree(offs); cudaFree(dr); cudaFree(dc); cudaFree(dv);
+    *rind = h.r; *cind = h.c; *values = h.v; h.r = nullptr; h.c = nullptr; h.v = nullptr;
     *nnz = (int)total;
     return SGPU_OK;
 }
@@ -180,8 +195,20 @@ int sgpu_jacobian_coo(sgpu_ctx* c, int* nnz, unsigned int** rind, unsigned int**
     if (!c || !nnz || !rind || !cind || !values) return SGPU_ERR_ARG;
     if (apply_lhs_transform && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS transform needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
     if (int rc = jacobian_build(c, nullptr)) return rc;
-    return c->v.nv == 5 ? jacobian_export_t<5>(c, nnz, rind, cind, values, apply_lhs_transform)
-                        : jacobian_export_t<4>(c, nnz, rind, cind, values, apply_lhs_transform);
+    return c->v.nv == 5 ? jacobian_export_t<5>(c, 0, c->v.njl, nnz, rind, cind, values, apply_lhs_transform)
+                        : jacobian_export_t<4>(c, 0, c->v.njl, nnz, rind, cind, values, apply_lhs_transform);
+}
+
+int sgpu_jacobian_coo_rows(sgpu_ctx* c, int j_first, int j_count, int* nnz, unsigned int** rind, unsigned int** cind, double** values,
+                           int apply_lhs_transform) {
+    if (!c || !nnz || !rind || !cind || !values) return SGPU_ERR_ARG;
+    if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
+    if (apply_lhs_transform && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS transform needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
+    const int ja = std::max(j_first, c->v.j0), jb = std::min(j_first + j_count, c->v.j1);
+    if (jb <= ja) FAIL(c, SGPU_ERR_ARG, "rows [%d, %d) do not intersect the owned rows [%d, %d)", j_first, j_first + j_count, c->v.j0, c->v.j1);
+    CK(c, cudaSetDevice(c->device));
+    return c->v.nv == 5 ? jacobian_export_t<5>(c, ja - c->v.j0, jb - c->v.j0, nnz, rind, cind, values, apply_lhs_transform)
+                        : jacobian_export_t<4>(c, ja - c->v.j0, jb - c->v.j0, nnz, rind, cind, values, apply_lhs_transform);
 }
 
 int sgpu_dres_dbeta(sgpu_ctx* c, double* out) {
@@ -191,15 +218,15 @@ int sgpu_dres_dbeta(sgpu_ctx* c, double* out) {
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
     if (int rc = apply_bcs(c, SGPU_STATE_Q)) return rc;
-    double* tmp = nullptr;
-    CK(c, cudaMalloc(&tmp, v.plane*sizeof(double)));
+    DevBuf tmpb;
+    CK(c, tmpb.alloc(v.plane*sizeof(double)));
+    double* tmp = tmpb.as<double>();
     sa_dbeta_kernel<true><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->g, metrics_of(c), c->q[0], c->wdist, tmp);
     CKL(c); c->launches++;
     // per-cell field [nic][njc]: reuse the state download with one plane broadcast, then compact on the host side
     std::vector<double> h((size_t)v.plane);
     CK(c, cudaMemcpyAsync(h.data(), tmp, v.plane*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(tmp);
     for (int i = 0; i < v.nic; i++) for (int jl = 0; jl < v.njl; jl++) out[(size_t)i*v.njc + v.j0 + jl] = h[v.at(jl + JOFF, i + IOFF)];
     return SGPU_OK;
 }
@@ -213,8 +240,9 @@ int sgpu_surface_gradient(sgpu_ctx* c, int which, int i_first, int count, double
     CK(c, cudaSetDevice(c->device));
     if (!c->ghost_tab) if (int rc = build_ghost_table(c)) return rc;
     if (int rc = apply_bcs(c, which)) return rc;
-    double* g = nullptr;
-    CK(c, cudaMalloc(&g, v.plane*v.nv*sizeof(double)));
+    DevBuf gb;
+    CK(c, gb.alloc(v.plane*v.nv*sizeof(double)));
+    double* g = gb.as<double>();
     CK(c, cudaMemsetAsync(g, 0, v.plane*v.nv*sizeof(double), c->stream));
     // cl = -Fc sin(aoa) + Fn cos(aoa), cd = Fc cos(aoa) + Fn sin(aoa)   (io.cpp:240-246)
     const double ca = cos(aoa), sa = sin(aoa);
@@ -228,9 +256,7 @@ int sgpu_surface_gradient(sgpu_ctx* c, int which, int i_first, int count, double
         else surface_grad_kernel<4><<<(count + 63)/64, 64, 0, c->stream>>>(v, c->g, m, gt, c->q[which], c->xv, c->yv, i_first, count, a_np, a_cp, a_nv, a_cv, c->d.mu_inf, qinf, g);
         CKL(c); c->launches++;
     }
-    int rc = download_planes(c, g, v.nv, dFdq);
-    cudaFree(g);
-    return rc;
+    return download_planes(c, g, v.nv, dFdq);
 }
 
 int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) {
@@ -238,8 +264,9 @@ int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) 
     if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
-    double *xp = nullptr, *yp = nullptr;
-    CK(c, cudaMalloc(&xp, v.plane*v.nv*sizeof(double))); CK(c, cudaMalloc(&yp, v.plane*v.nv*sizeof(double)));
+    DevBuf xb, yb;
+    CK(c, xb.alloc(v.plane*v.nv*sizeof(double))); CK(c, yb.alloc(v.plane*v.nv*sizeof(double)));
+    double *xp = xb.as<double>(), *yp = yb.as<double>();
     CK(c, cudaMemsetAsync(xp, 0, v.plane*v.nv*sizeof(double), c->stream));
     CK(c, cudaMemsetAsync(yp, 0, v.plane*v.nv*sizeof(double), c->stream));
     // x: GLOBAL host AoS -> planes (owned rows + the slab's ghost rows)
@@ -258,9 +285,7 @@ int sgpu_jacobian_apply(sgpu_ctx* c, int transpose, const double* x, double* y) 
     if (v.nv == 5) jac_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, xp, yp, transpose);
     else jac_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, xp, yp, transpose);
     CKL(c); c->launches++;
-    int rc = download_planes(c, yp, v.nv, y);
-    cudaFree(xp); cudaFree(yp);
-    return rc;
+    return download_planes(c, yp, v.nv, y);
 }
 
 } // extern "C"

@@ -869,9 +869,9 @@ __device__ __forceinline__ bool entry_present(int nv, int s, int r, int c) {
 }
 
 template <int NV>
-__global__ void jac_count_kernel(View v, GhostTable gt, int nslots, bool viscous, bool order2, int* __restrict__ counts) {
+__global__ void jac_count_kernel(View v, GhostTable gt, int nslots, bool viscous, bool order2, int jl0, int nrw, int* __restrict__ counts) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    const int jl = blockIdx.y;
+    const int jw = blockIdx.y, jl = jl0 + jw;                      // row window [jl0, jl0 + nrw) of the slab
     if (i >= v.nic) return;
     const int gj = v.j0 + jl;
     SlotCols sc; resolve_slots(gt, nslots, i, gj, viscous, order2, sc);
@@ -888,16 +888,16 @@ __global__ void jac_count_kernel(View v, GhostTable gt, int nslots, bool viscous
                 cnt += present ? 1 : 0;
             }
         }
-        counts[((size_t)i*v.njl + jl)*NV + r] = cnt;
+        counts[((size_t)i*nrw + jw)*NV + r] = cnt;
     }
 }
 
 template <int NV>
 __global__ void jac_fill_kernel(View v, GhostTable gt, int nslots, bool viscous, bool order2, const double* __restrict__ J,
                                 const long long* __restrict__ offsets, const double* __restrict__ dt, int lhs_transform,
-                                unsigned int* __restrict__ rind, unsigned int* __restrict__ cind, double* __restrict__ values) {
+                                int jl0, int nrw, unsigned int* __restrict__ rind, unsigned int* __restrict__ cind, double* __restrict__ values) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    const int jl = blockIdx.y;
+    const int jw = blockIdx.y, jl = jl0 + jw;
     if (i >= v.nic) return;
     const int gj = v.j0 + jl;
     const size_t o = v.at(jl + JOFF, i + IOFF);
@@ -915,7 +915,7 @@ __global__ void jac_fill_kernel(View v, GhostTable gt, int nslots, bool viscous,
     }
     const unsigned int rowcell = (unsigned int)i*(unsigned int)v.njc + (unsigned int)gj;
     for (int r = 0; r < NV; r++) {
-        long long pos = offsets[((size_t)i*v.njl + jl)*NV + r];
+        long long pos = offsets[((size_t)i*nrw + jw)*NV + r];
         const unsigned int row = rowcell*NV + r;
         for (int k = 0; k < n; k++) {
             const int s = ord[k];

@@ -164,9 +164,9 @@ static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io, bool refactor =
     int precond = io->precond;
     const int max_iter = io->max_iter > 0 ? io->max_iter : 500;
     const double rtol = io->rtol > 0 ? io->rtol : 1e-10;
-    cudaEvent_t e0, e1, e2, t0, t1, t2;
-    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1)); CK(c, cudaEventCreate(&e2));
-    CK(c, cudaEventCreate(&t0)); CK(c, cudaEventCreate(&t1)); CK(c, cudaEventCreate(&t2));
+    struct Events { cudaEvent_t e[6] = {}; ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); } } evs;   // released on every exit path
+    for (auto& x : evs.e) CK(c, cudaEventCreate(&x));
+    const cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], t0 = evs.e[3], t1 = evs.e[4], t2 = evs.e[5];
     bool timed = false;
     io->matvec_ms = io->precond_ms = 0.0f;
     CK(c, cudaEventRecord(e0, c->stream));
@@ -252,7 +252,6 @@ static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io, bool refactor =
     CK(c, cudaEventSynchronize(e2));
     cudaEventElapsedTime(&io->setup_ms, e0, e1); cudaEventElapsedTime(&io->solve_ms, e1, e2);
     if (timed) { cudaEventElapsedTime(&io->precond_ms, t0, t1); cudaEventElapsedTime(&io->matvec_ms, t1, t2); }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
     io->iterations = iters;
     io->converged = bnorm == 0.0 || io->rel_residual <= rtol;
     return SGPU_OK;

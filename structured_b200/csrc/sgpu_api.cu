@@ -46,6 +46,7 @@ struct sgpu_ctx {
     double* halo_peer[2] = {nullptr, nullptr};
     bool halo_peer_ipc[2] = {false, false};
     unsigned long long halo_seq = 0;
+    int* halo_err = nullptr;               // device word raised by a halo wait that timed out
     JacStore jac{};
     LinWork* lin = nullptr;              // device linear solve workspace (linsolve_api.inl)
     // pipelined host path
@@ -122,8 +123,12 @@ int sgpu_create(const sgpu_desc* d, sgpu_ctx** out) {
     sgpu_ctx* c = new sgpu_ctx();
     c->d = *d; c->bcs.assign(d->bc, d->bc + d->n_bc); c->d.bc = c->bcs.data();
     c->device = d->device;
-    for (auto& b : c->bcs)                                         // BoundaryContainer::get_index, bc.cpp:436-457
+    for (auto& b : c->bcs) {                                       // BoundaryContainer::get_index, bc.cpp:436-457
         if (b.end < 0) b.end = ((b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP) ? nic : njc) + 2 + b.end;
+        // a periodic table fills BOTH ghost lines of its direction whichever face it names (bc.cpp:329-365): store the
+        // canonical face so that face-based filters (column / row chunks of the host pipeline) treat both spellings alike
+        if (b.type == SGPU_BC_PERIODIC) b.face = (b.face == SGPU_FACE_RIGHT) ? SGPU_FACE_LEFT : (b.face == SGPU_FACE_TOP ? SGPU_FACE_BOTTOM : b.face);
+    }
     View& v = c->v;
     v.nic = nic; v.njc = njc; v.ni = d->ni; v.nj = d->nj; v.j0 = j0; v.j1 = j1; v.njl = j1 - j0; v.nv = 4 + d->ntrans;
     v.pitch = ((nic + 2*IOFF + 15)/16)*16; v.rows = v.njl + 2*JOFF; v.plane = (size_t)v.rows*v.pitch;
@@ -151,6 +156,8 @@ int sgpu_create(const sgpu_desc* d, sgpu_ctx** out) {
     if (ce == cudaSuccess) ce = alloc(&c->l2sq_dev, 8);
     if (ce == cudaSuccess) ce = alloc(&c->halo_recv[0], (size_t)4*v.nv*nic + 2);
     if (ce == cudaSuccess) ce = alloc(&c->halo_recv[1], (size_t)4*v.nv*nic + 2);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->halo_err, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(c->halo_err, 0, sizeof(int));
     if (ce == cudaSuccess) ce = cudaMemset(c->halo_recv[0], 0, ((size_t)4*v.nv*nic + 2)*sizeof(double));
     if (ce == cudaSuccess) ce = cudaMemset(c->halo_recv[1], 0, ((size_t)4*v.nv*nic + 2)*sizeof(double));
     if (ce != cudaSuccess) {
@@ -195,13 +202,22 @@ int sgpu_destroy(sgpu_ctx* c) {
     if (c->ghost_tab) cudaFree(c->ghost_tab);
     if (c->wall_last) cudaFree(c->wall_last);
     if (c->jac_err) cudaFree(c->jac_err);
+    if (c->halo_err) cudaFree(c->halo_err);
     for (auto& p : c->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
     return SGPU_OK;
 }
 
 int sgpu_set_stream(sgpu_ctx* c, void* s) { if (!c) return SGPU_ERR_ARG; c->stream = (cudaStream_t)s; return SGPU_OK; }
-int sgpu_synchronize(sgpu_ctx* c) { if (!c) return SGPU_ERR_ARG; CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream)); return SGPU_OK; }
+int sgpu_synchronize(sgpu_ctx* c) {
+    if (!c) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream));
+    if (c->halo_seq) {                                             // a halo wait that gave up (neighbour never pushed)
+        int e = 0; CK(c, cudaMemcpy(&e, c->halo_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) { CK(c, cudaMemset(c->halo_err, 0, sizeof(int))); FAIL(c, SGPU_ERR_STATE, "halo exchange timed out %d time(s): a neighbour slab did not push its boundary rows", e); }
+    }
+    return SGPU_OK;
+}
 int sgpu_dims(const sgpu_ctx* c, int* nic, int* njc, int* nv, int* j_begin, int* j_end) {
     if (!c) return SGPU_ERR_ARG;
     if (nic) *nic = c->v.nic; if (njc) *njc = c->v.njc; if (nv) *nv = c->v.nv; if (j_begin) *j_begin = c->v.j0; if (j_end) *j_end = c->v.j1;
@@ -257,6 +273,66 @@ int sgpu_set_field_window(sgpu_ctx* c, const char* name, const double* f, int j_
 int sgpu_set_field(sgpu_ctx* c, const char* name, const double* f) {
     if (!c) return SGPU_ERR_ARG;
     return sgpu_set_field_window(c, name, f, 0, c->v.njc);
+}
+
+int sgpu_get_field(sgpu_ctx* c, const char* name, double* out) {
+    if (!c || !name || !out) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const double* src = !strcmp(name, "wall_distance") ? c->wdist : (!strcmp(name, "beta") ? c->beta : nullptr);
+    if (!src) FAIL(c, SGPU_ERR_ARG, "unknown field '%s' (wall_distance | beta)", name);
+    const View& v = c->v;                                          // cold path: whole plane to the host, scatter there
+    std::vector<double> h(v.plane);
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(h.data(), src, sizeof(double)*v.plane, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < v.nic; i++)
+        for (int j = v.j0; j < v.j1; j++) out[(size_t)i*v.njc + j] = h[v.at(j - v.j0 + JOFF, i + IOFF)];
+    return SGPU_OK;
+}
+
+// Wall distance on the device (SA extension).  segments: [nseg][4] = x0 y0 x1 y1 of the wall edges.
+int sgpu_compute_wall_distance(sgpu_ctx* c, const double* segments, int nseg) {
+    if (!c || (!segments && nseg > 0) || nseg < 0) return SGPU_ERR_ARG;
+    if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    if (nseg == 0) {                                               // no wall anywhere: the destruction term vanishes as d -> inf
+        fill_kernel<<<296, 256, 0, c->stream>>>(c->wdist, v.plane, 1e30);
+        CKL(c); c->launches++;
+        return SGPU_OK;
+    }
+    std::vector<double> h((size_t)nseg*5);
+    for (int k = 0; k < nseg; k++) {
+        const double ax = segments[4*k], ay = segments[4*k + 1], bx = segments[4*k + 2] - ax, by = segments[4*k + 3] - ay;
+        const double l2 = bx*bx + by*by;
+        h[5*k] = ax; h[5*k + 1] = ay; h[5*k + 2] = bx; h[5*k + 3] = by; h[5*k + 4] = l2 > 0.0 ? 1.0/l2 : 0.0;
+    }
+    if (int rc = ensure_stage(c, h.size())) return rc;
+    CK(c, cudaMemcpyAsync(c->stage, h.data(), sizeof(double)*h.size(), cudaMemcpyHostToDevice, c->stream));
+    wall_distance_kernel<<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, c->xv, c->yv, c->stage, nseg, c->wdist);
+    CKL(c); c->launches++;
+    CK(c, cudaStreamSynchronize(c->stream));                       // h goes out of scope
+    return SGPU_OK;
+}
+
+// The same with the segments derived from the [[boundary]] tables: every edge of the grid boundary covered by a `wall`
+// or `isothermalwall` table.  xv, yv: GLOBAL host vertex arrays [ni][nj] (Mesh::xv.data()).
+int sgpu_wall_distance_from_bcs(sgpu_ctx* c, const double* xv, const double* yv) {
+    if (!c || !xv || !yv) return SGPU_ERR_ARG;
+    const View& v = c->v;
+    std::vector<double> seg;
+    auto X = [&](const double* a, int i, int j) { return a[(size_t)i*v.nj + j]; };
+    for (const sgpu_bc& b : c->bcs) {
+        if (b.type != SGPU_BC_WALL && b.type != SGPU_BC_ISOTHERMALWALL) continue;
+        const bool horiz = b.face == SGPU_FACE_BOTTOM || b.face == SGPU_FACE_TOP;
+        const int n = horiz ? v.nic : v.njc;
+        for (int p = std::max(b.start, 1); p <= std::min(b.end, n); p++) {     // padded index p <-> cell p - 1
+            int i0, j0, i1, j1;
+            if (horiz) { i0 = p - 1; i1 = p; j0 = j1 = (b.face == SGPU_FACE_BOTTOM ? 0 : v.nj - 1); }
+            else { j0 = p - 1; j1 = p; i0 = i1 = (b.face == SGPU_FACE_LEFT ? 0 : v.ni - 1); }
+            seg.push_back(X(xv, i0, j0)); seg.push_back(X(yv, i0, j0)); seg.push_back(X(xv, i1, j1)); seg.push_back(X(yv, i1, j1));
+        }
+    }
+    return sgpu_compute_wall_distance(c, seg.data(), (int)(seg.size()/4));
 }
 
 // download a cell plane group to a GLOBAL host AoS array (owned rows only); window = host holds owned rows only
@@ -491,6 +567,7 @@ static int residual_host_pipelined_cols(sgpu_ctx* c, const double* q, int qj0, i
     const int nstrips_all = (v.nic + RCELLS - 1)/RCELLS;
     int nch = std::min(18, nstrips_all/2);                      // measured at 4096^2 (69 strips): 12 chunks 962, 18 1040, 23 1032, 35 1005 Mcell/s
     if (const char* e = getenv("SGPU_PIPE_CHUNKS")) nch = std::max(1, std::min(atoi(e), nstrips_all));
+    nch = std::min(nch, 64);                                    // pipe_up / pipe_cmp hold 64 events
     const int jlo = std::max(std::max(v.j0 - 2, 0), qj0), jhi = std::min(std::min(v.j1 + 2, v.njc), qj0 + qjn);   // rows uploaded
     const int nrows_up = jhi - jlo, r0_up = jlo - v.j0 + JOFF;
     bool vert_periodic = false;
@@ -787,6 +864,15 @@ int sgpu_halo_pack(sgpu_ctx* c, int which, int side, double* buf) {
     CKL(c); c->launches++;
     return SGPU_OK;
 }
+// the two GHOST rows of a side in the layout of sgpu_halo_pack: lets a caller verify what an exchange delivered
+int sgpu_halo_pack_ghost(sgpu_ctx* c, int which, int side, double* buf) {
+    if (!c || !buf || side < 0 || side > 1 || which < 0 || which > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_pack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], buf, halo_rows(c, side, true));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
 int sgpu_halo_unpack(sgpu_ctx* c, int which, int side, const double* buf) {
     if (!c || !buf || side < 0 || side > 1 || which < 0 || which > 1) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
@@ -841,6 +927,10 @@ int sgpu_halo_push(sgpu_ctx* c, int which) {
     if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
+    for (int side = 0; side < 2; side++) {                          // a neighbour without a registered buffer would leave its
+        const bool has_nb = side == 0 ? v.j0 > 0 : v.j1 < v.njc;    // halo_wait_kernel spinning forever: refuse instead
+        if (has_nb && !c->halo_peer[side]) FAIL(c, SGPU_ERR_STATE, "halo push: side %d has a neighbour slab but no peer receive buffer (sgpu_halo_set_peer / sgpu_halo_open_peer)", side);
+    }
     c->halo_seq++;
     const size_t slot = (size_t)(c->halo_seq & 1ull)*halo_slot_doubles(c);
     for (int side = 0; side < 2; side++) {
@@ -857,11 +947,13 @@ int sgpu_halo_pull(sgpu_ctx* c, int which) {
     if (!c || which < 0 || which > 1) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     const View& v = c->v;
+    if (c->halo_seq == 0) FAIL(c, SGPU_ERR_STATE, "halo pull before the first halo push");
     const size_t slot = (size_t)(c->halo_seq & 1ull)*halo_slot_doubles(c);
     for (int side = 0; side < 2; side++) {
         const bool has_nb = side == 0 ? v.j0 > 0 : v.j1 < v.njc;
         if (!has_nb) continue;
-        halo_wait_kernel<<<1, 1, 0, c->stream>>>(halo_flag(c, c->halo_recv[side]), c->halo_seq);
+        if (!c->halo_peer[side]) FAIL(c, SGPU_ERR_STATE, "halo pull: side %d has a neighbour slab but no registered peer", side);
+        halo_wait_kernel<<<1, 1, 0, c->stream>>>(halo_flag(c, c->halo_recv[side]), c->halo_seq, 20000000000ull, c->halo_err);
         CKL(c);
         halo_unpack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, c->q[which], c->halo_recv[side] + slot, halo_rows(c, side, true));
         CKL(c); c->launches += 2;

@@ -61,3 +61,77 @@ def have_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def crop_case(case, ia, ib, ja, jb, wall_distance=None):
+    """Window [ia, ib) x [ja, jb) of a large case as a small case for the CPU oracle: physical boundary tables are kept
+    (shifted, clipped) where the window touches that boundary, cut edges get `freestream` ghosts.  Residual and Jacobian
+    rows of cells at least 3 cells away from every CUT edge equal those of the large case (stencil radius 2 + the corner
+    ghosts a cut edge's BC cannot reproduce); the limiter constants stay those of the large grid (`global_counts`).
+    Periodic / wake tables cannot be cropped: the window must stay 3 cells away from such boundaries."""
+    import copy
+    from structured_b200.cases import Boundary
+    c = copy.copy(case)
+    c.ni, c.nj = ib - ia + 1, jb - ja + 1
+    c.xv = np.ascontiguousarray(case.xv[ia:ib + 1, ja:jb + 1]); c.yv = np.ascontiguousarray(case.yv[ia:ib + 1, ja:jb + 1])
+    wd = case.wall_distance if wall_distance is None else wall_distance
+    c.wall_distance = None if wd is None else np.ascontiguousarray(wd[ia:ib, ja:jb])
+    c.beta = None if case.beta is None else np.ascontiguousarray(case.beta[ia:ib, ja:jb])
+    c.global_counts = (case.nic, case.njc)
+    c.window = None
+    touch = {"bottom": ja == 0, "top": jb == case.njc, "left": ia == 0, "right": ib == case.nic}
+    bcs = []
+    for b in case.boundaries:
+        assert b.type not in ("periodic", "wake") or not touch[b.face], "periodic / wake boundaries cannot be cropped"
+        if not touch[b.face]:
+            continue
+        horiz = b.face in ("bottom", "top")
+        n_old, off, n_new = (case.nic, ia, ib - ia) if horiz else (case.njc, ja, jb - ja)
+        end = b.end if b.end >= 0 else n_old + 2 + b.end
+        s, e = max(b.start - off, 0), min(end - off, n_new + 1)
+        if e >= s:
+            bcs.append(Boundary(b.type, b.face, s, e, b.u, b.v, b.T))
+    for f in ("bottom", "top", "left", "right"):
+        if not touch[f]:
+            bcs.append(Boundary("freestream", f, 0, -1))
+    c.boundaries = bcs
+    return c
+
+
+def rows_of_cells(njc, nv, cells):
+    """flat Jacobian row numbers (i*njc + j)*nv + k of a list of cells"""
+    cells = np.asarray(cells, dtype=np.int64).reshape(-1, 2)
+    return ((cells[:, 0] * njc + cells[:, 1])[:, None] * nv + np.arange(nv)[None, :]).reshape(-1)
+
+
+def crop_interior(case, box):
+    """cells of a crop box that are >= 3 cells away from every cut edge: (i0, i1, j0, j1), half open"""
+    ia, ib, ja, jb = box
+    return (ia if ia == 0 else ia + 3, ib if ib == case.nic else ib - 3, ja if ja == 0 else ja + 3, jb if jb == case.njc else jb - 3)
+
+
+def oracle_on_crop(case, q, box, wall_distance=None, lhs=True, want_jacobian=True):
+    """CPU oracle on a window of a LARGE case: returns (residual of the window's trustworthy cells [i0:i1, j0:j1],
+    (i0, i1, j0, j1), Jacobian rows of those cells as COO with GLOBAL numbering or None)."""
+    from oracle.bindings import PortOracle
+    ia, ib, ja, jb = box
+    cc = crop_case(case, ia, ib, ja, jb, wall_distance=wall_distance)
+    port = PortOracle(cc)
+    qc = np.ascontiguousarray(q[ia:ib, ja:jb])
+    i0, i1, j0, j1 = crop_interior(case, box)
+    res = port.residual(qc, lhs)[i0 - ia:i1 - ia, j0 - ja:j1 - ja]
+    coo = None
+    if want_jacobian:
+        ri, ci, va = port.jacobian(qc, lhs)
+        nv, w = case.nv, jb - ja
+
+        def to_global(idx):
+            idx = idx.astype(np.int64)
+            cell, k = idx // nv, idx % nv
+            return (((cell // w) + ia) * case.njc + (cell % w) + ja) * nv + k
+        gr, gc = to_global(ri), to_global(ci)
+        cells = [(i, j) for i in range(i0, i1) for j in range(j0, j1)]
+        keep = np.isin(gr, rows_of_cells(case.njc, nv, cells))
+        coo = (gr[keep], gc[keep], va[keep])
+    port.close()
+    return res, (i0, i1, j0, j1), coo

@@ -207,10 +207,11 @@ def test_error_behaviour_mirrors_reference_messages():
     eq.close()
 
 
-def test_full_size_4096_properties():
-    """BASELINE.json's 1-GPU size (4096 x 4096, SA): size-independent properties instead of an oracle run --
-    device norms == norms of the downloaded field; two j-slabs reproduce the one-slab field bit for bit
-    (checksum of checksums + sampled rows); explicit-step bookkeeping keeps q finite."""
+def test_full_size_4096_matches_oracle_and_properties():
+    """BASELINE.json's 1-GPU size (4096 x 4096, SA), the bench workload itself: the residual of EVERY cell against the
+    CPU oracle (one oracle evaluation, ~10 s), then size-independent properties -- device norms == norms of the downloaded
+    field; two j-slabs reproduce the one-slab field bit for bit (checksum of checksums + sampled rows)."""
+    from oracle.bindings import PortOracle
     n = 4096
     case = turbulent_channel_case(n, n, ntrans=1)
     q = case.perturbed_q()
@@ -219,6 +220,12 @@ def test_full_size_4096_properties():
     l2 = eq.residual_device(0, norms=True)
     rhs = eq.get_rhs()
     assert np.isfinite(rhs).all()
+    port = PortOracle(case)
+    want_rhs = port.residual(q)
+    port.close()
+    err = field_rel_err(rhs, want_rhs)
+    assert err.max() <= TOL, err
+    del want_rhs, port
     want = np.einsum("ijk,ijk->k", rhs, rhs)
     assert np.abs(l2 - want).max() <= 1e-12 * want.max()
     col_sum = rhs.sum(axis=0)                                  # [njc][nv] checksum per row
@@ -240,18 +247,29 @@ def test_full_size_4096_properties():
     assert np.array_equal(got_sum, col_sum)
 
 
-@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("periodic", ["left", "right", None])
 @pytest.mark.parametrize("ntrans", [0, 1])
 def test_host_column_pipeline_equals_device_path_bitwise(ntrans, periodic):
     """sgpu_residual_host pipelines column chunks (H2D | BCs + kernel | D2H); every chunking must give the bits of the
-    device-resident path, including the corner ghosts a periodic side copies from the wrap-around column"""
-    case = turbulent_channel_case(430, 52, ntrans=ntrans, reynolds=2e4, periodic=periodic)
-    eq = gpu_eq(case)
+    device-resident path, including the corner ghosts a periodic side copies from the wrap-around column -- whichever
+    face the periodic table names (the reference fills both ghost columns for either, bc.cpp:329-365).  The pipelined
+    path runs on a context whose ghost cells hold ANOTHER state's values, so a boundary condition skipped in some
+    chunk cannot hide behind ghosts left over from the device-path evaluation."""
+    case = turbulent_channel_case(430, 52, ntrans=ntrans, reynolds=2e4, periodic=periodic is not None)
+    if periodic == "right":
+        for b in case.boundaries:
+            if b.type == "periodic":
+                b.face = "right"
     q = case.perturbed_q(0.02)
-    eq.set_state(q)
-    eq.residual_device()
-    dev = eq.get_rhs()
-    for chunks in ("2", "3", "7"):
+    ref = gpu_eq(case)
+    ref.set_state(q)
+    ref.residual_device()
+    dev = ref.get_rhs()
+    ref.close()
+    eq = gpu_eq(case)
+    for chunks in ("2", "3", "7", "70"):
+        eq.set_state(case.perturbed_q(0.05) * 1.1)             # poison: ghosts of a different state
+        eq.residual_device()
         os.environ["SGPU_PIPE_CHUNKS"] = chunks
         try:
             assert np.array_equal(eq.calc_residual(q), dev), chunks

@@ -141,3 +141,58 @@ def test_port_surface_matches_reference_library_channel():
     assert np.array_equal(s["wall"], wall)
     assert len(rows) == len(s["xw"])
     ref.close(); port.close()
+
+
+def test_crop_reproduces_the_full_grid_oracle_bit_for_bit():
+    """tests/helpers.py::crop_case is what lets the GPU tests compare Jacobian rows at BASELINE's sizes: a window of a
+    large case (physical boundaries kept, cut edges frozen, the large grid's limiter constants) reproduces the
+    full-grid oracle on every cell >= 3 cells away from a cut edge -- residual and Jacobian rows, exactly."""
+    from helpers import oracle_on_crop, rows_of_cells
+    from structured_b200.cases import flat_plate_case
+    case = flat_plate_case(90, 70, reynolds=1e5)
+    port = PortOracle(case)
+    case.wall_distance = port.wall_distance()
+    q = case.perturbed_q(0.02)
+    res = port.residual(q, True)
+    full = port.jacobian(q, True)
+    ile = 18
+    for box in ((0, 22, 0, 20), (ile - 10, ile + 12, 0, 18), (68, 90, 0, 20), (40, 62, 25, 47), (0, 20, 50, 70), (70, 90, 48, 70)):
+        r, (i0, i1, j0, j1), coo = oracle_on_crop(case, q, box)
+        assert np.array_equal(r, res[i0:i1, j0:j1])
+        rows = rows_of_cells(case.njc, 5, [(i, j) for i in range(i0, i1) for j in range(j0, j1)])
+        keep = np.isin(full[0], rows)
+        assert jac_rel_err(q.size, coo, (full[0][keep], full[1][keep], full[2][keep])) == 0.0
+        assert keep.sum() == len(coo[2])
+    port.close()
+
+
+def test_static_colouring_rows_equal_the_pattern_coloured_jacobian():
+    """port_jacobian_rows (colour = (i mod 5, j mod 5, k), no pattern pass) against the sparse_jac stand-in"""
+    from helpers import rows_of_cells
+    from structured_b200.cases import zoo_case
+    case = zoo_case("A", 33, 21, ntrans=1)
+    port = PortOracle(case)
+    q = case.perturbed_q(0.02)
+    full = port.jacobian(q, True)
+    cells = [(i, j) for i in range(0, 33, 4) for j in range(0, 21, 3)]
+    rows = port.jacobian_rows(q, cells)
+    keep = np.isin(full[0], rows_of_cells(case.njc, 5, cells)) & (full[2] != 0.0)
+    assert jac_rel_err(q.size, rows, (full[0][keep], full[1][keep], full[2][keep])) == 0.0
+    port.close()
+
+
+def test_port_wall_distance_against_numpy():
+    from structured_b200.cases import flat_plate_case, wall_segments, zoo_case, ZOO_SA
+    for case in [flat_plate_case(60, 40)] + [zoo_case(z, ntrans=1) for z in ZOO_SA]:
+        port = PortOracle(case)
+        got = port.wall_distance()
+        seg = wall_segments(case)
+        xc = 0.25 * (case.xv[:-1, :-1] + case.xv[1:, :-1] + case.xv[:-1, 1:] + case.xv[1:, 1:])
+        yc = 0.25 * (case.yv[:-1, :-1] + case.yv[1:, :-1] + case.yv[:-1, 1:] + case.yv[1:, 1:])
+        a, ab = seg[:, :2], seg[:, 2:] - seg[:, :2]
+        d = np.stack([xc, yc], axis=-1)[:, :, None, :] - a[None, None, :, :]
+        t = np.clip((d * ab).sum(-1) / (ab * ab).sum(-1), 0.0, 1.0)
+        want = np.sqrt((((d - t[..., None] * ab) ** 2).sum(-1)).min(axis=-1))
+        assert np.abs(got - want).max() <= 1e-13 * want.max()
+        assert got.min() > 0
+        port.close()
