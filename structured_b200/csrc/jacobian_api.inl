@@ -66,6 +66,51 @@ static int launch_jacobian_t(sgpu_ctx* c, const JacParams& p) {
     return SGPU_OK;
 }
 
+// single-pass marching build (jacobian_march.cuh): strips of 31 columns x row chunks, then the boundary-band fold
+template <int NV, int ORDER, int FLUX, bool VISC>
+static int launch_jacobian_march_t(sgpu_ctx* c, const JacParams& p) {
+    using Cfg = JmCfg<NV, ORDER, VISC>;
+    const View& v = c->v;
+    auto kern = jac_march_kernel<NV, ORDER, FLUX, VISC>;
+    static int occ_dev[64] = {0}, sms_dev[64] = {0};
+    int& occ = occ_dev[c->device & 63]; int& sms = sms_dev[c->device & 63];
+    if (!occ) {
+        CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+        CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32*JM_WARPS, Cfg::smem_bytes));
+        CK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (occ < 1) occ = 1;
+    }
+    if (!c->jgeo_valid) {                                           // static per-face geometry weights, once per grid
+        if (!c->jgeo) CK(c, cudaMalloc(&c->jgeo, (size_t)2*JG_N*v.plane*sizeof(double)));
+        CK(c, cudaMemsetAsync(c->jgeo, 0, (size_t)2*JG_N*v.plane*sizeof(double), c->stream));
+        jac_geom_kernel<VISC><<<dim3((v.pitch + 127)/128, v.rows), 128, 0, c->stream>>>(v, p.m, c->jgeo, c->jgeo + (size_t)JG_N*v.plane);
+        CKL(c); c->launches++;
+        c->jgeo_valid = true;
+    }
+    JmParams jp;
+    jp.gchi = c->jgeo; jp.geta = c->jgeo + (size_t)JG_N*v.plane;
+    jp.v = v; jp.g = p.g; jp.m = p.m; jp.q = p.q; jp.J = p.J; jp.wdist = p.wdist; jp.beta = p.beta;
+    jp.eps_chi = p.eps_chi; jp.eps_eta = p.eps_eta;
+    jp.nstrips = (v.nic + JM_CELLS - 1)/JM_CELLS;
+    // chunk count: an integer number of full waves of (SMs x resident CTAs) where possible, chunks tall enough to amortise
+    // the prologue (ring fill + one extra eta core ~ 2 rows)
+    const int wave = std::max(1, occ*sms);
+    int best = 1; double best_cost = 1e300;
+    for (int nch = 1; nch <= std::max(1, v.njl/8); nch++) {
+        const int rpc = (v.njl + nch - 1)/nch, nchunks = (v.njl + rpc - 1)/rpc;
+        const long long waves = ((long long)jp.nstrips*nchunks + wave - 1)/wave;
+        const double cost = (double)waves*(rpc + 2.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = nchunks; }
+    }
+    jp.rpc = (v.njl + best - 1)/best; jp.nchunks = (v.njl + jp.rpc - 1)/jp.rpc;
+    kern<<<jp.nstrips*jp.nchunks, 32*JM_WARPS, Cfg::smem_bytes, c->stream>>>(jp);
+    CKL(c);
+    jac_fold_kernel<NV><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, p.g, p.m, p.gt, p.q, p.J, p.nslots, p.err);
+    CKL(c);
+    c->launches += 1;
+    return SGPU_OK;
+}
+
 static int jacobian_build(sgpu_ctx* c, float* build_ms) {
     if (!c->have_grid) FAIL(c, SGPU_ERR_STATE, "sgpu_set_grid has not been called");
     CK(c, cudaSetDevice(c->device));
@@ -79,8 +124,10 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
         CK(c, cudaMalloc(&c->jac.blocks, need*sizeof(double)));
         c->jac.cap = need;
     }
+    const char* jm = getenv("SGPU_JAC");
+    const bool two_stage = jm && !strcmp(jm, "two_stage");          // the round-1 build (per-face scratch in HBM), kept for A/B runs
     const int stiles = (v.pitch + STILE - 1)/STILE;
-    const size_t dir_s = (size_t)(v.rows + 1)*stiles*STILE*8*v.nv*v.nv;   // per-face scratch of one direction: 8 stencil cells each
+    const size_t dir_s = two_stage ? (size_t)(v.rows + 1)*stiles*STILE*8*v.nv*v.nv : 0;   // per-face scratch of one direction: 8 stencil cells each
     const size_t need_s = 2*dir_s;
     if (need_s > c->jac_scratch_cap) {
         if (c->jac_scratch) CK(c, cudaFree(c->jac_scratch));
@@ -103,7 +150,7 @@ static int jacobian_build(sgpu_ctx* c, float* build_ms) {
     int rc = SGPU_ERR_ARG;
     const bool roe = c->d.flux == SGPU_FLUX_ROE;
     const int order = c->d.lhs_order;                              // calc_residual(..., lhs = true), src/solver/solver.cpp:80
-#define JAC_CASE(NV_, ORD_, FL_, VI_) rc = launch_jacobian_t<NV_, ORD_, FL_, VI_>(c, p)
+#define JAC_CASE(NV_, ORD_, FL_, VI_) rc = two_stage ? launch_jacobian_t<NV_, ORD_, FL_, VI_>(c, p) : launch_jacobian_march_t<NV_, ORD_, FL_, VI_>(c, p)
     if (v.nv == 5) {
         if (order == 2) { if (roe) JAC_CASE(5, 2, SGPU_FLUX_ROE, true); else JAC_CASE(5, 2, SGPU_FLUX_AUSM, true); }
         else            { if (roe) JAC_CASE(5, 1, SGPU_FLUX_ROE, true); else JAC_CASE(5, 1, SGPU_FLUX_AUSM, true); }

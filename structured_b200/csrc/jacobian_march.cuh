@@ -1,0 +1,580 @@
+// K-JAC, single pass: the block-stencil Jacobian d rhs / d q of calc_residual(q, lhs = true)
+// (the reference's trace_on .. sparse_jac, src/solver/solver.cpp:72-90,156) written ONCE, complete, with no per-face
+// scratch in HBM.
+//
+// A CTA owns a strip of 31 cell columns (+ the chi face that closes it: 32 lanes) and marches a chunk of rows upward.
+// What a face contributes to the 13 stencil blocks of its two cells factors as
+//     d D_face / d q_s  =  [ face "core" ]  x  [ per-cell chain d(W, z)_s / d q_s ]
+// where the core -- dF/d(ql, qr) of the flux function (forward-mode duals through the SAME roe_flux / ausm_flux the
+// residual kernel runs), the limiter derivatives, the viscous-flux coefficients -- is 68 doubles per face.  Cores live in
+// SHARED MEMORY only: the chi core of a row is exchanged between neighbouring lanes, the eta core of the row below is kept
+// in a two-row ring.  The on-chip state is per CELL (3 cores + a ring of per-cell primitives, ~2.3 KB), so occupancy is
+// bought with THREADS PER CELL: the four warps of a CTA work on the same 31 cells, lanes = columns (coalesced), warps =
+// tasks --
+//   phase A  (cores)     warp 0: chi limiter derivatives + flux passes 0,1     warp 1: chi flux passes 2,3 + viscous coefficients
+//                        warp 2: eta limiter derivatives + flux passes 0,1     warp 3: eta flux passes 2,3 + viscous coefficients
+//   phase B  (assembly)  the 13 slots are split over the warps; per slot and equation row the coefficient vectors of the
+//                        <= 4 contributing faces are summed first and the per-cell chain is applied once; every J entry
+//                        is stored exactly once (streaming stores).  The warps also convert the next rows entering the
+//                        rings and prepare the SA source sensitivities of the next row.
+// Two __syncthreads per row; three CTAs (12 warps) per SM.  Ghost cells are independent slots here; jac_fold_kernel
+// folds them into the interior cells they are functions of afterwards (boundary band only).
+#pragma once
+#include "jacobian_kernel.cuh"
+
+namespace sg {
+
+constexpr int JM_CELLS = 31;            // cells per strip; lane 31 only owns the chi face that closes the strip
+constexpr int JM_WARPS = 4;
+constexpr int JM_RC = 36;               // ring columns: cells i0-2 .. i0+33
+
+template <int V> struct IC { static constexpr int value = V; };   // compile-time int passed through generic lambdas
+
+template <int NV, int ORDER, bool VISC> struct JmCfg {
+    static constexpr bool SA = NV > 4;
+    static constexpr int NWV = 6;                                   // ring W: rho, u, v, p, 1/rho, rho nu~
+    static constexpr int NZV = VISC ? (SA ? 6 : 3) : 1;             // ring Z: T, mu, dmu/dT [, mu_t, c_mt, dmu_t/dq4]
+    static constexpr int C_FD = 0, C_F0 = 32, C_DL = 33, C_DR = C_DL + (ORDER == 2 ? 12 : 0), C_V = C_DR + (ORDER == 2 ? 12 : 0);
+    static constexpr int CORE = C_V + (VISC ? 11 : 0);
+    static constexpr int W_DBL = 6*NWV*JM_RC, Z_DBL = 4*NZV*JM_RC, C_DBL = CORE*32, S_DBL = SA ? 2*7*32 : 0;
+    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(W_DBL + Z_DBL + 3*C_DBL + S_DBL);
+};
+enum { JW_R = 0, JW_U, JW_V, JW_P, JW_RI, JW_RN };
+enum { JZ_T = 0, JZ_MU, JZ_DMUDT, JZ_MUT, JZ_CMT, JZ_DMUT4 };
+enum { JV_MU = 0, JV_KK, JV_UB, JV_VB, JV_TXX, JV_TYY, JV_TXY, JV_TX, JV_TY, JV_GN, JV_MUSA };
+enum { JF_C0 = 0, JF_C1 = 1, JF_E0 = 2, JF_E1 = 3 };   // chi face i (-), chi face i+1 (+), eta face j (-), eta face j+1 (+)
+enum { JC_NONE = -1, JC_D0 = 0, JC_D1 = 1, JC_P = 2, JC_M = 3 };
+
+// role of the stencil cell at offset (dx, dy) from the row cell in each of its four faces
+__host__ __device__ constexpr int jm_line_role(int f, int dx, int dy) {       // 0:LL 1:L 2:R 3:RR, -1: not on the face's line
+    return f == JF_C0 ? ((dy == 0 && dx >= -2 && dx <= 1) ? dx + 2 : -1)
+         : f == JF_C1 ? ((dy == 0 && dx >= -1 && dx <= 2) ? dx + 1 : -1)
+         : f == JF_E0 ? ((dx == 0 && dy >= -2 && dy <= 1) ? dy + 2 : -1)
+         :              ((dx == 0 && dy >= -1 && dy <= 2) ? dy + 1 : -1);
+}
+__host__ __device__ constexpr int jm_dual_class(int f, int dx, int dy) {
+    // chi faces: D0/D1 = the two cells of the face's row, P = row above, M = row below (src/utils/mesh.cpp:44-53)
+    // eta faces: D0/D1 = the two cells of the face's column, P = column to the right, M = column to the left (:93-98)
+    const int a = (f == JF_C0 || f == JF_C1) ? dx - (f == JF_C1 ? 1 : 0) : dy - (f == JF_E1 ? 1 : 0);   // -1: D0 side, 0: D1 side
+    const int b = (f == JF_C0 || f == JF_C1) ? dy : dx;                                                  // 0: direct, +1: P, -1: M
+    if (a != -1 && a != 0) return JC_NONE;
+    return b == 0 ? (a == -1 ? JC_D0 : JC_D1) : (b == 1 ? JC_P : (b == -1 ? JC_M : JC_NONE));
+}
+
+// Static face geometry of the viscous dual cells (src/utils/mesh.cpp:54-82,99-126), evaluated ONCE per grid: the Green-Gauss
+// gradient and the face average are linear in the six cells of the dual cell, so everything the Jacobian needs from the
+// metrics is, per face, its normal and the weight (wx, wy) with which a cell of each class enters d/dx, d/dy:
+//   D0 / D1 (the face's own two cells), P / M (the two cells completing each vertex average).
+enum { JG_NX = 0, JG_NY, JG_XD0, JG_YD0, JG_XD1, JG_YD1, JG_XP, JG_YP, JG_XM, JG_YM, JG_N };
+
+struct JmParams {
+    View v; Gas g; Metrics m;
+    const double* q; double* J;
+    const double* wdist; const double* beta;
+    const double* gchi; const double* geta;      // [JG_N][plane]: chi face i at (row(j), col(i)), eta face at (row(face j), col(i))
+    double eps_chi, eps_eta;
+    int nstrips, nchunks, rpc;
+};
+
+template <bool VISC>
+__global__ void jac_geom_kernel(View v, Metrics m, double* __restrict__ gchi, double* __restrict__ geta) {
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= v.pitch || r >= v.rows) return;
+    const int i = c - IOFF, jl = r - JOFF;
+    const size_t o = v.at(r, c), pl = v.plane;
+    auto put = [&](double* G, const FaceGeom& fg) {
+        G[JG_NX*pl + o] = fg.nx; G[JG_NY*pl + o] = fg.ny;
+        if (VISC) {
+            const double iv = fg.ivol2, qx = 0.25*(fg.tx - fg.bx), qy = 0.25*(fg.ty - fg.by);
+            G[JG_XD0*pl + o] = (qx - fg.lx)*iv; G[JG_YD0*pl + o] = (qy - fg.ly)*iv;
+            G[JG_XD1*pl + o] = (qx + fg.rx)*iv; G[JG_YD1*pl + o] = (qy + fg.ry)*iv;
+            G[JG_XP*pl + o] = 0.25*fg.tx*iv; G[JG_YP*pl + o] = 0.25*fg.ty*iv;
+            G[JG_XM*pl + o] = -0.25*fg.bx*iv; G[JG_YM*pl + o] = -0.25*fg.by*iv;
+        }
+    };
+    FaceGeom fg;
+    if (i >= 0 && i <= v.nic && jl >= 0 && jl < v.njl) {               // chi face i of cell row jl (same clamped variants as the residual kernel)
+        fg.nx = m.ncx[o]; fg.ny = m.ncy[o];
+        if (VISC) {
+            const int ca = imax(i - 1, 0) + IOFF, cb = imin(i, v.nic - 1) + IOFF;
+            const int cR = imin(i + 1, v.ni - 1) + IOFF, cL = imax(i - 1, 0) + IOFF;
+            fg.tx = m.nex[v.at(r + 1, ca)] + m.nex[v.at(r + 1, cb)]; fg.ty = m.ney[v.at(r + 1, ca)] + m.ney[v.at(r + 1, cb)];
+            fg.bx = m.nex[v.at(r, ca)] + m.nex[v.at(r, cb)]; fg.by = m.ney[v.at(r, ca)] + m.ney[v.at(r, cb)];
+            fg.rx = fg.nx + m.ncx[v.at(r, cR)]; fg.ry = fg.ny + m.ncy[v.at(r, cR)];
+            fg.lx = fg.nx + m.ncx[v.at(r, cL)]; fg.ly = fg.ny + m.ncy[v.at(r, cL)];
+            fg.ivol2 = rcp_fast(m.vol[v.at(r, ca)] + m.vol[v.at(r, cb)]);
+        }
+        put(gchi, fg);
+    }
+    if (i >= 0 && i < v.nic && jl >= 0 && jl <= v.njl) {               // eta face with local face row jl
+        const int fj = v.j0 + jl;
+        fg.nx = m.nex[o]; fg.ny = m.ney[o];
+        if (VISC) {
+            const int a = imax(fj - 1, 0), b = imin(fj, v.njc - 1);
+            const int rA = a - v.j0 + JOFF, rB = b - v.j0 + JOFF;
+            const int rT = imin(fj + 1, v.nj - 1) - v.j0 + JOFF, rBo = imax(fj - 1, 0) - v.j0 + JOFF;
+            // generic roles: t* = plus side (right), b* = minus side (left), r* = D1 (top), l* = D0 (bottom)
+            fg.rx = fg.nx + m.nex[v.at(rT, c)]; fg.ry = fg.ny + m.ney[v.at(rT, c)];
+            fg.lx = fg.nx + m.nex[v.at(rBo, c)]; fg.ly = fg.ny + m.ney[v.at(rBo, c)];
+            fg.bx = m.ncx[v.at(rA, c)] + m.ncx[v.at(rB, c)]; fg.by = m.ncy[v.at(rA, c)] + m.ncy[v.at(rB, c)];
+            fg.tx = m.ncx[v.at(rA, c + 1)] + m.ncx[v.at(rB, c + 1)]; fg.ty = m.ncy[v.at(rA, c + 1)] + m.ncy[v.at(rB, c + 1)];
+            fg.ivol2 = rcp_fast(m.vol[v.at(rA, c)] + m.vol[v.at(rB, c)]);
+        }
+        put(geta, fg);
+    }
+}
+
+// which slots each warp assembles in phase B (-1 = none); balanced by contributing faces: slot 0 has four, edges three
+// viscous + two reconstruction lines, corners two, arms one
+__constant__ int c_jm_slots[JM_WARPS][4] = {{0, 5, 9, -1}, {1, 2, 10, 11}, {3, 4, 12, -1}, {6, 7, 8, -1}};
+
+template <int NV, int ORDER, int FLUX, bool VISC>
+__global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParams prm) {
+    using Cfg = JmCfg<NV, ORDER, VISC>;
+    constexpr bool SA = Cfg::SA;
+    constexpr int NWV = Cfg::NWV, NZV = Cfg::NZV;
+    constexpr int NS = ORDER == 2 ? 13 : 9;
+    extern __shared__ double smem[];
+    double* sW = smem;                               // [6 rows][NWV][JM_RC]
+    double* sZ = sW + Cfg::W_DBL;                    // [4 rows][NZV][JM_RC]
+    double* sC = sZ + Cfg::Z_DBL;                    // chi cores of the current row   [CORE][32]
+    double* sE = sC + Cfg::C_DBL;                    // eta cores, ring of two rows    [2][CORE][32]
+    double* sS = sE + 2*Cfg::C_DBL;                  // SA source sensitivities        [2][7][32]
+
+    const View& v = prm.v; const Gas& g = prm.g; const Metrics& m = prm.m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x % prm.nstrips, chunk = blockIdx.x / prm.nstrips;
+    const int i0 = strip*JM_CELLS;
+    const int ra = chunk*prm.rpc, rb = imin(ra + prm.rpc, v.njl);
+    const int i = i0 + lane;                         // own cell column / own chi face
+    const size_t pl = v.plane;
+    const int cc0 = lane + 2;                        // ring column of the own cell
+    const int ic = imin(i, v.nic - 1) + IOFF;        // plane column of the own cell (clamped for the lanes past the grid)
+
+    auto wrow = [&](int jl) { return sW + (((jl % 6) + 6) % 6)*NWV*JM_RC; };
+    auto zrow = [&](int jl) { return sZ + ((jl + 8) & 3)*NZV*JM_RC; };
+
+    // ---- ring maintenance -------------------------------------------------------------------------------------
+    // primitives of cell row jl, ring column cc, straight from the state planes (FluidModel::primvars, fluid.cpp:50-67)
+    auto convert_w = [&](int jl, int cc) {
+        const int c = imax(imin(i0 - 2 + cc + IOFF, v.pitch - 1), 0), r = imax(imin(jl + JOFF, v.rows - 1), 0);
+        const size_t o = v.at(r, c);
+        double rho, u, vv, p, T;
+        cons_to_prim<double>(g, __ldg(prm.q + o), __ldg(prm.q + pl + o), __ldg(prm.q + 2*pl + o), __ldg(prm.q + 3*pl + o), rho, u, vv, p, T);
+        double* W = wrow(jl);
+        W[JW_R*JM_RC + cc] = rho; W[JW_U*JM_RC + cc] = u; W[JW_V*JM_RC + cc] = vv; W[JW_P*JM_RC + cc] = p;
+        W[JW_RI*JM_RC + cc] = rcp_fast(rho);
+        W[JW_RN*JM_RC + cc] = SA ? __ldg(prm.q + 4*pl + o) : 0.0;
+    };
+    // T, mu, mu_t and the derivative factors of cell row jl (from ring W)
+    auto convert_z = [&](int jl, int cc) {
+        if (!VISC) return;
+        const double* W = wrow(jl); double* Z = zrow(jl);
+        const double ri = W[JW_RI*JM_RC + cc], T = W[JW_P*JM_RC + cc]*ri*g.iR;
+        const double cb = cbrt(T*g.iT_ref), mu = g.mu_ref*cb*cb;
+        const double dmudT = (2.0/3.0)*mu*rcp_fast(T);
+        Z[JZ_T*JM_RC + cc] = T; Z[JZ_MU*JM_RC + cc] = mu; Z[JZ_DMUDT*JM_RC + cc] = dmudT;
+        if (SA) {
+            const double rn = W[JW_RN*JM_RC + cc];
+            const double chi = rn*rcp_fast(mu), c3 = SA_CV1*SA_CV1*SA_CV1, x3 = chi*chi*chi, den = rcp_fast(x3 + c3);
+            const double fv1 = x3*den, dfv1 = 3.0*chi*chi*c3*den*den;
+            Z[JZ_MUT*JM_RC + cc] = rn*fv1;
+            Z[JZ_CMT*JM_RC + cc] = -chi*chi*dfv1*dmudT;
+            Z[JZ_DMUT4*JM_RC + cc] = fv1 + chi*dfv1;
+        }
+    };
+    auto convert_w_row = [&](int jl) {
+#pragma unroll 1
+        for (int cc = lane; cc < JM_RC; cc += 32) convert_w(jl, cc);
+    };
+    auto convert_z_row = [&](int jl) {
+#pragma unroll 1
+        for (int cc = lane; cc < JM_RC; cc += 32) convert_z(jl, cc);
+    };
+
+    // the CellD of the chain rule (jacobian_kernel.cuh) rebuilt from the rings; full = with the viscous / SA derivative rows
+    auto load_cell = [&](int jl, int cc, bool full, CellD<NV>& w) {
+        const double* W = wrow(jl);
+        w.r = W[JW_R*JM_RC + cc]; w.u = W[JW_U*JM_RC + cc]; w.v = W[JW_V*JM_RC + cc]; w.p = W[JW_P*JM_RC + cc]; w.ri = W[JW_RI*JM_RC + cc];
+        w.rn = W[JW_RN*JM_RC + cc]; w.nut = w.rn*w.ri;
+        const double ke = 0.5*(w.u*w.u + w.v*w.v), s = w.ri*g.iR;
+        w.dT[0] = (GM1*ke - w.p*w.ri)*s; w.dT[1] = -GM1*w.u*s; w.dT[2] = -GM1*w.v*s; w.dT[3] = GM1*s;
+        w.T = 0; w.mu = 0; w.mut = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { w.dmu[k] = 0.0; w.dmut[k] = 0.0; }
+        w.dmut[4] = 0.0;
+        if (VISC && full) {
+            const double* Z = zrow(jl);
+            w.T = Z[JZ_T*JM_RC + cc]; w.mu = Z[JZ_MU*JM_RC + cc];
+            const double dmudT = Z[JZ_DMUDT*JM_RC + cc];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w.dmu[k] = dmudT*w.dT[k];
+            if (SA) {
+                w.mut = Z[JZ_MUT*JM_RC + cc];
+                const double cmt = Z[JZ_CMT*JM_RC + cc];
+#pragma unroll
+                for (int k = 0; k < 4; k++) w.dmut[k] = cmt*w.dT[k];
+                w.dmut[4] = Z[JZ_DMUT4*JM_RC + cc];
+            }
+        }
+    };
+
+    // ---- phase A: one half of the core of one face -- ONE code path for all four warps (dir and half are warp-uniform
+    //      run-time values: four specialised copies starved the instruction cache, ncu no_instruction 7 cycles per issue) ----
+    //   dir  = 0: chi face i of cell row jA            -> sC          line cells (jA, i-2 .. i+1)
+    //   dir  = 1: eta face with local face row jA      -> sE[jA & 1]  line cells (jA-2 .. jA+1, i)
+    //   half = 0: stores the limiter derivatives, flux passes 0,1 (d/d ql), F0;  half = 1: flux passes 2,3 (d/d qr), viscous coefficients
+    auto face_core = [&](int dir, int half, int jA) {
+        const int di = dir ? 0 : 1, dj = dir ? 1 : 0;
+        const int rLL = dir ? jA - 2 : jA, cLL = dir ? cc0 : cc0 - 2;
+        bool Lint, Rint;
+        if (dir) { const int fj = v.j0 + jA; Lint = fj - 1 >= 0; Rint = fj <= v.njc - 1; }
+        else { Lint = i - 1 >= 0; Rint = i <= v.nic - 1; }
+        const double eps = dir ? prm.eps_eta : prm.eps_chi;
+        const double* G = (dir ? prm.geta + v.at(jA + JOFF, ic) : prm.gchi + v.at(jA + JOFF, imin(i, v.nic) + IOFF));
+        double* core = dir ? sE + (jA & 1)*Cfg::C_DBL + lane : sC + lane;
+        const double nx = __ldg(G + JG_NX*pl), ny = __ldg(G + JG_NY*pl);
+        double ql[4], qr[4];
+        {
+            const double* W0 = wrow(rLL); const double* W1 = wrow(rLL + dj); const double* W2 = wrow(rLL + 2*dj); const double* W3 = wrow(rLL + 3*dj);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                              // src/model/reconstruction.cpp:94-111,133-150 by 3-lane duals
+                const double wLL = W0[k*JM_RC + cLL], wL = W1[k*JM_RC + cLL + di], wR = W2[k*JM_RC + cLL + 2*di], wRR = W3[k*JM_RC + cLL + 3*di];
+                double d[6] = {0, 1, 0, 0, 1, 0};
+                ql[k] = wL; qr[k] = wR;
+                if (ORDER == 2) {
+                    typedef Dual<3> D3;
+                    D3 hi, lo, hi2, lo2;
+                    { D3 a(wLL), b(wL), c(wR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi, lo); }
+                    { D3 a(wL), b(wR), c(wRR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi2, lo2); }
+                    if (Lint) { ql[k] = hi.v; d[0] = hi.d[0]; d[1] = hi.d[1]; d[2] = hi.d[2]; }
+                    if (Rint) { qr[k] = lo2.v; d[3] = lo2.d[0]; d[4] = lo2.d[1]; d[5] = lo2.d[2]; }
+                    if (half == 0) {
+#pragma unroll
+                        for (int n = 0; n < 3; n++) { core[(Cfg::C_DL + k*3 + n)*32] = d[n]; core[(Cfg::C_DR + k*3 + n)*32] = d[3 + n]; }
+                    }
+                }
+            }
+        }
+        // dF/d(ql, qr): forward-mode passes of two lanes through the flux function the residual kernel runs
+        typedef Dual<2> D2;
+#pragma unroll 1
+        for (int pp = 0; pp < 2; pp++) {
+            const int s0 = (half*2 + pp)*2;                            // seeded inputs s0, s0 + 1 of (ql_0..3, qr_0..3)
+            D2 a[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { a[k] = D2(ql[k]); a[4 + k] = D2(qr[k]); }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { a[k].d[0] = (k == s0) ? 1.0 : 0.0; a[k].d[1] = (k == s0 + 1) ? 1.0 : 0.0; }
+            D2 F[4];
+            if (FLUX == SGPU_FLUX_ROE) roe_flux<D2>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
+            else ausm_flux<D2>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
+#pragma unroll
+            for (int r = 0; r < 4; r++) { core[(Cfg::C_FD + r*8 + s0)*32] = F[r].d[0]; core[(Cfg::C_FD + r*8 + s0 + 1)*32] = F[r].d[1]; }
+            if (s0 == 0) core[Cfg::C_F0*32] = F[0].v;
+        }
+        if (VISC && half == 1) {                                       // the face aggregates, linear in the six cells (mesh.cpp:10-131)
+            const int rD = rLL + dj, cD = cLL + di;                    // D0; D1 = D0 + (dj, di); P / M = one step across the line
+            const int pj = dir ? 0 : 1, pi = dir ? 1 : 0;
+            double sD0[7], sD1[7], sP[7], sM[7];
+#pragma unroll
+            for (int n = 0; n < 7; n++) { sP[n] = sM[n] = 0.0; }
+#pragma unroll
+            for (int n = 0; n < 6; n++) {
+                const int rr = rD + (n & 1)*dj + (n < 2 ? 0 : (n < 4 ? pj : -pj)), cc = cD + (n & 1)*di + (n < 2 ? 0 : (n < 4 ? pi : -pi));
+                const double* W = wrow(rr); const double* Z = zrow(rr);
+                const double rn = W[JW_RN*JM_RC + cc];
+                const double z[7] = {W[JW_U*JM_RC + cc], W[JW_V*JM_RC + cc], Z[JZ_T*JM_RC + cc], Z[JZ_MU*JM_RC + cc],
+                                     SA ? Z[JZ_MUT*JM_RC + cc] : 0.0, SA ? rn*W[JW_RI*JM_RC + cc] : 0.0, rn};
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    if (n == 0) sD0[k] = z[k]; else if (n == 1) sD1[k] = z[k]; else if (n < 4) sP[k] += z[k]; else sM[k] += z[k];
+                }
+            }
+            const double xD0 = __ldg(G + JG_XD0*pl), yD0 = __ldg(G + JG_YD0*pl), xD1 = __ldg(G + JG_XD1*pl), yD1 = __ldg(G + JG_YD1*pl);
+            const double xP = __ldg(G + JG_XP*pl), yP = __ldg(G + JG_YP*pl), xM = __ldg(G + JG_XM*pl), yM = __ldg(G + JG_YM*pl);
+            auto gx = [&](int k) { return xD0*sD0[k] + xD1*sD1[k] + xP*sP[k] + xM*sM[k]; };
+            auto gy = [&](int k) { return yD0*sD0[k] + yD1*sD1[k] + yP*sP[k] + yM*sM[k]; };
+            auto bar = [&](int k) { return 0.375*(sD0[k] + sD1[k]) + 0.0625*(sP[k] + sM[k]); };
+            const double ux = gx(0), uy = gy(0), vx = gx(1), vy = gy(1);
+            const double mub = bar(3), mutb = SA ? bar(4) : 0.0;
+            const double div = ux + vy;
+            core[(Cfg::C_V + JV_MU)*32] = mub + mutb;
+            core[(Cfg::C_V + JV_KK)*32] = SA ? (mub*g.cp_over_pr + mutb*g.cp_over_prt) : mub*g.cp_over_pr;
+            core[(Cfg::C_V + JV_UB)*32] = bar(0); core[(Cfg::C_V + JV_VB)*32] = bar(1);
+            core[(Cfg::C_V + JV_TXX)*32] = 2.0*ux - (2.0/3.0)*div; core[(Cfg::C_V + JV_TYY)*32] = 2.0*vy - (2.0/3.0)*div;   // tau / mu
+            core[(Cfg::C_V + JV_TXY)*32] = uy + vx;
+            core[(Cfg::C_V + JV_TX)*32] = gx(2); core[(Cfg::C_V + JV_TY)*32] = gy(2);
+            core[(Cfg::C_V + JV_GN)*32] = SA ? (gx(5)*nx + gy(5)*ny)*(1.0/SA_SIGMA) : 0.0;
+            core[(Cfg::C_V + JV_MUSA)*32] = SA ? (mub + bar(6))*(1.0/SA_SIGMA) : 0.0;
+        }
+    };
+
+    // ---- SA source sensitivities of cell (i, jl) -> sS[jl & 1]: dS/d(rho, nut, mu, om, dndx, dndy) and sign(dvdx - dudy) ----
+    // weight of the stencil cell (dx, dy) in the Green-Gauss gradient over the cell's own four faces with face values
+    // 3/8 (the two cells of the face) + 1/16 (the four cells completing its vertex averages)
+    struct Met8 { double cxl, cyl, cxr, cyr, exb, eyb, ext, eyt, Vi; };
+    auto load_met8 = [&](int jl, Met8& M) {
+        const int r = jl + JOFF;
+        const size_t o = v.at(r, ic);
+        M.cxl = __ldg(m.ncx + o); M.cyl = __ldg(m.ncy + o); M.cxr = __ldg(m.ncx + o + 1); M.cyr = __ldg(m.ncy + o + 1);
+        M.exb = __ldg(m.nex + o); M.eyb = __ldg(m.ney + o); M.ext = __ldg(m.nex + v.at(r + 1, ic)); M.eyt = __ldg(m.ney + v.at(r + 1, ic));
+        M.Vi = 1.0/__ldg(m.vol + o);
+    };
+    auto sa_w = [&](const Met8& M, int dx, int dy, double& wx, double& wy) {
+        const double wc = dy == 0 ? 0.375 : 0.0625, we = dx == 0 ? 0.375 : 0.0625;     // chi faces touch dx in {-1,0} / {0,1}; eta faces dy likewise
+        const double ax = wc*((dx >= 0 ? M.cxr : 0.0) - (dx <= 0 ? M.cxl : 0.0)) + we*((dy >= 0 ? M.ext : 0.0) - (dy <= 0 ? M.exb : 0.0));
+        const double ay = wc*((dx >= 0 ? M.cyr : 0.0) - (dx <= 0 ? M.cyl : 0.0)) + we*((dy >= 0 ? M.eyt : 0.0) - (dy <= 0 ? M.eyb : 0.0));
+        wx = ax*M.Vi; wy = ay*M.Vi;
+    };
+    auto sa_prep = [&](int jl) {
+        if (!SA) return;
+        Met8 M; load_met8(jl, M);
+        double dvdx = 0, dudy = 0, dndx = 0, dndy = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                double wx, wy; sa_w(M, dx, dy, wx, wy);
+                const double* W = wrow(jl + dy); const int cc = cc0 + dx;
+                const double uu = W[JW_U*JM_RC + cc], vv = W[JW_V*JM_RC + cc], nn = W[JW_RN*JM_RC + cc]*W[JW_RI*JM_RC + cc];
+                dvdx += wx*vv; dudy += wy*uu; dndx += wx*nn; dndy += wy*nn;
+            }
+        const double aa = dvdx - dudy;
+        const double* W = wrow(jl);
+        const double rho = W[JW_R*JM_RC + cc0], nut = W[JW_RN*JM_RC + cc0]*W[JW_RI*JM_RC + cc0];
+        const double mu = VISC ? zrow(jl)[JZ_MU*JM_RC + cc0] : g.mu_ref;
+        typedef Dual<6> D6;
+        D6 a_rho(rho), a_nut(nut), a_mu(mu), a_om(fabs(aa)), a_nx(dndx), a_ny(dndy);
+        a_rho.d[0] = 1; a_nut.d[1] = 1; a_mu.d[2] = 1; a_om.d[3] = 1; a_nx.d[4] = 1; a_ny.d[5] = 1;
+        const size_t o = v.at(jl + JOFF, ic);
+        const D6 S = sa_source<D6>(a_rho, a_nut, a_mu, a_om, a_nx, a_ny, __ldg(prm.wdist + o), __ldg(prm.beta + o));
+        double* out = sS + (jl & 1)*7*32 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; k++) out[k*32] = S.d[k];
+        out[6*32] = aa < 0.0 ? -1.0 : 1.0;
+    };
+
+    // ---- phase B: one stencil slot of the row cell (i, jl); s, and with it every branch below, is warp-uniform --------
+    const bool cell_ok = lane < JM_CELLS && i < v.nic;
+    auto assemble_slot = [&](int s, int jl, const Met8& M8) {
+        const int DX = c_slot_dx[s], DY = c_slot_dy[s];
+        const bool inner = DX >= -1 && DX <= 1 && DY >= -1 && DY <= 1, corner = DX != 0 && DY != 0;
+        const size_t o = v.at(jl + JOFF, ic);
+        double* Jp = prm.J + ((size_t)s*NV*NV)*pl + o;
+        if (!VISC && corner) {                                         // corners exist through the viscous stencil only
+            if (cell_ok) for (int e = 0; e < NV*NV; e++) __stcs(Jp + e*pl, 0.0);
+            return;
+        }
+        const double Vi = M8.Vi;
+        double cw[5][4], cu[4], cv[4], cT3 = 0.0, cmu[5], cmut[4], cnut4 = 0.0, ex0 = 0.0, ex4 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) cw[r][k] = 0.0;
+            cmu[r] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) { cu[r] = cv[r] = cmut[r] = 0.0; }
+        const double nut_s = wrow(jl + DY)[JW_RN*JM_RC + cc0 + DX]*wrow(jl + DY)[JW_RI*JM_RC + cc0 + DX], ri_s = wrow(jl + DY)[JW_RI*JM_RC + cc0 + DX];
+#pragma unroll 1
+        for (int f = 0; f < 4; f++) {
+            const int lr = jm_line_role(f, DX, DY), dc = VISC ? jm_dual_class(f, DX, DY) : JC_NONE;
+            if (lr < 0 && dc == JC_NONE) continue;
+            const double* core = (f < 2) ? sC + lane + f : sE + ((jl + f) & 1)*Cfg::C_DBL + lane;      // C0, C1 | E0 (face row jl), E1 (jl + 1)
+            const double sc = (f & 1) ? Vi : -Vi;
+            if (lr >= 0) {                                             // D = -F: reconstruction chain, line cells LL L | R RR
+                const int il = lr <= 2 ? lr : -1, ir = lr >= 1 ? lr - 1 : -1;      // which dl[k][.] / dr[k][.] belongs to this cell
+                double nut_up = 0.0;
+                if (SA) {
+                    const double F0 = core[Cfg::C_F0*32]; const bool upL = F0 >= 0.0;
+                    // the upwind cell of the face relative to the row cell: L = (-1,0) C0, (0,0) C1/E1, (0,-1) E0; R = L + one step
+                    const int st = upL ? 0 : 1;
+                    const int udx = (f < 2) ? (f == JF_C0 ? -1 : 0) + st : 0, udy = (f < 2) ? 0 : (f == JF_E0 ? -1 : 0) + st;
+                    const double* W = wrow(jl + udy);
+                    nut_up = W[JW_RN*JM_RC + cc0 + udx]*W[JW_RI*JM_RC + cc0 + udx];
+                    if ((lr == 1 && upL) || (lr == 2 && !upL)) {       // d(-F0 nut_up)/d q of the upwind cell: (+F0 nut/rho, ., ., ., -F0/rho)
+                        ex0 += sc*(F0*nut_s*ri_s);
+                        ex4 -= sc*(F0*ri_s);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    double dlk = (il == 1) ? 1.0 : 0.0, drk = (ir == 1) ? 1.0 : 0.0;
+                    if (ORDER == 2) {
+                        dlk = il >= 0 ? core[(Cfg::C_DL + k*3 + imax(il, 0))*32] : 0.0;
+                        drk = ir >= 0 ? core[(Cfg::C_DR + k*3 + imax(ir, 0))*32] : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const double c = core[(Cfg::C_FD + r*8 + k)*32]*dlk + core[(Cfg::C_FD + r*8 + 4 + k)*32]*drk;
+                        cw[r][k] -= sc*c;
+                        if (SA && r == 0) cw[4][k] -= sc*nut_up*c;
+                    }
+                }
+            }
+            if (dc != JC_NONE) {                                       // viscous flux: the dual cell's six cells (flux.cpp:12-48 through mesh.cpp:10-131)
+                const double* G = (f < 2) ? prm.gchi + v.at(jl + JOFF, imin(i + f, v.nic) + IOFF) : prm.geta + v.at(jl + (f - 2) + JOFF, ic);
+                const double nxf = __ldg(G + JG_NX*pl), nyf = __ldg(G + JG_NY*pl);
+                const double wx = sc*__ldg(G + (JG_XD0 + 2*dc)*pl), wy = sc*__ldg(G + (JG_YD0 + 2*dc)*pl), wb = sc*(dc <= JC_D1 ? 0.375 : 0.0625);
+                const double mu = core[(Cfg::C_V + JV_MU)*32], kk = core[(Cfg::C_V + JV_KK)*32];
+                const double ub = core[(Cfg::C_V + JV_UB)*32], vb = core[(Cfg::C_V + JV_VB)*32];
+                const double txx_h = core[(Cfg::C_V + JV_TXX)*32], tyy_h = core[(Cfg::C_V + JV_TYY)*32], txy_h = core[(Cfg::C_V + JV_TXY)*32];
+                const double Tx = core[(Cfg::C_V + JV_TX)*32], Ty = core[(Cfg::C_V + JV_TY)*32];
+                const double c43 = 4.0/3.0*mu, c23 = 2.0/3.0*mu;       // flux.cpp:36-45
+                const double txx = mu*txx_h, tyy = mu*tyy_h, txy = mu*txy_h;
+                // d G_r / d(ux, uy, vx, vy) . (wx, wy) etc., rows 1..3
+                cu[1] += (c43*nxf)*wx + (mu*nyf)*wy;       cv[1] += (mu*nyf)*wx + (-c23*nxf)*wy;
+                cu[2] += (-c23*nyf)*wx + (mu*nxf)*wy;      cv[2] += (mu*nxf)*wx + (c43*nyf)*wy;
+                const double g_uy3 = mu*(nxf*vb + nyf*ub);
+                cu[3] += (nxf*ub*c43 - nyf*vb*c23)*wx + g_uy3*wy + (nxf*txx + nyf*txy)*wb;
+                cv[3] += g_uy3*wx + (-nxf*ub*c23 + nyf*vb*c43)*wy + (nxf*txy + nyf*tyy)*wb;
+                cT3 += (kk*nxf)*wx + (kk*nyf)*wy;
+                const double gmu1 = txx_h*nxf + txy_h*nyf, gmu2 = txy_h*nxf + tyy_h*nyf;
+                const double gmu3 = nxf*(ub*txx_h + vb*txy_h) + nyf*(ub*txy_h + vb*tyy_h), gk3 = nxf*Tx + nyf*Ty;
+                cmu[1] += gmu1*wb; cmu[2] += gmu2*wb; cmu[3] += (gmu3 + gk3*g.cp_over_pr)*wb;
+                if (SA) {
+                    cmut[1] += gmu1*wb; cmut[2] += gmu2*wb; cmut[3] += (gmu3 + gk3*g.cp_over_prt)*wb;
+                    const double gn = core[(Cfg::C_V + JV_GN)*32], musa_s = core[(Cfg::C_V + JV_MUSA)*32];
+                    cmu[4] += gn*wb;                                   // G4 = (mub + rnb)/sigma (grad nut . n): d/d mu and d/d rn share gn wb
+                    cnut4 += musa_s*(wx*nxf + wy*nyf);
+                }
+            }
+        }
+        // SA source row (rhs[4] += S V then / V): weights of this cell in the cell-centred gradients
+        double s_cu = 0.0, s_cv = 0.0, s_cn = 0.0, s_rho = 0.0, s_mu = 0.0;
+        if (SA && inner) {
+            const double* Sd = sS + (jl & 1)*7*32 + lane;
+            double wx, wy; sa_w(M8, DX, DY, wx, wy);
+            const double sgn = Sd[6*32], S3 = Sd[3*32]*sgn;
+            s_cu = -S3*wy; s_cv = S3*wx; s_cn = Sd[4*32]*wx + Sd[5*32]*wy;
+            if (DX == 0 && DY == 0) { s_rho = Sd[0]; s_mu = Sd[2*32]; s_cn += Sd[1*32]; }
+        }
+        CellD<NV> cs;
+        load_cell(jl + DY, cc0 + DX, inner, cs);
+#pragma unroll
+        for (int r = 0; r < NV; r++) {
+            double out[NV];
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
+            chain_W<NV>(cs, cw[r], out);
+            if (VISC && r >= 1) {                                      // all-zero coefficients outside the 3x3 block
+                if (r < 4) chain_Z<NV>(cs, cu[r], cv[r], r == 3 ? cT3 : 0.0, cmu[r], SA ? cmut[r] : 0.0, 0.0, 0.0, out);
+                else chain_Z<NV>(cs, s_cu, s_cv, 0.0, cmu[4] + s_mu, 0.0, cnut4 + s_cn, cmu[4], out);
+            }
+            if (SA && r == 4) { out[0] += ex0 + s_rho; out[4] += ex4; }
+            if (cell_ok) {
+#pragma unroll
+                for (int c2 = 0; c2 < NV; c2++) __stcs(Jp + (size_t)(r*NV + c2)*pl, out[c2]);
+            }
+        }
+    };
+
+    // ---- prologue: ring rows ra-2 .. ra+2 (W), ra-1 .. ra+1 (Z), the eta core of face ra, SA prep of row ra ----
+#pragma unroll 1
+    for (int jl = ra - 2 + warp; jl <= ra + 2; jl += JM_WARPS) convert_w_row(jl);
+    __syncthreads();
+#pragma unroll 1
+    for (int jl = ra - 1 + warp; jl <= ra + 1; jl += JM_WARPS) convert_z_row(jl);
+    __syncthreads();
+    if (warp >= 2) face_core(1, warp & 1, ra);
+    else if (warp == 0) sa_prep(ra);
+
+#pragma unroll 1
+    for (int jl = ra; jl < rb; jl++) {
+        // ---- phase A: cores of chi face (i, jl) [warps 0, 1] and eta face (i, jl+1) [warps 2, 3]
+        face_core(warp >> 1, warp & 1, jl + (warp >> 1));
+        __syncthreads();
+        // ---- phase B: assembly, next ring rows, SA prep of the next row
+        Met8 M8; load_met8(jl, M8);
+#pragma unroll 1
+        for (int n = 0; n < 4; n++) {
+            const int s = c_jm_slots[warp][n];
+            if (s >= 0 && s < NS) assemble_slot(s, jl, M8);
+        }
+        if (jl + 1 < rb) {
+            if (warp == 0) convert_w_row(jl + 3);
+            else if (warp == 3) { convert_z_row(jl + 2); sa_prep(jl + 1); }
+        }
+        __syncthreads();
+    }
+}
+
+// Fold ghost slots into the interior cells they are functions of (boundary band only): the chain d ghost / d interior of
+// the boundary condition that wrote the ghost cell last (src/model/bc.cpp), corners first, then arms, then edges.
+template <int NV>
+__global__ void __launch_bounds__(128) jac_fold_kernel(View v, Gas g, Metrics m, GhostTable gt, const double* __restrict__ q, double* __restrict__ J,
+                                                       int nslots, int* __restrict__ err) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jl = blockIdx.y;
+    if (i >= v.nic) return;
+    const int gj = v.j0 + jl;
+    if (!((i < 2) || (i > v.nic - 3) || (gj < 2) || (gj > v.njc - 3))) return;
+    const size_t o = v.at(jl + JOFF, i + IOFF);
+    unsigned touched = (1u << nslots) - 1u;
+    const int ip0 = i + 1, jp0 = gj + 1;                           // padded coordinates of the row cell
+    const int order_list[12] = {5, 6, 7, 8, 9, 10, 11, 12, 1, 2, 3, 4};
+    // three sweeps: a fold may deposit into a ghost slot that was already visited (chains of two BC maps)
+#pragma unroll 1
+    for (int n3 = 0; n3 < 36; n3++) {
+        const int s = order_list[n3 % 12];
+        if (s >= nslots || !(touched & (1u << s))) continue;
+        int ip = ip0 + c_slot_dx[s], jp = jp0 + c_slot_dy[s];
+        if (!gt.is_ghost(ip, jp)) continue;
+        if (ip < 0 || ip > gt.nic + 1 || jp < 0 || jp > gt.njc + 1) continue;   // beyond the ghost layer: never read
+        gt.resolve(ip, jp);
+        if (!gt.is_ghost(ip, jp)) continue;                        // copy-type ghost: keeps its slot, column remapped at export
+        const GhostDesc& gd = gt.at(ip, jp);
+        double B[NV*NV];
+        double* p = J + ((size_t)s*NV*NV)*v.plane + o;
+#pragma unroll
+        for (int e = 0; e < NV*NV; e++) { B[e] = p[e*v.plane]; p[e*v.plane] = 0.0; }
+        if (gd.type == SGPU_BC_FREESTREAM || gd.type < 0) continue;   // constants: no dependency
+        const int aip = gd.a_ip, ajp = gd.a_jp, bip = gd.b_ip, bjp = gd.b_jp;
+        const bool has_b = gd.type != SGPU_BC_OUTFLOW;
+        double qa[NV], qb[NV];
+        auto ldq = [&](int pip, int pjp, double* dst) {
+            const int rr = pjp - 1 - v.j0 + JOFF, cc2 = pip - 1 + IOFF;
+#pragma unroll
+            for (int k = 0; k < NV; k++) dst[k] = q[k*v.plane + v.at(rr, cc2)];
+        };
+        ldq(aip, ajp, qa);
+        if (has_b) ldq(bip, bjp, qb); else {
+#pragma unroll
+            for (int k = 0; k < NV; k++) qb[k] = qa[k];
+        }
+        double nx = 0.0, ny = 0.0;
+        if (gd.type == SGPU_BC_SLIPWALL) {
+            const int rf = (gd.face == SGPU_FACE_BOTTOM ? 0 : v.njc) - v.j0 + JOFF, cf = ip - 1 + IOFF;
+            nx = m.nex[v.at(rf, cf)]; ny = m.ney[v.at(rf, cf)];
+        }
+        double Ma[NV*NV], Mb[NV*NV];
+        bc_ghost_jacobian<NV>(g, gd, nx, ny, qa, qb, Ma, Mb);
+#pragma unroll 1
+        for (int t = 0; t < (has_b ? 2 : 1); t++) {
+            int tip = t ? bip : aip, tjp = t ? bjp : ajp;
+            gt.resolve(tip, tjp);
+            int ts = -1;
+            for (int s2 = 0; s2 < nslots; s2++) {
+                int sip = ip0 + c_slot_dx[s2], sjp = jp0 + c_slot_dy[s2];
+                gt.resolve(sip, sjp);
+                if (sip == tip && sjp == tjp) { ts = s2; break; }
+            }
+            if (ts < 0) { atomicAdd(err, 1); continue; }
+            const double* M = t ? Mb : Ma;
+            double* pt = J + ((size_t)ts*NV*NV)*v.plane + o;
+#pragma unroll
+            for (int rr = 0; rr < NV; rr++)
+#pragma unroll
+                for (int cc2 = 0; cc2 < NV; cc2++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NV; k++) sacc += B[rr*NV + k]*M[k*NV + cc2];
+                    pt[(rr*NV + cc2)*v.plane] += sacc;
+                }
+        }
+    }
+}
+
+} // namespace sg

@@ -8,12 +8,14 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/structured_gpu.h"
 #include "common.cuh"
 #include "aux_kernels.cuh"
 #include "residual_kernel.cuh"
 #include "jacobian_kernel.cuh"
+#include "jacobian_march.cuh"
 #include "linsolve_kernels.cuh"
 
 using namespace sg;
@@ -55,6 +57,7 @@ struct sgpu_ctx {
     cudaEvent_t pipe_up[64] = {}, pipe_cmp[64] = {}, pipe_start = nullptr;
     double* pipe_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pipe_stage_cap = 0;
     double* jac_scratch = nullptr; size_t jac_scratch_cap = 0; bool jac_two_stage = false;
+    double* jgeo = nullptr; bool jgeo_valid = false;   // static face-geometry weight planes of the Jacobian build (jac_geom_kernel)
     void* ghost_tab = nullptr;
     int* jac_err = nullptr;
     bool have_grid = false, have_dt = false;
@@ -193,6 +196,7 @@ int sgpu_destroy(sgpu_ctx* c) {
     jac_free(c->jac);
     lin_free(c->lin);
     if (c->jac_scratch) cudaFree(c->jac_scratch);
+    if (c->jgeo) cudaFree(c->jgeo);
     for (int k = 0; k < 4; k++) if (c->pipe_stage[k]) cudaFree(c->pipe_stage[k]);
     if (c->pipe_init) {
         for (int k = 0; k < 3; k++) cudaStreamDestroy(c->pipe_stream[k]);
@@ -247,7 +251,7 @@ int sgpu_set_grid_window(sgpu_ctx* c, const double* xv, const double* yv, int jv
                                                                             (double*)m.nex, (double*)m.ney, (double*)m.vol);
     CKL(c); c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
-    c->have_grid = true;
+    c->have_grid = true; c->jgeo_valid = false;
     return SGPU_OK;
 }
 int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
