@@ -37,7 +37,7 @@ template <int NV, int ORDER, bool VISC> struct JmCfg {
     static constexpr int C_FD = 0, C_F0 = 32, C_DL = 33, C_DR = C_DL + (ORDER == 2 ? 12 : 0), C_V = C_DR + (ORDER == 2 ? 12 : 0);
     static constexpr int CORE = C_V + (VISC ? 11 : 0);
     static constexpr int W_DBL = 6*NWV*JM_RC, Z_DBL = 4*NZV*JM_RC, C_DBL = CORE*32, S_DBL = SA ? 2*7*32 : 0;
-    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(W_DBL + Z_DBL + 3*C_DBL + S_DBL);
+    static constexpr size_t smem_bytes = sizeof(double)*(size_t)(W_DBL + Z_DBL + 3*C_DBL + S_DBL + 2);
 };
 enum { JW_R = 0, JW_U, JW_V, JW_P, JW_RI, JW_RN };
 enum { JZ_T = 0, JZ_MU, JZ_DMUDT, JZ_MUT, JZ_CMT, JZ_DMUT4 };
@@ -66,6 +66,20 @@ __host__ __device__ constexpr int jm_dual_class(int f, int dx, int dy) {
 // metrics is, per face, its normal and the weight (wx, wy) with which a cell of each class enters d/dx, d/dy:
 //   D0 / D1 (the face's own two cells), P / M (the two cells completing each vertex average).
 enum { JG_NX = 0, JG_NY, JG_XD0, JG_YD0, JG_XD1, JG_YD1, JG_XP, JG_YP, JG_XM, JG_YM, JG_N };
+
+// packed roles of slot s: bits 0-2 dx+2, 3-5 dy+2, then per face f six bits: line role + 1, dual class + 1
+__host__ __device__ constexpr unsigned jm_desc(int s) {
+    const int dxs[13] = {0, -1, 1, 0, 0, -1, 1, -1, 1, -2, 2, 0, 0}, dys[13] = {0, 0, 0, -1, 1, -1, -1, 1, 1, 0, 0, -2, 2};   // = c_slot_dx / c_slot_dy
+    if (s < 0 || s > 12) return 0u;
+    unsigned d = (unsigned)(dxs[s] + 2) | ((unsigned)(dys[s] + 2) << 3);
+    for (int f = 0; f < 4; f++)
+        d |= ((unsigned)(jm_line_role(f, dxs[s], dys[s]) + 1) | ((unsigned)(jm_dual_class(f, dxs[s], dys[s]) + 1) << 3)) << (6 + 6*f);
+    return d;
+}
+// phase B task order (most expensive first; the warps pull tasks from a shared counter): slot 0, the four edges, the SA
+// preparation of the next row (13), the corners, the ring rows entering (14: W, 15: Z), the arms
+constexpr unsigned long long JM_TASKS = 0xCBA9FE8765D43210ull;      // nibble n = task n
+constexpr int JM_NTASK = 16;
 
 struct JmParams {
     View v; Gas g; Metrics m;
@@ -125,10 +139,6 @@ __global__ void jac_geom_kernel(View v, Metrics m, double* __restrict__ gchi, do
     }
 }
 
-// which slots each warp assembles in phase B (-1 = none); balanced by contributing faces: slot 0 has four, edges three
-// viscous + two reconstruction lines, corners two, arms one
-__constant__ int c_jm_slots[JM_WARPS][4] = {{0, 5, 9, -1}, {1, 2, 10, 11}, {3, 4, 12, -1}, {6, 7, 8, -1}};
-
 template <int NV, int ORDER, int FLUX, bool VISC>
 __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParams prm) {
     using Cfg = JmCfg<NV, ORDER, VISC>;
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
     double* sC = sZ + Cfg::Z_DBL;                    // chi cores of the current row   [CORE][32]
     double* sE = sC + Cfg::C_DBL;                    // eta cores, ring of two rows    [2][CORE][32]
     double* sS = sE + 2*Cfg::C_DBL;                  // SA source sensitivities        [2][7][32]
+    int* sTask = (int*)(sS + Cfg::S_DBL);            // phase B task counter
 
     const View& v = prm.v; const Gas& g = prm.g; const Metrics& m = prm.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,70 +255,87 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
                 double d[6] = {0, 1, 0, 0, 1, 0};
                 ql[k] = wL; qr[k] = wR;
                 if (ORDER == 2) {
-                    typedef Dual<3> D3;
-                    D3 hi, lo, hi2, lo2;
-                    { D3 a(wLL), b(wL), c(wR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi, lo); }
-                    { D3 a(wL), b(wR), c(wRR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi2, lo2); }
-                    if (Lint) { ql[k] = hi.v; d[0] = hi.d[0]; d[1] = hi.d[1]; d[2] = hi.d[2]; }
-                    if (Rint) { qr[k] = lo2.v; d[3] = lo2.d[0]; d[4] = lo2.d[1]; d[5] = lo2.d[2]; }
-                    if (half == 0) {
+                    if (half == 0) {                                   // values + derivatives (stored); the other half needs the values only
+                        typedef Dual<3> D3;
+                        D3 hi, lo, hi2, lo2;
+                        { D3 a(wLL), b(wL), c(wR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi, lo); }
+                        { D3 a(wL), b(wR), c(wRR); a.d[0] = 1; b.d[1] = 1; c.d[2] = 1; muscl_cell<D3>(a, b, c, eps, hi2, lo2); }
+                        if (Lint) { ql[k] = hi.v; d[0] = hi.d[0]; d[1] = hi.d[1]; d[2] = hi.d[2]; }
+                        if (Rint) { qr[k] = lo2.v; d[3] = lo2.d[0]; d[4] = lo2.d[1]; d[5] = lo2.d[2]; }
 #pragma unroll
                         for (int n = 0; n < 3; n++) { core[(Cfg::C_DL + k*3 + n)*32] = d[n]; core[(Cfg::C_DR + k*3 + n)*32] = d[3 + n]; }
+                    } else {
+                        double hi, lo, hi2, lo2;
+                        muscl_cell<double>(wLL, wL, wR, eps, hi, lo); muscl_cell<double>(wL, wR, wRR, eps, hi2, lo2);
+                        if (Lint) ql[k] = hi;
+                        if (Rint) qr[k] = lo2;
                     }
                 }
             }
         }
         // dF/d(ql, qr): forward-mode passes of two lanes through the flux function the residual kernel runs
-        typedef Dual<2> D2;
-#pragma unroll 1
-        for (int pp = 0; pp < 2; pp++) {
-            const int s0 = (half*2 + pp)*2;                            // seeded inputs s0, s0 + 1 of (ql_0..3, qr_0..3)
-            D2 a[8];
+        // (one pass of four lanes per half: 696 instructions against 2 x 568 for two passes of two lanes)
+        {
+            typedef Dual<4> D4;
+            const double sl = half ? 0.0 : 1.0, sr = half ? 1.0 : 0.0; // seeds: d/d ql_0..3 (half 0) or d/d qr_0..3 (half 1)
+            D4 a[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { a[k] = D2(ql[k]); a[4 + k] = D2(qr[k]); }
+            for (int k = 0; k < 4; k++) {
+                a[k] = D4(ql[k]); a[4 + k] = D4(qr[k]);
+                a[k].d[k] = sl; a[4 + k].d[k] = sr;
+            }
+            D4 F[4];
+            if (FLUX == SGPU_FLUX_ROE) roe_flux<D4>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
+            else ausm_flux<D4>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { a[k].d[0] = (k == s0) ? 1.0 : 0.0; a[k].d[1] = (k == s0 + 1) ? 1.0 : 0.0; }
-            D2 F[4];
-            if (FLUX == SGPU_FLUX_ROE) roe_flux<D2>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
-            else ausm_flux<D2>(nx, ny, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], F);
+            for (int r = 0; r < 4; r++)
 #pragma unroll
-            for (int r = 0; r < 4; r++) { core[(Cfg::C_FD + r*8 + s0)*32] = F[r].d[0]; core[(Cfg::C_FD + r*8 + s0 + 1)*32] = F[r].d[1]; }
-            if (s0 == 0) core[Cfg::C_F0*32] = F[0].v;
+                for (int l = 0; l < 4; l++) core[(Cfg::C_FD + r*8 + half*4 + l)*32] = F[r].d[l];
+            if (half == 0) core[Cfg::C_F0*32] = F[0].v;
         }
-        if (VISC && half == 1) {                                       // the face aggregates, linear in the six cells (mesh.cpp:10-131)
+        if (VISC) {                                                    // the face aggregates, linear in the six cells (mesh.cpp:10-131)
+            // half 0: the velocity part (stress / mu, face velocities); half 1: temperature, viscosities, nu~ (balances the phase)
             const int rD = rLL + dj, cD = cLL + di;                    // D0; D1 = D0 + (dj, di); P / M = one step across the line
             const int pj = dir ? 0 : 1, pi = dir ? 1 : 0;
-            double sD0[7], sD1[7], sP[7], sM[7];
+            const double xD0 = __ldg(G + JG_XD0*pl), yD0 = __ldg(G + JG_YD0*pl), xD1 = __ldg(G + JG_XD1*pl), yD1 = __ldg(G + JG_YD1*pl);
+            const double xP = __ldg(G + JG_XP*pl), yP = __ldg(G + JG_YP*pl), xM = __ldg(G + JG_XM*pl), yM = __ldg(G + JG_YM*pl);
+            constexpr int NZ = 5;
+            double sD0[NZ], sD1[NZ], sP[NZ], sM[NZ];
 #pragma unroll
-            for (int n = 0; n < 7; n++) { sP[n] = sM[n] = 0.0; }
+            for (int n = 0; n < NZ; n++) { sP[n] = sM[n] = 0.0; }
 #pragma unroll
             for (int n = 0; n < 6; n++) {
                 const int rr = rD + (n & 1)*dj + (n < 2 ? 0 : (n < 4 ? pj : -pj)), cc = cD + (n & 1)*di + (n < 2 ? 0 : (n < 4 ? pi : -pi));
                 const double* W = wrow(rr); const double* Z = zrow(rr);
-                const double rn = W[JW_RN*JM_RC + cc];
-                const double z[7] = {W[JW_U*JM_RC + cc], W[JW_V*JM_RC + cc], Z[JZ_T*JM_RC + cc], Z[JZ_MU*JM_RC + cc],
-                                     SA ? Z[JZ_MUT*JM_RC + cc] : 0.0, SA ? rn*W[JW_RI*JM_RC + cc] : 0.0, rn};
+                double z[NZ];
+                if (half == 0) { z[0] = W[JW_U*JM_RC + cc]; z[1] = W[JW_V*JM_RC + cc]; z[2] = z[3] = z[4] = 0.0; }
+                else {
+                    const double rn = W[JW_RN*JM_RC + cc];
+                    z[0] = Z[JZ_T*JM_RC + cc]; z[1] = Z[JZ_MU*JM_RC + cc]; z[2] = SA ? Z[JZ_MUT*JM_RC + cc] : 0.0;
+                    z[3] = SA ? rn*W[JW_RI*JM_RC + cc] : 0.0; z[4] = rn;
+                }
 #pragma unroll
-                for (int k = 0; k < 7; k++) {
+                for (int k = 0; k < NZ; k++) {
                     if (n == 0) sD0[k] = z[k]; else if (n == 1) sD1[k] = z[k]; else if (n < 4) sP[k] += z[k]; else sM[k] += z[k];
                 }
             }
-            const double xD0 = __ldg(G + JG_XD0*pl), yD0 = __ldg(G + JG_YD0*pl), xD1 = __ldg(G + JG_XD1*pl), yD1 = __ldg(G + JG_YD1*pl);
-            const double xP = __ldg(G + JG_XP*pl), yP = __ldg(G + JG_YP*pl), xM = __ldg(G + JG_XM*pl), yM = __ldg(G + JG_YM*pl);
             auto gx = [&](int k) { return xD0*sD0[k] + xD1*sD1[k] + xP*sP[k] + xM*sM[k]; };
             auto gy = [&](int k) { return yD0*sD0[k] + yD1*sD1[k] + yP*sP[k] + yM*sM[k]; };
             auto bar = [&](int k) { return 0.375*(sD0[k] + sD1[k]) + 0.0625*(sP[k] + sM[k]); };
-            const double ux = gx(0), uy = gy(0), vx = gx(1), vy = gy(1);
-            const double mub = bar(3), mutb = SA ? bar(4) : 0.0;
-            const double div = ux + vy;
-            core[(Cfg::C_V + JV_MU)*32] = mub + mutb;
-            core[(Cfg::C_V + JV_KK)*32] = SA ? (mub*g.cp_over_pr + mutb*g.cp_over_prt) : mub*g.cp_over_pr;
-            core[(Cfg::C_V + JV_UB)*32] = bar(0); core[(Cfg::C_V + JV_VB)*32] = bar(1);
-            core[(Cfg::C_V + JV_TXX)*32] = 2.0*ux - (2.0/3.0)*div; core[(Cfg::C_V + JV_TYY)*32] = 2.0*vy - (2.0/3.0)*div;   // tau / mu
-            core[(Cfg::C_V + JV_TXY)*32] = uy + vx;
-            core[(Cfg::C_V + JV_TX)*32] = gx(2); core[(Cfg::C_V + JV_TY)*32] = gy(2);
-            core[(Cfg::C_V + JV_GN)*32] = SA ? (gx(5)*nx + gy(5)*ny)*(1.0/SA_SIGMA) : 0.0;
-            core[(Cfg::C_V + JV_MUSA)*32] = SA ? (mub + bar(6))*(1.0/SA_SIGMA) : 0.0;
+            if (half == 0) {
+                const double ux = gx(0), uy = gy(0), vx = gx(1), vy = gy(1);
+                const double div = ux + vy;
+                core[(Cfg::C_V + JV_UB)*32] = bar(0); core[(Cfg::C_V + JV_VB)*32] = bar(1);
+                core[(Cfg::C_V + JV_TXX)*32] = 2.0*ux - (2.0/3.0)*div; core[(Cfg::C_V + JV_TYY)*32] = 2.0*vy - (2.0/3.0)*div;   // tau / mu
+                core[(Cfg::C_V + JV_TXY)*32] = uy + vx;
+            } else {
+                const double mub = bar(1), mutb = SA ? bar(2) : 0.0;
+                core[(Cfg::C_V + JV_MU)*32] = mub + mutb;
+                core[(Cfg::C_V + JV_KK)*32] = SA ? (mub*g.cp_over_pr + mutb*g.cp_over_prt) : mub*g.cp_over_pr;
+                core[(Cfg::C_V + JV_TX)*32] = gx(0); core[(Cfg::C_V + JV_TY)*32] = gy(0);
+                core[(Cfg::C_V + JV_GN)*32] = SA ? (gx(3)*nx + gy(3)*ny)*(1.0/SA_SIGMA) : 0.0;
+                core[(Cfg::C_V + JV_MUSA)*32] = SA ? (mub + bar(4))*(1.0/SA_SIGMA) : 0.0;
+            }
         }
     };
 
@@ -358,8 +386,10 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
 
     // ---- phase B: one stencil slot of the row cell (i, jl); s, and with it every branch below, is warp-uniform --------
     const bool cell_ok = lane < JM_CELLS && i < v.nic;
+    const unsigned my_desc = jm_desc(lane);          // lane s holds the role descriptor of slot s: fetched by shuffle, no table load
     auto assemble_slot = [&](int s, int jl, const Met8& M8) {
-        const int DX = c_slot_dx[s], DY = c_slot_dy[s];
+        const unsigned desc = __shfl_sync(0xffffffffu, my_desc, s);
+        const int DX = (int)(desc & 7u) - 2, DY = (int)((desc >> 3) & 7u) - 2;
         const bool inner = DX >= -1 && DX <= 1 && DY >= -1 && DY <= 1, corner = DX != 0 && DY != 0;
         const size_t o = v.at(jl + JOFF, ic);
         double* Jp = prm.J + ((size_t)s*NV*NV)*pl + o;
@@ -378,10 +408,24 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
 #pragma unroll
         for (int r = 0; r < 4; r++) { cu[r] = cv[r] = cmut[r] = 0.0; }
         const double nut_s = wrow(jl + DY)[JW_RN*JM_RC + cc0 + DX]*wrow(jl + DY)[JW_RI*JM_RC + cc0 + DX], ri_s = wrow(jl + DY)[JW_RI*JM_RC + cc0 + DX];
+        // geometry of the (up to four) viscous contributions first: 16 independent loads in flight instead of an L2 round trip
+        // at the head of every face (the shared-memory carve-out leaves these planes almost no L1)
+        // (the face loop stays ROLLED: unrolled, the kernel outgrows the instruction cache -- 7.5 k instructions, ncu
+        //  no_instruction 2.8 cycles per issue against 0.3 at 5.7 k; the geometry of face f + 1 is requested while face f is
+        //  processed instead, the shared-memory carve-out leaves these planes almost no L1)
+        double n_nx = 0.0, n_ny = 0.0, n_wx = 0.0, n_wy = 0.0;
+        auto geom_req = [&](int f) {
+            const int dcf = imax((int)((desc >> (9 + 6*f)) & 7u) - 1, 0);
+            const double* G = (f < 2) ? prm.gchi + v.at(jl + JOFF, imin(i + f, v.nic) + IOFF) : prm.geta + v.at(jl + (f - 2) + JOFF, ic);
+            n_nx = __ldg(G + JG_NX*pl); n_ny = __ldg(G + JG_NY*pl);
+            n_wx = __ldg(G + (JG_XD0 + 2*dcf)*pl); n_wy = __ldg(G + (JG_YD0 + 2*dcf)*pl);
+        };
+        if (VISC && inner) geom_req(0);
 #pragma unroll 1
         for (int f = 0; f < 4; f++) {
-            const int lr = jm_line_role(f, DX, DY), dc = VISC ? jm_dual_class(f, DX, DY) : JC_NONE;
-            if (lr < 0 && dc == JC_NONE) continue;
+            const int lr = (int)((desc >> (6 + 6*f)) & 7u) - 1, dc = (VISC && inner) ? (int)((desc >> (9 + 6*f)) & 7u) - 1 : JC_NONE;
+            const double g_nx = n_nx, g_ny = n_ny, g_wx = n_wx, g_wy = n_wy;
+            if (VISC && inner && f < 3) geom_req(f + 1);
             const double* core = (f < 2) ? sC + lane + f : sE + ((jl + f) & 1)*Cfg::C_DBL + lane;      // C0, C1 | E0 (face row jl), E1 (jl + 1)
             const double sc = (f & 1) ? Vi : -Vi;
             if (lr >= 0) {                                             // D = -F: reconstruction chain, line cells LL L | R RR
@@ -399,12 +443,13 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
                         ex4 -= sc*(F0*ri_s);
                     }
                 }
+                const double* dlp = core + (Cfg::C_DL + imax(il, 0))*32; const double* drp = core + (Cfg::C_DR + imax(ir, 0))*32;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     double dlk = (il == 1) ? 1.0 : 0.0, drk = (ir == 1) ? 1.0 : 0.0;
                     if (ORDER == 2) {
-                        dlk = il >= 0 ? core[(Cfg::C_DL + k*3 + imax(il, 0))*32] : 0.0;
-                        drk = ir >= 0 ? core[(Cfg::C_DR + k*3 + imax(ir, 0))*32] : 0.0;
+                        dlk = il >= 0 ? dlp[k*3*32] : 0.0;
+                        drk = ir >= 0 ? drp[k*3*32] : 0.0;
                     }
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
@@ -415,9 +460,8 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
                 }
             }
             if (dc != JC_NONE) {                                       // viscous flux: the dual cell's six cells (flux.cpp:12-48 through mesh.cpp:10-131)
-                const double* G = (f < 2) ? prm.gchi + v.at(jl + JOFF, imin(i + f, v.nic) + IOFF) : prm.geta + v.at(jl + (f - 2) + JOFF, ic);
-                const double nxf = __ldg(G + JG_NX*pl), nyf = __ldg(G + JG_NY*pl);
-                const double wx = sc*__ldg(G + (JG_XD0 + 2*dc)*pl), wy = sc*__ldg(G + (JG_YD0 + 2*dc)*pl), wb = sc*(dc <= JC_D1 ? 0.375 : 0.0625);
+                const double nxf = g_nx, nyf = g_ny;
+                const double wx = sc*g_wx, wy = sc*g_wy, wb = sc*(dc <= JC_D1 ? 0.375 : 0.0625);
                 const double mu = core[(Cfg::C_V + JV_MU)*32], kk = core[(Cfg::C_V + JV_KK)*32];
                 const double ub = core[(Cfg::C_V + JV_UB)*32], vb = core[(Cfg::C_V + JV_VB)*32];
                 const double txx_h = core[(Cfg::C_V + JV_TXX)*32], tyy_h = core[(Cfg::C_V + JV_TYY)*32], txy_h = core[(Cfg::C_V + JV_TXY)*32];
@@ -459,7 +503,7 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
 #pragma unroll
             for (int c2 = 0; c2 < NV; c2++) out[c2] = 0.0;
             chain_W<NV>(cs, cw[r], out);
-            if (VISC && r >= 1) {                                      // all-zero coefficients outside the 3x3 block
+            if (VISC && r >= 1 && inner) {                             // all-zero coefficients outside the 3x3 block
                 if (r < 4) chain_Z<NV>(cs, cu[r], cv[r], r == 3 ? cT3 : 0.0, cmu[r], SA ? cmut[r] : 0.0, 0.0, 0.0, out);
                 else chain_Z<NV>(cs, s_cu, s_cv, 0.0, cmu[4] + s_mu, 0.0, cnut4 + s_cn, cmu[4], out);
             }
@@ -471,34 +515,67 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
         }
     };
 
-    // ---- prologue: ring rows ra-2 .. ra+2 (W), ra-1 .. ra+1 (Z), the eta core of face ra, SA prep of row ra ----
+    // ---- ring rows ra-2 .. ra+2 (W), ra-1 .. ra+1 (Z) ----
 #pragma unroll 1
     for (int jl = ra - 2 + warp; jl <= ra + 2; jl += JM_WARPS) convert_w_row(jl);
     __syncthreads();
 #pragma unroll 1
     for (int jl = ra - 1 + warp; jl <= ra + 1; jl += JM_WARPS) convert_z_row(jl);
     __syncthreads();
-    if (warp >= 2) face_core(1, warp & 1, ra);
-    else if (warp == 0) sa_prep(ra);
 
+    // The loop starts one row early: iteration ra - 1 only produces what row ra inherits from "the row below" -- the eta
+    // core of face ra and the SA sensitivities of row ra -- through the SAME call sites as every other row (one inlined
+    // copy of each routine: smaller code, and chunk seams cannot change a bit of the result).
+#ifdef JM_TIMING
+    long long tA = 0, tB = 0, tW = 0, t0, t1;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
+#define JM_T(acc) { asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) :: "memory"); acc += t1 - t0; t0 = t1; }
+#else
+#define JM_T(acc)
+#endif
 #pragma unroll 1
-    for (int jl = ra; jl < rb; jl++) {
+    for (int jl = ra - 1; jl < rb; jl++) {
+        const bool lead = jl < ra;
         // ---- phase A: cores of chi face (i, jl) [warps 0, 1] and eta face (i, jl+1) [warps 2, 3]
-        face_core(warp >> 1, warp & 1, jl + (warp >> 1));
+        if (threadIdx.x == 0) *sTask = 0;               // nobody pulls tasks between the barrier behind us and the one ahead
+        if (!lead || warp >= 2) face_core(warp >> 1, warp & 1, jl + (warp >> 1));
+        JM_T(tA)
         __syncthreads();
-        // ---- phase B: assembly, next ring rows, SA prep of the next row
-        Met8 M8; load_met8(jl, M8);
-#pragma unroll 1
-        for (int n = 0; n < 4; n++) {
-            const int s = c_jm_slots[warp][n];
-            if (s >= 0 && s < NS) assemble_slot(s, jl, M8);
-        }
-        if (jl + 1 < rb) {
-            if (warp == 0) convert_w_row(jl + 3);
-            else if (warp == 3) { convert_z_row(jl + 2); sa_prep(jl + 1); }
-        }
+#ifdef JM_TIMING
+        if (((volatile double*)sW)[lane] == 1.2345e300) tW = 0;    // a barrier-protected read: the clock below is read after the RELEASE
+#endif
+        JM_T(tW)
+        // ---- phase B: the 13 slots, the ring rows entering and the SA preparation of the next row are TASKS pulled from a
+        //      shared counter, most expensive first -- the warps finish within one cheap task of each other whatever the
+        //      template configuration
+        if (!lead) {
+            Met8 M8; load_met8(jl, M8);
+            const bool more = jl + 1 < rb;
+            while (true) {
+                int n = 0;
+                if (lane == 0) n = atomicAdd(sTask, 1);
+                n = __shfl_sync(0xffffffffu, n, 0);
+                if (n >= JM_NTASK) break;
+                const int task = (int)((JM_TASKS >> (4*n)) & 15ull);
+                if (task < 13) { if (task < NS) assemble_slot(task, jl, M8); }
+                else if (more) {
+                    if (task == 13) sa_prep(jl + 1);
+                    else if (task == 14) convert_w_row(jl + 3);
+                    else convert_z_row(jl + 2);
+                }
+            }
+        } else if (warp == 3) sa_prep(jl + 1);
+        JM_T(tB)
         __syncthreads();
+#ifdef JM_TIMING
+        if (((volatile double*)sW)[lane] == 1.2345e300) tW = 0;
+#endif
+        JM_T(tW)
     }
+#ifdef JM_TIMING
+    if (lane == 0 && blockIdx.x % 997 == 5) printf("cta %d warp %d: phase A %lld  phase B %lld  barrier wait %lld cycles over %d rows\n", blockIdx.x, warp, tA, tB, tW, rb - ra);
+#endif
+#undef JM_T
 }
 
 // Fold ghost slots into the interior cells they are functions of (boundary band only): the chain d ghost / d interior of

@@ -1,4 +1,4 @@
-"""usage: python tools/line_stalls.py <ncu --page source --csv export of residual_kernel<5,2,0,1>>
+"""usage: python tools/line_stalls.py <ncu --page source --csv export> [mangled kernel name substring, default residual_kernel<5,2,0,1>]
 Aggregates warp-stall samples by CUDA source line: the SASS order of the profile is matched with `nvdisasm -g` of the
 in-tree library (same build), whose `//## File ..., line N` markers give each instruction its line."""
 import collections
@@ -14,6 +14,9 @@ KERNEL = "_ZN2sg15residual_kernelILi5ELi2ELi0ELb1EEEvNS_9ResParamsE"
 
 
 def line_table():
+    global KERNEL
+    if len(sys.argv) > 2:
+        KERNEL = sys.argv[2]
     with tempfile.TemporaryDirectory() as wd:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "structured_b200", "libstructured_gpu.so")], cwd=wd, check=True, stdout=subprocess.DEVNULL)
         cubin = [f for f in os.listdir(wd) if f.endswith(".cubin")][0]
@@ -46,12 +49,15 @@ def main():
         tot += n
         agg[seq[k]]["n"] += n
         agg[seq[k]]["inst"] += 1
+        agg[seq[k]]["exec"] += int(r[idx["Instructions Executed"]])
         for h in hdr:
             if h.startswith("stall_") and "Not Issued" not in h:
                 agg[seq[k]][h[6:]] += int(r[idx[h]])
-    print("total samples", tot)
-    for key, c in sorted(agg.items(), key=lambda kv: -kv[1]["n"])[:45]:
-        print(key, "n", c["n"], round(100 * c["n"] / tot, 1), "inst", c["inst"], {k: v for k, v in c.items() if k not in ("n", "inst") and v > 0.08 * c["n"]})
+    texec = sum(c["exec"] for c in agg.values())
+    print("total samples", tot, "warp instructions executed", texec)
+    for key, c in sorted(agg.items(), key=lambda kv: -kv[1]["n"])[:int(os.environ.get("TOP", "45"))]:
+        print(key, "n", c["n"], round(100 * c["n"] / tot, 1), "inst", c["inst"], "exec%", round(100 * c["exec"] / max(texec, 1), 1),
+              {k: v for k, v in c.items() if k not in ("n", "inst", "exec") and v > 0.08 * c["n"]})
 
 
 if __name__ == "__main__":
