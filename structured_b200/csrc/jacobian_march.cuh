@@ -25,7 +25,10 @@
 namespace sg {
 
 constexpr int JM_CELLS = 31;            // cells per strip; lane 31 only owns the chi face that closes the strip
-constexpr int JM_WARPS = 4;
+#ifndef JM_NWARPS
+#define JM_NWARPS 4
+#endif
+constexpr int JM_WARPS = JM_NWARPS;     // 4 face-core warps; 5 = one more that prepares the rings / SA sensitivities during phase A (measured slower: 128 registers, 33.9 vs 24.5 ms)
 constexpr int JM_RC = 36;               // ring columns: cells i0-2 .. i0+33
 
 template <int V> struct IC { static constexpr int value = V; };   // compile-time int passed through generic lambdas
@@ -67,19 +70,25 @@ __host__ __device__ constexpr int jm_dual_class(int f, int dx, int dy) {
 //   D0 / D1 (the face's own two cells), P / M (the two cells completing each vertex average).
 enum { JG_NX = 0, JG_NY, JG_XD0, JG_YD0, JG_XD1, JG_YD1, JG_XP, JG_YP, JG_XM, JG_YM, JG_N };
 
-// packed roles of slot s: bits 0-2 dx+2, 3-5 dy+2, then per face f six bits: line role + 1, dual class + 1
-__host__ __device__ constexpr unsigned jm_desc(int s) {
+// packed roles of slot s: bits 0-2 dx+2, 3-5 dy+2, 6-8 number of contributing faces, then one byte per CONTRIBUTING face from
+// bit 16: face id (2 bits), line role + 1 (3 bits), dual class + 1 (3 bits)
+__host__ __device__ constexpr unsigned long long jm_desc(int s, bool visc) {
     const int dxs[13] = {0, -1, 1, 0, 0, -1, 1, -1, 1, -2, 2, 0, 0}, dys[13] = {0, 0, 0, -1, 1, -1, -1, 1, 1, 0, 0, -2, 2};   // = c_slot_dx / c_slot_dy
-    if (s < 0 || s > 12) return 0u;
-    unsigned d = (unsigned)(dxs[s] + 2) | ((unsigned)(dys[s] + 2) << 3);
-    for (int f = 0; f < 4; f++)
-        d |= ((unsigned)(jm_line_role(f, dxs[s], dys[s]) + 1) | ((unsigned)(jm_dual_class(f, dxs[s], dys[s]) + 1) << 3)) << (6 + 6*f);
-    return d;
+    if (s < 0 || s > 12) return 0ull;
+    unsigned long long d = (unsigned long long)(dxs[s] + 2) | ((unsigned long long)(dys[s] + 2) << 3);
+    int n = 0;
+    for (int f = 0; f < 4; f++) {
+        const int lr = jm_line_role(f, dxs[s], dys[s]), dc = visc ? jm_dual_class(f, dxs[s], dys[s]) : JC_NONE;
+        if (lr < 0 && dc == JC_NONE) continue;
+        d |= ((unsigned long long)f | ((unsigned long long)(lr + 1) << 2) | ((unsigned long long)(dc + 1) << 5)) << (16 + 8*n);
+        n++;
+    }
+    return d | ((unsigned long long)n << 6);
 }
 // phase B task order (most expensive first; the warps pull tasks from a shared counter): slot 0, the four edges, the SA
 // preparation of the next row (13), the corners, the ring rows entering (14: W, 15: Z), the arms
-constexpr unsigned long long JM_TASKS = 0xCBA9FE8765D43210ull;      // nibble n = task n
-constexpr int JM_NTASK = 16;
+constexpr unsigned long long JM_TASKS = JM_NWARPS > 4 ? 0x000CBA9876543210ull : 0xCBA9FE8765D43210ull;      // nibble n = task n
+constexpr int JM_NTASK = JM_NWARPS > 4 ? 13 : 16;                  // with a fifth warp tasks 13..15 are its phase-A work
 
 struct JmParams {
     View v; Gas g; Metrics m;
@@ -209,13 +218,13 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
         const double* W = wrow(jl);
         w.r = W[JW_R*JM_RC + cc]; w.u = W[JW_U*JM_RC + cc]; w.v = W[JW_V*JM_RC + cc]; w.p = W[JW_P*JM_RC + cc]; w.ri = W[JW_RI*JM_RC + cc];
         w.rn = W[JW_RN*JM_RC + cc]; w.nut = w.rn*w.ri;
-        const double ke = 0.5*(w.u*w.u + w.v*w.v), s = w.ri*g.iR;
-        w.dT[0] = (GM1*ke - w.p*w.ri)*s; w.dT[1] = -GM1*w.u*s; w.dT[2] = -GM1*w.v*s; w.dT[3] = GM1*s;
         w.T = 0; w.mu = 0; w.mut = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { w.dmu[k] = 0.0; w.dmut[k] = 0.0; }
+        for (int k = 0; k < 4; k++) { w.dT[k] = 0.0; w.dmu[k] = 0.0; w.dmut[k] = 0.0; }
         w.dmut[4] = 0.0;
-        if (VISC && full) {
+        if (VISC && full) {                                        // (the arms only go through chain_W: u, v, 1/rho)
+            const double ke = 0.5*(w.u*w.u + w.v*w.v), s = w.ri*g.iR;
+            w.dT[0] = (GM1*ke - w.p*w.ri)*s; w.dT[1] = -GM1*w.u*s; w.dT[2] = -GM1*w.v*s; w.dT[3] = GM1*s;
             const double* Z = zrow(jl);
             w.T = Z[JZ_T*JM_RC + cc]; w.mu = Z[JZ_MU*JM_RC + cc];
             const double dmudT = Z[JZ_DMUDT*JM_RC + cc];
@@ -386,10 +395,10 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
 
     // ---- phase B: one stencil slot of the row cell (i, jl); s, and with it every branch below, is warp-uniform --------
     const bool cell_ok = lane < JM_CELLS && i < v.nic;
-    const unsigned my_desc = jm_desc(lane);          // lane s holds the role descriptor of slot s: fetched by shuffle, no table load
+    const unsigned long long my_desc = jm_desc(lane, VISC);   // lane s holds the role descriptor of slot s: fetched by shuffle, no table load
     auto assemble_slot = [&](int s, int jl, const Met8& M8) {
-        const unsigned desc = __shfl_sync(0xffffffffu, my_desc, s);
-        const int DX = (int)(desc & 7u) - 2, DY = (int)((desc >> 3) & 7u) - 2;
+        const unsigned long long desc = __shfl_sync(0xffffffffu, my_desc, s);
+        const int DX = (int)(desc & 7ull) - 2, DY = (int)((desc >> 3) & 7ull) - 2, nface = (int)((desc >> 6) & 7ull);
         const bool inner = DX >= -1 && DX <= 1 && DY >= -1 && DY <= 1, corner = DX != 0 && DY != 0;
         const size_t o = v.at(jl + JOFF, ic);
         double* Jp = prm.J + ((size_t)s*NV*NV)*pl + o;
@@ -411,21 +420,25 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
         // geometry of the (up to four) viscous contributions first: 16 independent loads in flight instead of an L2 round trip
         // at the head of every face (the shared-memory carve-out leaves these planes almost no L1)
         // (the face loop stays ROLLED: unrolled, the kernel outgrows the instruction cache -- 7.5 k instructions, ncu
-        //  no_instruction 2.8 cycles per issue against 0.3 at 5.7 k; the geometry of face f + 1 is requested while face f is
-        //  processed instead, the shared-memory carve-out leaves these planes almost no L1)
+        //  no_instruction 2.8 cycles per issue against 0.3 at 5.7 k; it runs over the CONTRIBUTING faces only, and the geometry
+        //  of the next one is requested while the current one is processed: the shared-memory carve-out leaves these planes
+        //  almost no L1)
         double n_nx = 0.0, n_ny = 0.0, n_wx = 0.0, n_wy = 0.0;
-        auto geom_req = [&](int f) {
-            const int dcf = imax((int)((desc >> (9 + 6*f)) & 7u) - 1, 0);
+        auto geom_req = [&](unsigned ent) {
+            const int f = (int)(ent & 3u), dcf = (int)((ent >> 5) & 7u) - 1;
+            if (dcf < 0) return;
             const double* G = (f < 2) ? prm.gchi + v.at(jl + JOFF, imin(i + f, v.nic) + IOFF) : prm.geta + v.at(jl + (f - 2) + JOFF, ic);
             n_nx = __ldg(G + JG_NX*pl); n_ny = __ldg(G + JG_NY*pl);
             n_wx = __ldg(G + (JG_XD0 + 2*dcf)*pl); n_wy = __ldg(G + (JG_YD0 + 2*dcf)*pl);
         };
-        if (VISC && inner) geom_req(0);
+        unsigned ents = (unsigned)(desc >> 16);
+        if (VISC) geom_req(ents & 255u);
 #pragma unroll 1
-        for (int f = 0; f < 4; f++) {
-            const int lr = (int)((desc >> (6 + 6*f)) & 7u) - 1, dc = (VISC && inner) ? (int)((desc >> (9 + 6*f)) & 7u) - 1 : JC_NONE;
+        for (int e = 0; e < nface; e++) {
+            const unsigned ent = ents & 255u; ents >>= 8;
+            const int f = (int)(ent & 3u), lr = (int)((ent >> 2) & 7u) - 1, dc = (int)((ent >> 5) & 7u) - 1;
             const double g_nx = n_nx, g_ny = n_ny, g_wx = n_wx, g_wy = n_wy;
-            if (VISC && inner && f < 3) geom_req(f + 1);
+            if (VISC && e + 1 < nface) geom_req(ents & 255u);
             const double* core = (f < 2) ? sC + lane + f : sE + ((jl + f) & 1)*Cfg::C_DBL + lane;      // C0, C1 | E0 (face row jl), E1 (jl + 1)
             const double sc = (f & 1) ? Vi : -Vi;
             if (lr >= 0) {                                             // D = -F: reconstruction chain, line cells LL L | R RR
@@ -538,7 +551,11 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
         const bool lead = jl < ra;
         // ---- phase A: cores of chi face (i, jl) [warps 0, 1] and eta face (i, jl+1) [warps 2, 3]
         if (threadIdx.x == 0) *sTask = 0;               // nobody pulls tasks between the barrier behind us and the one ahead
-        if (!lead || warp >= 2) face_core(warp >> 1, warp & 1, jl + (warp >> 1));
+        if (warp < 4) { if (!lead || warp >= 2) face_core(warp >> 1, warp & 1, jl + (warp >> 1)); }
+        else if (!lead) {                               // fifth warp: SA sensitivities of THIS row, ring rows of the next rows
+            sa_prep(jl);
+            if (jl + 1 < rb) { convert_w_row(jl + 3); convert_z_row(jl + 2); }
+        }
         JM_T(tA)
         __syncthreads();
 #ifdef JM_TIMING
@@ -564,7 +581,7 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
                     else convert_z_row(jl + 2);
                 }
             }
-        } else if (warp == 3) sa_prep(jl + 1);
+        } else if (warp == 3 && JM_WARPS == 4) sa_prep(jl + 1);
         JM_T(tB)
         __syncthreads();
 #ifdef JM_TIMING
