@@ -95,6 +95,10 @@ int sgpu_set_grid(sgpu_ctx* ctx, const double* xv, const double* yv);
  * slab's rows plus its two ghost rows on each interior side. */
 int sgpu_set_grid_window(sgpu_ctx* ctx, const double* xv, const double* yv, int jv_first, int jv_count);
 int sgpu_set_field_window(sgpu_ctx* ctx, const char* name, const double* field, int j_first, int j_count);
+/* Large grids: the vertices straight from a BINARY file -- "SGRIDF64", int32 ni, int32 nj, x[nj][ni],
+ * y[nj][ni] float64, the order of Mesh::plot3d_loader (src/utils/mesh.cpp:146-169) without the ASCII parse.  Only the
+ * window of rows this slab needs is read; a file row is a row of the device vertex planes (no transpose). */
+int sgpu_set_grid_file(sgpu_ctx* ctx, const char* path);
 /* SA extension inputs, GLOBAL [nic][njc]: name = "wall_distance" | "beta" (no reference counterpart) */
 int sgpu_set_field(sgpu_ctx* ctx, const char* name, const double* field);
 int sgpu_get_field(sgpu_ctx* ctx, const char* name, double* field);   /* GLOBAL [nic][njc]; owned rows written */
@@ -249,13 +253,22 @@ int sgpu_implicit_step(sgpu_ctx* ctx, double cfl, double under_relaxation, sgpu_
 /* Building blocks on DEVICE vectors for a slab-partitioned Krylov solve (one process per GPU; the iteration itself is
  * host logic over torch.distributed, structured_b200/slab.py: dot products are all-reduced, the two ghost rows of the
  * operand are exchanged before every product).  A vector = nv state planes of this slab, sgpu_vec_size doubles, zero
- * outside the owned cells except for halo rows filled by sgpu_vec_halo_unpack.  SGPU_MAT_LHS and SGPU_MAT_J only. */
+ * outside the owned cells except for halo rows filled by sgpu_vec_halo_unpack. */
 int sgpu_vec_size(const sgpu_ctx* ctx, long long* n);
 int sgpu_vec_from_rhs(sgpu_ctx* ctx, double* vec_dev);                                  /* what set_rhs receives */
 int sgpu_vec_add_to_state(sgpu_ctx* ctx, int which, const double* vec_dev, double omega);  /* q += omega*x, ls_eigen.cpp:66-70 */
 int sgpu_vec_halo_pack(sgpu_ctx* ctx, const double* vec_dev, int side, double* buf_dev);   /* layout of sgpu_halo_pack */
 int sgpu_vec_halo_unpack(sgpu_ctx* ctx, double* vec_dev, int side, const double* buf_dev);
 int sgpu_op_apply(sgpu_ctx* ctx, int matrix, const double* x_dev, double* y_dev);       /* y = A x on the owned rows */
+/* Transposed matrices (SGPU_MAT_JT, SGPU_MAT_LHS_T) on a slab: sgpu_op_apply needs NO operand halo, but leaves in the two
+ * ghost rows of y what this slab's rows contribute to the neighbour's boundary cells.  pack_ghost copies those rows out
+ * (layout of sgpu_halo_pack) and clears them; after the transport the receiver ADDS the buffer to its two boundary rows
+ * on that side: the one extra ghost-row exchange of two block rows of SURVEY.md section 8(e). */
+int sgpu_vec_halo_pack_ghost(sgpu_ctx* ctx, double* vec_dev, int side, double* buf_dev);
+int sgpu_vec_halo_add(sgpu_ctx* ctx, double* vec_dev, int side, const double* buf_dev);
+/* device vector <-> GLOBAL host array [nic][njc][nv] (owned rows) */
+int sgpu_vec_from_host(sgpu_ctx* ctx, const double* host, double* vec_dev);
+int sgpu_vec_to_host(sgpu_ctx* ctx, const double* vec_dev, double* host);
 int sgpu_precond_setup(sgpu_ctx* ctx, int matrix, int precond);                         /* slab-local factors */
 int sgpu_precond_apply(sgpu_ctx* ctx, int matrix, int precond, const double* r_dev, double* z_dev);
 

@@ -28,6 +28,30 @@ static void gpu_check(int rc, sgpu_ctx* ctx, const char* what) {
     std::abort();
 }
 
+// ---- SA extension through the drop-in -----------------------------------------------------------------------------
+// The reference's Solution is laminar (ntrans = 0 hard-coded, src/solver/solution.cpp:9): its arrays hold four variables
+// per cell.  An OPTIONAL `[turbulence]` table in the .inp file (stock files have none and behave exactly as before) turns
+// the Spalart-Allmaras extension on:
+//     [turbulence]
+//     ntrans = 1
+//     wall_distance = "compute"      # or the name of a file of nic*njc raw doubles, [i][j]
+//     beta_file = "beta.bin"         # optional correction field beta(x), nic*njc raw doubles, default 1
+// The five-variable state then lives on the device and in `g_q5` (host, [nic][njc][5]); Solution::q receives the four
+// mean-flow variables before IOManager::write, and the complete state is written next to the reference's files as
+// `<label>.sa.out` (raw doubles, the layout of the reference's `.out` restart with nv = 5).
+struct TurbulenceCfg { int ntrans = 0; std::string wall_distance = "compute", beta_file; };
+static TurbulenceCfg g_turb;
+static std::vector<double> g_q5;
+
+static bool read_raw(const std::string& fn, std::vector<double>& a, size_t n) {
+    FILE* f = fopen(fn.c_str(), "rb");
+    if (!f) return false;
+    a.resize(n);
+    const size_t got = fread(a.data(), sizeof(double), n, f);
+    fclose(f);
+    return got == n;
+}
+
 // builds the context from what Mesh/Config/BoundaryContainer hold (src/model/bc.cpp:470-488, src/utils/config.cpp:32-87)
 template <class Tx, class Tad>
 static sgpu_ctx* make_ctx(std::shared_ptr<Mesh<Tx, Tad>> mesh, std::shared_ptr<Config<Tx>> cfg) {
@@ -48,8 +72,14 @@ static sgpu_ctx* make_ctx(std::shared_ptr<Mesh<Tx, Tad>> mesh, std::shared_ptr<C
         e.T = b->template get_qualified_as<double>("T").value_or(0.0);
         bcs.push_back(e);
     }
+    g_turb.ntrans = (int)toml->template get_qualified_as<int64_t>("turbulence.ntrans").value_or(0);
+    g_turb.wall_distance = toml->template get_qualified_as<std::string>("turbulence.wall_distance").value_or("compute");
+    g_turb.beta_file = toml->template get_qualified_as<std::string>("turbulence.beta_file").value_or("");
+#if defined(STRUCTURED_GPU_IMPLICIT) && !defined(STRUCTURED_GPU_DEVICE_SOLVE)
+    if (g_turb.ntrans) { spdlog::get("console")->critical("[turbulence] needs the device-resident binaries: LinearSolverEigen is sized for the reference's four variables"); std::abort(); }
+#endif
     sgpu_desc d{};
-    d.ni = (int)mesh->ni; d.nj = (int)mesh->nj; d.ntrans = (int)mesh->solution->ntrans;
+    d.ni = (int)mesh->ni; d.nj = (int)mesh->nj; d.ntrans = g_turb.ntrans ? g_turb.ntrans : (int)mesh->solution->ntrans;
     d.order = (int)cfg->solver->order; d.lhs_order = (int)cfg->solver->lhs_order;
     d.flux = cfg->solver->flux == "roe" ? SGPU_FLUX_ROE : SGPU_FLUX_AUSM;
     d.rho_inf = cfg->freestream->rho_inf; d.u_inf = cfg->freestream->u_inf; d.v_inf = cfg->freestream->v_inf;
@@ -59,8 +89,34 @@ static sgpu_ctx* make_ctx(std::shared_ptr<Mesh<Tx, Tad>> mesh, std::shared_ptr<C
     sgpu_ctx* ctx = nullptr;
     if (sgpu_create(&d, &ctx)) { spdlog::get("console")->critical("sgpu_create: {}", sgpu_last_error(nullptr)); std::abort(); }
     gpu_check(sgpu_set_grid(ctx, mesh->xv.data(), mesh->yv.data()), ctx, "sgpu_set_grid");
-    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q, mesh->solution->q.data()), ctx, "sgpu_set_state");
-    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q_TMP, mesh->solution->q_tmp.data()), ctx, "sgpu_set_state");
+    if (!g_turb.ntrans) {
+        gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q, mesh->solution->q.data()), ctx, "sgpu_set_state");
+        gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q_TMP, mesh->solution->q_tmp.data()), ctx, "sgpu_set_state");
+        return ctx;
+    }
+    const size_t nc = (size_t)mesh->nic*mesh->njc;
+    std::vector<double> field;
+    if (g_turb.wall_distance == "compute") gpu_check(sgpu_wall_distance_from_bcs(ctx, mesh->xv.data(), mesh->yv.data()), ctx, "sgpu_wall_distance_from_bcs");
+    else {
+        if (!read_raw(g_turb.wall_distance, field, nc)) { spdlog::get("console")->critical("turbulence.wall_distance: cannot read {} doubles from {}", nc, g_turb.wall_distance); std::abort(); }
+        gpu_check(sgpu_set_field(ctx, "wall_distance", field.data()), ctx, "sgpu_set_field");
+    }
+    if (!g_turb.beta_file.empty()) {
+        if (!read_raw(g_turb.beta_file, field, nc)) { spdlog::get("console")->critical("turbulence.beta_file: cannot read {} doubles from {}", nc, g_turb.beta_file); std::abort(); }
+        gpu_check(sgpu_set_field(ctx, "beta", field.data()), ctx, "sgpu_set_field");
+    }
+    // state: the reference's initial / restarted mean flow + rho nu~ = 3 mu_inf (the freestream value of the SA ghost rule),
+    // or the complete five-variable state of an earlier run when io.restart is set and <label>.sa.out exists
+    g_q5.resize(nc*5);
+    if (!(cfg->io->restart && read_raw(cfg->io->label + ".sa.out", g_q5, nc*5))) {
+        const double* q4 = mesh->solution->q.data();
+        for (size_t c = 0; c < nc; c++) {
+            for (int k = 0; k < 4; k++) g_q5[5*c + k] = q4[4*c + k];
+            g_q5[5*c + 4] = 3.0*cfg->freestream->mu_inf;
+        }
+    }
+    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q, g_q5.data()), ctx, "sgpu_set_state");
+    gpu_check(sgpu_set_state(ctx, SGPU_STATE_Q_TMP, g_q5.data()), ctx, "sgpu_set_state");
     return ctx;
 }
 
@@ -83,7 +139,7 @@ template <class Tx, class Tad>
 bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, Tx t) {
     static sgpu_ctx* ctx = make_ctx<Tx, Tad>(mesh, config);        // one context per Mesh (main adds exactly one, src/main.cpp:40)
     auto solution = mesh->solution;
-    const size_t nv = solution->nq + solution->ntrans;
+    const size_t nv = solution->nq + (g_turb.ntrans ? g_turb.ntrans : solution->ntrans);
     double l2sq[8] = {0}, l2norm[8] = {0};
     // steps that end in IOManager::write (src/solver/solver.cpp:136-141,192-194) keep the wall rows of their last residual evaluation
     const bool will_write = counter > config->solver->iteration_max || counter % config->io->fileout_frequency == 0;
@@ -141,7 +197,16 @@ bool Solver<Tx, Tad>::step(std::shared_ptr<Mesh<Tx,Tad>> mesh, size_t counter, T
     // rows grad_u_eta[i][0], grad_v_eta[i][0] of EulerEquation's work arrays as the LAST calc_residual of this step left them
     // (tracked on the device for the steps that write, see below)
     auto sync_host = [&]() {
-        gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state");
+        if (!g_turb.ntrans) gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, solution->q.data()), ctx, "sgpu_get_state");
+        else {                                                      // four mean-flow variables for the reference's writers + the full state
+            gpu_check(sgpu_get_state(ctx, SGPU_STATE_Q, g_q5.data()), ctx, "sgpu_get_state");
+            const size_t nc = (size_t)mesh->nic*mesh->njc;
+            double* q4 = solution->q.data();
+            for (size_t c = 0; c < nc; c++) for (int k = 0; k < 4; k++) q4[4*c + k] = g_q5[5*c + k];
+            FILE* f = fopen((label + ".sa.out").c_str(), "wb");
+            if (f) { fwrite(g_q5.data(), sizeof(double), g_q5.size(), f); fclose(f); }
+            logger->info("SA: |rhs(rho nu~)| = {:.3e}, full state written to {}.sa.out", l2norm[4], label);
+        }
         const size_t nic = mesh->nic;
         std::vector<double> gu(2*nic), gv(2*nic);
         gpu_check(sgpu_wall_data(ctx, SGPU_STATE_LAST_RESIDUAL, SGPU_STATE_Q, gu.data(), gv.data(), nullptr, nullptr), ctx, "sgpu_wall_data");

@@ -21,13 +21,14 @@ _U = ctypes.POINTER(ctypes.c_uint)
 
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_set_stream", "sgpu_synchronize", "sgpu_dims",
-    "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_field", "sgpu_compute_wall_distance",
+    "sgpu_set_grid", "sgpu_set_grid_window", "sgpu_set_grid_file", "sgpu_set_field", "sgpu_set_field_window", "sgpu_get_field", "sgpu_compute_wall_distance",
     "sgpu_wall_distance_from_bcs", "sgpu_get_metrics", "sgpu_set_state", "sgpu_set_state_window", "sgpu_get_state", "sgpu_copy_state",
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_coo_rows", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
     "sgpu_wall_data", "sgpu_track_wall", "sgpu_surface", "sgpu_surface_gradient",
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
-    "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_op_apply",
+    "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_vec_halo_pack_ghost", "sgpu_vec_halo_add",
+    "sgpu_vec_from_host", "sgpu_vec_to_host", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_pack_ghost", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
@@ -179,6 +180,10 @@ class GpuEulerEquation:
     # ---- static inputs
     def set_field(self, name: str, field: np.ndarray):
         self._ck(self.L.sgpu_set_field(self.h, name.encode(), _dp(np.ascontiguousarray(field, dtype=np.float64))))
+
+    def set_grid_file(self, path: str):
+        """vertices from a binary file (cases.write_grid_bin); on a slab only its window of rows is read"""
+        self._ck(self.L.sgpu_set_grid_file(self.h, os.fsencode(path)))
 
     def get_field(self, name: str) -> np.ndarray:
         out = np.zeros((self.nic, self.njc))
@@ -370,6 +375,22 @@ class GpuEulerEquation:
 
     def vec_halo_unpack(self, vec_ptr: int, side: int, buf_ptr: int):
         self._ck(self.L.sgpu_vec_halo_unpack(self.h, ctypes.c_void_p(vec_ptr), side, ctypes.c_void_p(buf_ptr)))
+
+    def vec_halo_pack_ghost(self, vec_ptr: int, side: int, buf_ptr: int):
+        self._ck(self.L.sgpu_vec_halo_pack_ghost(self.h, ctypes.c_void_p(vec_ptr), side, ctypes.c_void_p(buf_ptr)))
+
+    def vec_halo_add(self, vec_ptr: int, side: int, buf_ptr: int):
+        self._ck(self.L.sgpu_vec_halo_add(self.h, ctypes.c_void_p(vec_ptr), side, ctypes.c_void_p(buf_ptr)))
+
+    def vec_from_host(self, host: np.ndarray, vec_ptr: int):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.shape == (self.nic, self.njc, self.nv)
+        self._ck(self.L.sgpu_vec_from_host(self.h, _dp(host), ctypes.c_void_p(vec_ptr)))
+
+    def vec_to_host(self, vec_ptr: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._state_array() if out is None else out
+        self._ck(self.L.sgpu_vec_to_host(self.h, ctypes.c_void_p(vec_ptr), _dp(out)))
+        return out
 
     def op_apply(self, matrix: str, x_ptr: int, y_ptr: int):
         self._ck(self.L.sgpu_op_apply(self.h, MATRICES[matrix], ctypes.c_void_p(x_ptr), ctypes.c_void_p(y_ptr)))

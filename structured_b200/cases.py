@@ -119,8 +119,36 @@ class Case:
 # ------------------------------------------------------------------------------------------------
 # reference file formats
 # ------------------------------------------------------------------------------------------------
+GRID_BIN_MAGIC = b"SGRIDF64"   # binary vertex file: magic, int32 ni, int32 nj, x[nj][ni] float64, y[nj][ni] float64 (j outer, i inner)
+
+
+def write_grid_bin(filename: str, xv: np.ndarray, yv: np.ndarray) -> None:
+    """Binary variant of the p3d file for large grids (parsing 134 M ASCII vertices takes minutes):
+    the same j-outer / i-inner order as Mesh::plot3d_loader (src/utils/mesh.cpp:146-169), raw little-endian float64."""
+    ni, nj = xv.shape
+    with open(filename, "wb") as f:
+        f.write(GRID_BIN_MAGIC)
+        np.array([ni, nj], dtype="<i4").tofile(f)
+        np.ascontiguousarray(xv.T, dtype="<f8").tofile(f)
+        np.ascontiguousarray(yv.T, dtype="<f8").tofile(f)
+
+
+def read_grid_bin(filename: str, ni: int, nj: int, rows: Optional[tuple] = None):
+    """-> xv, yv [ni][rows]; rows = (first vertex row, count) reads only that window (what one rank of a slab run needs)"""
+    with open(filename, "rb") as f:
+        if f.read(8) != GRID_BIN_MAGIC:
+            raise ValueError("file format not found!")  # src/utils/mesh.cpp:364
+        hdr = np.fromfile(f, dtype="<i4", count=2)
+    assert int(hdr[0]) == ni and int(hdr[1]) == nj, "binary grid header mismatch"
+    j0, n = (0, nj) if rows is None else rows
+    mm = np.memmap(filename, dtype="<f8", mode="r", offset=16, shape=(2, nj, ni))
+    return np.ascontiguousarray(mm[0, j0:j0 + n, :].T), np.ascontiguousarray(mm[1, j0:j0 + n, :].T)
+
+
 def read_grid(filename: str, ni: int, nj: int, fmt: str):
-    """Mesh::simple_loader / plot3d_loader (src/utils/mesh.cpp:134-169): j outer, i inner."""
+    """Mesh::simple_loader / plot3d_loader (src/utils/mesh.cpp:134-169): j outer, i inner; "bin": the binary variant."""
+    if fmt == "bin":
+        return read_grid_bin(filename, ni, nj)
     tok = np.array(open(filename).read().split(), dtype=np.float64)
     if fmt == "simple":
         xy = tok[: 2 * ni * nj].reshape(nj, ni, 2)
@@ -170,6 +198,14 @@ def case_from_toml(text: str, xv: Optional[np.ndarray] = None, yv: Optional[np.n
     c.label = io.get("label", "flow")
     tb = t.get("turbulence", {})  # new optional table; stock files do not have it
     c.ntrans = int(tb.get("ntrans", 0))
+    if c.ntrans:
+        nc = (ni - 1, nj - 1)
+        wd = tb.get("wall_distance", "compute")
+        if wd != "compute":
+            c.wall_distance = np.fromfile(wd if os.path.isabs(wd) else os.path.join(base_dir, wd), dtype=np.float64).reshape(nc)
+        if tb.get("beta_file"):
+            bf = tb["beta_file"]
+            c.beta = np.fromfile(bf if os.path.isabs(bf) else os.path.join(base_dir, bf), dtype=np.float64).reshape(nc)
     for b in t.get("boundary", []):
         c.boundaries.append(Boundary(type=b.get("type", ""), face=b.get("face", ""), start=int(b.get("start", 0)),
                                      end=int(b.get("end", 0)), u=float(b.get("u", 0.0)), v=float(b.get("v", 0.0)),
@@ -206,6 +242,17 @@ def write_case(case: Case, directory: str, name: str = "case") -> str:
               "cfl = %s" % repr(float(case.cfl)), 'scheme = "%s"' % case.scheme, 'flux = "%s"' % case.flux,
               "iteration_max = %d" % case.iteration_max, "", "[io]", "stdout_frequency = 1000000",
               "fileout_frequency = 1000000", "restart = false", 'label = "%s"' % name, ""]
+    if case.ntrans:              # optional table of the GPU drop-in (integration/solver_gpu.cpp); the stock reference ignores it
+        lines += ["[turbulence]", "ntrans = %d" % case.ntrans]
+        if case.wall_distance is None:
+            lines.append('wall_distance = "compute"')
+        else:
+            np.ascontiguousarray(case.wall_distance, dtype=np.float64).tofile(os.path.join(directory, name + ".wdist.bin"))
+            lines.append('wall_distance = "./%s.wdist.bin"' % name)
+        if case.beta is not None:
+            np.ascontiguousarray(case.beta, dtype=np.float64).tofile(os.path.join(directory, name + ".beta.bin"))
+            lines.append('beta_file = "./%s.beta.bin"' % name)
+        lines.append("")
     for b in case.boundaries:
         lines += ["[[boundary]]", 'name = ""', 'type = "%s"' % b.type, 'face = "%s"' % b.face, "start = %d" % b.start,
                   "end = %d" % b.end, "u = %s" % repr(float(b.u)), "v = %s" % repr(float(b.v)), "T = %s" % repr(float(b.T)), ""]

@@ -17,6 +17,7 @@ struct LinWork {
     double* ydev = nullptr;        // m doubles
     double* hhost = nullptr;       // pinned, ldp doubles
     int* err = nullptr;
+    unsigned* ticket = nullptr;    // arrival counter of the in-kernel final reductions
     int blocks = 0, ldp = 0;
 };
 
@@ -24,7 +25,7 @@ static void lin_free(LinWork*& L) {
     if (!L) return;
     cudaFree(L->V); cudaFree(L->w); cudaFree(L->z); cudaFree(L->x); cudaFree(L->b); cudaFree(L->u);
     cudaFree(L->psi); cudaFree(L->g);
-    cudaFree(L->Dinv); cudaFree(L->partial); cudaFree(L->hdev); cudaFree(L->ydev); cudaFree(L->err);
+    cudaFree(L->Dinv); cudaFree(L->partial); cudaFree(L->hdev); cudaFree(L->ydev); cudaFree(L->err); cudaFree(L->ticket);
     if (L->hhost) cudaFreeHost(L->hhost);
     delete L; L = nullptr;
 }
@@ -46,6 +47,7 @@ static int lin_prepare(sgpu_ctx* c, int m) {
     CK(c, cudaMalloc(&L->partial, (size_t)L->blocks*L->ldp*sizeof(double)));
     CK(c, cudaMalloc(&L->hdev, L->ldp*sizeof(double))); CK(c, cudaMalloc(&L->ydev, (m + 1)*sizeof(double)));
     CK(c, cudaMalloc(&L->err, sizeof(int)));
+    CK(c, cudaMalloc(&L->ticket, sizeof(unsigned))); CK(c, cudaMemsetAsync(L->ticket, 0, sizeof(unsigned), c->stream));
     CK(c, cudaMallocHost(&L->hhost, L->ldp*sizeof(double)));
     // ghosts / padding of every vector stay 0 from here on: the kernels either write owned cells only or are flat combinations
     CK(c, cudaMemsetAsync(L->V, 0, vb*(m + 1), c->stream));
@@ -65,16 +67,19 @@ static int lin_apply_op(sgpu_ctx* c, int matrix, const double* x, double* y) {
     const bool order2 = c->d.lhs_order == 2;
     const int op = mat_op(matrix);
     if (mat_transposed(matrix)) {
-        // gather form for the inner row cells (writes every owned y once), then the boundary band's atomic scatter
-        if (v.nv == 5) op_apply_t_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
-        else op_apply_t_kernel<4><<<grd, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
+        // gather form for the inner row cells (writes every owned y once), then the boundary band's atomic scatter;
+        // interior slab edges: the ghost rows of y receive this slab's share of the neighbour's cells
+        const int jl0 = v.j0 > 0 ? -JOFF : 0, jl1 = v.j1 < v.njc ? v.njl + JOFF : v.njl;
+        const dim3 grdt((v.nic + 127)/128, jl1 - jl0);
+        if (v.nv == 5) op_apply_t_kernel<5><<<grdt, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, jl0);
+        else op_apply_t_kernel<4><<<grdt, 128, 0, c->stream>>>(v, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y, jl0);
         CKL(c); c->launches++;
         if (v.nv == 5) op_apply_t_band_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
         else op_apply_t_band_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, x, y);
         if (op == OP_LHS) {
             CKL(c); c->launches++;
-            if (v.nv == 5) lhs_fixup_kernel<5><<<grd, 128, 0, c->stream>>>(v, c->dt, x, y);
-            else lhs_fixup_kernel<4><<<grd, 128, 0, c->stream>>>(v, c->dt, x, y);
+            if (v.nv == 5) lhs_fixup_kernel<5><<<grdt, 128, 0, c->stream>>>(v, c->dt, x, y, jl0);
+            else lhs_fixup_kernel<4><<<grdt, 128, 0, c->stream>>>(v, c->dt, x, y, jl0);
         }
     } else if (v.nv == 5) op_apply_kernel<5><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, c->dt, op, x, y);
     else op_apply_kernel<4><<<grd, 128, 0, c->stream>>>(v, gt, c->jac.slots, c->viscous, order2, c->jac.blocks, c->dt, op, x, y);
@@ -126,19 +131,20 @@ static int lin_apply_pc(sgpu_ctx* c, int matrix, int precond, const double* r, d
     return SGPU_OK;
 }
 
-// out[j0 .. j0+cnt) on the device (L->hdev) = w . V_j ; no synchronisation
+// L->hdev[j0 .. j0+cnt) = w . V_j on the device (final reduction inside the kernel); no synchronisation
 static int lin_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, int j0 = 0) {
     LinWork* L = c->lin;
     for (int g = 0; g < cnt; g += DOT_GROUP) {
         const int k = std::min(DOT_GROUP, cnt - g);
-        dots_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, j0 + g);
+        dots_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, j0 + g, L->hdev, L->ticket);
         CKL(c); c->launches++;
     }
     return SGPU_OK;
 }
-static int lin_reduce(sgpu_ctx* c, int cnt) {
+// w -= V h (h = L->hdev[0 .. cnt)) and L->hdev[cnt] = |w|^2 of the result, one pass
+static int lin_gs_update(sgpu_ctx* c, double* w, const double* V, int cnt) {
     LinWork* L = c->lin;
-    reduce_partials_kernel<<<cnt, 256, 0, c->stream>>>(L->partial, L->blocks, L->ldp, L->hdev);
+    gs_update_kernel<<<L->blocks, 256, 0, c->stream>>>(w, V, L->n, cnt, L->hdev, L->partial, L->ldp, cnt, L->hdev, L->ticket);
     CKL(c); c->launches++;
     return SGPU_OK;
 }
@@ -150,7 +156,6 @@ static int lin_fetch(sgpu_ctx* c, int cnt) {
 }
 static int lin_norm(sgpu_ctx* c, const double* a, double* out) {
     if (int rc = lin_dots(c, a, a, 1)) return rc;
-    if (int rc = lin_reduce(c, 1)) return rc;
     if (int rc = lin_fetch(c, 1)) return rc;
     *out = std::sqrt(c->lin->hhost[0]);
     return SGPU_OK;
@@ -192,7 +197,6 @@ static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io, bool refactor =
         if (beta <= rtol*bnorm || iters >= max_iter) break;
         // V0 = r/beta
         if (int rc = lin_dots(c, L->w, L->w, 1)) return rc;
-        if (int rc = lin_reduce(c, 1)) return rc;
         scale_rsqrt_kernel<<<G, 256, 0, c->stream>>>(L->V, L->w, n, L->hdev); CKL(c); c->launches++;
         std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
         int k = 0;
@@ -205,21 +209,18 @@ static int lin_gmres(sgpu_ctx* c, int matrix, sgpu_linsolve* io, bool refactor =
             if (tm) CK(c, cudaEventRecord(t1, c->stream));
             if (int rc = lin_apply_op(c, matrix, L->z, L->w)) return rc;
             if (tm) { CK(c, cudaEventRecord(t2, c->stream)); timed = true; }
-            // classical Gram-Schmidt against V_0..V_k, projections stay on the device for the update
+            // classical Gram-Schmidt against V_0..V_k: projections (one pass over w per 16 basis vectors), then update + |w|^2
+            // in one pass; everything stays on the device until the single fetch below
             if (int rc = lin_dots(c, L->w, L->V, k + 1)) return rc;
-            if (int rc = lin_reduce(c, k + 1)) return rc;
-            gs_update_kernel<<<G, 256, 0, c->stream>>>(L->w, L->V, n, k + 1, L->hdev); CKL(c); c->launches++;
+            if (int rc = lin_gs_update(c, L->w, L->V, k + 1)) return rc;
             std::vector<double> h(k + 2, 0.0);
             if (io->reorthogonalize) {
                 if (int rc = lin_fetch(c, k + 1)) return rc;
                 for (int j = 0; j <= k; j++) h[j] = L->hhost[j];
                 if (int rc = lin_dots(c, L->w, L->V, k + 1)) return rc;
-                if (int rc = lin_reduce(c, k + 1)) return rc;
-                gs_update_kernel<<<G, 256, 0, c->stream>>>(L->w, L->V, n, k + 1, L->hdev); CKL(c); c->launches++;
+                if (int rc = lin_gs_update(c, L->w, L->V, k + 1)) return rc;
             }
-            // |w|^2 into column k+1, next basis vector scaled from the device value
-            if (int rc = lin_dots(c, L->w, L->w, 1, k + 1)) return rc;
-            reduce_partials_kernel<<<1, 256, 0, c->stream>>>(L->partial + (k + 1), G, L->ldp, L->hdev + (k + 1)); CKL(c); c->launches++;
+            // next basis vector scaled from the device value of |w|^2 (column k+1)
             scale_rsqrt_kernel<<<G, 256, 0, c->stream>>>(L->V + (size_t)(k + 1)*n, L->w, n, L->hdev + (k + 1)); CKL(c); c->launches++;
             if (int rc = lin_fetch(c, k + 2)) return rc;
             for (int j = 0; j <= k; j++) h[j] += L->hhost[j];
@@ -343,9 +344,9 @@ int sgpu_adjoint_solve(sgpu_ctx* c, const double* g, double* psi, double cfl, in
 //      (sgpu_vec_size doubles); owned cells carry the data, the two ghost rows per interior slab edge are filled by
 //      sgpu_vec_halo_pack -> transport -> sgpu_vec_halo_unpack before every operator application.
 static int vec_check(sgpu_ctx* c, int matrix) {
-    if (matrix != SGPU_MAT_LHS && matrix != SGPU_MAT_J) FAIL(c, SGPU_ERR_ARG, "slab vector operations support SGPU_MAT_LHS and SGPU_MAT_J (the transposed products scatter across slab edges)");
+    if (matrix < SGPU_MAT_LHS || matrix > SGPU_MAT_LHS_T) FAIL(c, SGPU_ERR_ARG, "matrix must be SGPU_MAT_LHS, SGPU_MAT_J, SGPU_MAT_JT or SGPU_MAT_LHS_T");
     if (!c->jac.valid) FAIL(c, SGPU_ERR_STATE, "no device Jacobian: call sgpu_jacobian_device first");
-    if (matrix == SGPU_MAT_LHS && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS matrix needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
+    if ((matrix == SGPU_MAT_LHS || matrix == SGPU_MAT_LHS_T) && !c->have_dt) FAIL(c, SGPU_ERR_STATE, "the LHS matrix needs dt: call sgpu_calc_dt first (src/solver/solver.cpp:66,167-170)");
     return SGPU_OK;
 }
 int sgpu_vec_size(const sgpu_ctx* c, long long* n) {
@@ -384,6 +385,47 @@ int sgpu_vec_halo_unpack(sgpu_ctx* c, double* vec, int side, const double* buf) 
     halo_unpack_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, vec, buf, halo_rows(c, side, true));
     CKL(c); c->launches++;
     return SGPU_OK;
+}
+// transposed products on a slab partition: the ghost rows of y = A^T x hold this slab's contribution to the neighbour's
+// boundary cells.  pack_ghost copies them out (layout of sgpu_halo_pack) and clears them; add accumulates the neighbour's
+// buffer into this slab's two boundary rows on that side.
+int sgpu_vec_halo_pack_ghost(sgpu_ctx* c, double* vec, int side, double* buf) {
+    if (!c || !vec || !buf || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    const dim3 grd((v.nic + 255)/256, 2*v.nv);
+    halo_pack_kernel<<<grd, 256, 0, c->stream>>>(v, vec, buf, halo_rows(c, side, true));
+    CKL(c);
+    halo_zero_kernel<<<grd, 256, 0, c->stream>>>(v, vec, halo_rows(c, side, true));
+    CKL(c); c->launches += 2;
+    return SGPU_OK;
+}
+int sgpu_vec_halo_add(sgpu_ctx* c, double* vec, int side, const double* buf) {
+    if (!c || !vec || !buf || side < 0 || side > 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    halo_add_kernel<<<dim3((v.nic + 255)/256, 2*v.nv), 256, 0, c->stream>>>(v, vec, buf, halo_rows(c, side, false));
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+// host <-> device vector (GLOBAL host arrays [nic][njc][nv]; owned rows; ghost rows / padding of the vector are zeroed)
+int sgpu_vec_from_host(sgpu_ctx* c, const double* host, double* vec) {
+    if (!c || !host || !vec) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    CK(c, cudaMemsetAsync(vec, 0, v.plane*v.nv*sizeof(double), c->stream));
+    const size_t M = (size_t)v.njl*v.nv;
+    if (int rc = ensure_stage(c, (size_t)v.nic*M)) return rc;
+    CK(c, cudaMemcpy2DAsync(c->stage, sizeof(double)*M, host + (size_t)v.j0*v.nv, sizeof(double)*v.njc*v.nv, sizeof(double)*M, v.nic, cudaMemcpyHostToDevice, c->stream));
+    aos_to_planes_kernel<<<dim3((unsigned)((M + 31)/32), (v.nic + 31)/32), dim3(32, 8), 0, c->stream>>>(v, c->stage, vec, JOFF, v.njl);
+    CKL(c); c->launches++;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+int sgpu_vec_to_host(sgpu_ctx* c, const double* vec, double* host) {
+    if (!c || !host || !vec) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    return download_planes(c, vec, c->v.nv, host);
 }
 int sgpu_op_apply(sgpu_ctx* c, int matrix, const double* x, double* y) {
     if (!c || !x || !y) return SGPU_ERR_ARG;

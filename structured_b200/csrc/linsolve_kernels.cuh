@@ -87,11 +87,14 @@ __global__ void __launch_bounds__(128) op_apply_kernel(View v, GhostTable gt, in
 // -- the blocks of the neighbouring ROW cells are read at a shifted offset, still coalesced, and every y is written
 // once (deterministic, no atomics).  Row cells in the boundary band (remapped / folded columns) are added afterwards by
 // jac_apply_kernel's atomic scatter restricted to the band (op_apply_t_band_kernel below).
+// On a j-slab the launch also covers the two ghost rows of every interior edge (jl0 = -2 / rows up to njl + 2): what this
+// slab's row cells contribute to the neighbour's cells is left in the GHOST rows of y, which the caller sends over and
+// adds there (sgpu_vec_halo_pack_ghost -> transport -> sgpu_vec_halo_add: the transpose of the operand halo exchange).
 template <int NV>
 __global__ void __launch_bounds__(128) op_apply_t_kernel(View v, int nslots, bool viscous, bool order2,
-                                                         const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y) {
+                                                         const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y, int jl0) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    const int jl = blockIdx.y;
+    const int jl = jl0 + (int)blockIdx.y;
     if (i >= v.nic) return;
     const int gj = v.j0 + jl;
     const size_t o = v.at(jl + JOFF, i + IOFF);
@@ -145,13 +148,32 @@ __global__ void op_apply_t_band_kernel(View v, GhostTable gt, int nslots, bool v
     }
 }
 
+// ghost rows of a vector: dst rows += packed buffer [nv][2][nic] (reverse halo exchange of a transposed product)
+__global__ void halo_add_kernel(View v, double* __restrict__ vec, const double* __restrict__ buf, int r_first) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= v.nic) return;
+    const int k = blockIdx.y >> 1, rr = blockIdx.y & 1;
+    vec[k*v.plane + v.at(r_first + rr, i + IOFF)] += buf[((size_t)k*2 + rr)*v.nic + i];
+}
+__global__ void halo_zero_kernel(View v, double* __restrict__ vec, int r_first) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= v.nic) return;
+    const int k = blockIdx.y >> 1, rr = blockIdx.y & 1;
+    vec[k*v.plane + v.at(r_first + rr, i + IOFF)] = 0.0;
+}
+
 // after the scattered J^T x accumulation: y = -y + x/dt on the owned cells
 template <int NV>
-__global__ void lhs_fixup_kernel(View v, const double* __restrict__ dt, const double* __restrict__ x, double* __restrict__ y) {
+// (rows from jl0: on a slab the ghost rows of y carry the neighbour's share of J^T x, which only changes sign)
+__global__ void lhs_fixup_kernel(View v, const double* __restrict__ dt, const double* __restrict__ x, double* __restrict__ y, int jl0) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    const int jl = blockIdx.y;
+    const int jl = jl0 + (int)blockIdx.y;
     if (i >= v.nic) return;
     const size_t o = v.at(jl + JOFF, i + IOFF);
+    if (jl < 0 || jl >= v.njl) {
+        for (int r = 0; r < NV; r++) y[r*v.plane + o] = -y[r*v.plane + o];
+        return;
+    }
     const double idt = 1.0/dt[o];
     for (int r = 0; r < NV; r++) y[r*v.plane + o] = x[r*v.plane + o]*idt - y[r*v.plane + o];
 }
@@ -592,12 +614,32 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
 // ------------------------------------------------------------------------------------------------
 // Flat vector kernels (n = plane*nv elements; ghosts/padding are zero in every operand)
 // ------------------------------------------------------------------------------------------------
-constexpr int DOT_GROUP = 8;
+constexpr int DOT_GROUP = 16;
 constexpr int DOT_THREADS = 256;
 
-// partial[block][ldp] at columns j0..j0+cnt-1  =  this block's share of  w . V_j
+// The last block to arrive (atomic ticket) sums the per-block partials of `cnt` columns in block order -- deterministic,
+// and no separate reduction launch (one Gram-Schmidt sweep was 3 launches + 2 reductions per 8 basis vectors).
+__device__ __forceinline__ void last_block_reduce(double* __restrict__ partial, int ldp, int col0, int cnt, double* __restrict__ out, unsigned* ticket) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = wid; c < cnt; c += blockDim.x >> 5) {             // one warp per column, lanes stride over the blocks: fixed order
+        double s = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += ((volatile double*)partial)[(size_t)b*ldp + col0 + c];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) out[col0 + c] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// out[j0 .. j0+cnt) = w . V_j  (cnt <= DOT_GROUP basis vectors per pass over w)
 __global__ void __launch_bounds__(DOT_THREADS) dots_kernel(const double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt,
-                                                           double* __restrict__ partial, int ldp, int j0) {
+                                                           double* __restrict__ partial, int ldp, int j0, double* __restrict__ out, unsigned* ticket) {
     double acc[DOT_GROUP];
 #pragma unroll
     for (int j = 0; j < DOT_GROUP; j++) acc[j] = 0.0;
@@ -621,16 +663,32 @@ __global__ void __launch_bounds__(DOT_THREADS) dots_kernel(const double* __restr
         for (int k = 0; k < DOT_THREADS/32; k++) s += ws[threadIdx.x][k];
         partial[(size_t)blockIdx.x*ldp + j0 + threadIdx.x] = s;
     }
+    last_block_reduce(partial, ldp, j0, cnt, out, ticket);
 }
 
-// w -= sum_j h[j] V_j   (h on the device: no host round trip between the projection and the update)
-__global__ void gs_update_kernel(double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ h) {
+// w -= sum_j h[j] V_j  and, in the same pass, out[ncol] = |w_new|^2  (h on the device: no host round trip between the
+// projection and the update, and no extra pass over w for the norm of the next basis vector)
+__global__ void __launch_bounds__(256) gs_update_kernel(double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ h,
+                                                        double* __restrict__ partial, int ldp, int ncol, double* __restrict__ out, unsigned* ticket) {
     const size_t stride = (size_t)gridDim.x*blockDim.x;
+    double acc = 0.0;
     for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
         double s = w[e];
         for (int j = 0; j < cnt; j++) s -= h[j]*V[(size_t)j*n + e];
         w[e] = s;
+        acc += s*s;
     }
+    __shared__ double ws[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) ws[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < 8; k++) s += ws[k];
+        partial[(size_t)blockIdx.x*ldp + ncol] = s;
+    }
+    last_block_reduce(partial, ldp, ncol, 1, out, ticket);
 }
 
 // dst = src * (1/sqrt(*normsq))

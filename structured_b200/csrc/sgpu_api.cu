@@ -259,6 +259,38 @@ int sgpu_set_grid(sgpu_ctx* c, const double* xv, const double* yv) {
     return sgpu_set_grid_window(c, xv, yv, 0, c->v.nj);
 }
 
+// Binary vertex file (structured_b200/cases.py::write_grid_bin): "SGRIDF64", int32 ni, int32 nj, x[nj][ni], y[nj][ni]
+// float64 -- the p3d order (Mesh::plot3d_loader, src/utils/mesh.cpp:146-169) without the ASCII.  A file row IS a row of
+// the vertex planes, so only this slab's window of rows is read and it goes to the device with one 2-D copy per array:
+// no host transpose, no staging kernel.
+int sgpu_set_grid_file(sgpu_ctx* c, const char* path) {
+    if (!c || !path) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const View& v = c->v;
+    FILE* f = fopen(path, "rb");
+    if (!f) FAIL(c, SGPU_ERR_ARG, "cannot open grid file %s", path);
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    char magic[8]; int hdr[2];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SGRIDF64", 8) != 0) FAIL(c, SGPU_ERR_ARG, "file format not found! (%s is not a binary vertex file)", path);   // mesh.cpp:364
+    if (fread(hdr, sizeof(int), 2, f) != 2 || hdr[0] != v.ni || hdr[1] != v.nj) FAIL(c, SGPU_ERR_ARG, "grid file %s holds %d x %d vertices, the context %d x %d", path, hdr[0], hdr[1], v.ni, v.nj);
+    const int ja = std::max(v.j0 - 2, 0), jb = std::min(v.j1 + 2, v.nj - 1);       // vertex rows [ja, jb]
+    const int nrows = jb - ja + 1, r0 = ja - v.j0 + JOFF;
+    std::vector<double> h((size_t)nrows*v.ni);
+    double* dst[2] = {c->xv, c->yv};
+    for (int n = 0; n < 2; n++) {
+        const long long off = 16 + ((long long)n*v.nj + ja)*(long long)v.ni*(long long)sizeof(double);
+        if (fseeko(f, (off_t)off, SEEK_SET) != 0 || fread(h.data(), sizeof(double), h.size(), f) != h.size()) FAIL(c, SGPU_ERR_ARG, "grid file %s is truncated", path);
+        CK(c, cudaMemcpy2D(dst[n] + v.at(r0, IOFF), sizeof(double)*v.pitch, h.data(), sizeof(double)*v.ni, sizeof(double)*v.ni, nrows, cudaMemcpyHostToDevice));
+    }
+    Metrics m = metrics_of(c);
+    metrics_kernel<<<dim3((v.pitch + 127)/128, v.rows), 128, 0, c->stream>>>(v, c->xv, c->yv, (double*)m.ncx, (double*)m.ncy,
+                                                                            (double*)m.nex, (double*)m.ney, (double*)m.vol);
+    CKL(c); c->launches++;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->have_grid = true; c->jgeo_valid = false;
+    return SGPU_OK;
+}
+
 int sgpu_set_field_window(sgpu_ctx* c, const char* name, const double* f, int j_first, int j_count) {
     if (!c || !name || !f) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));

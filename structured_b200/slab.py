@@ -186,24 +186,77 @@ class SlabLinearSolver:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
-    def solve(self, matrix: str = "lhs", precond: str = "line_j", restart: int = 30, max_iter: int = 500, rtol: float = 1e-10):
-        """A x = rhs with the device rhs of the last residual and the Jacobian of the last jacobian_device();
-        returns (x as a device tensor laid out as state planes, info)."""
-        import torch
+    def apply_op(self, matrix: str, x, out) -> None:
+        """out = A x on this slab's rows.  Forward matrices ("lhs", "J") need the operand's two ghost rows per interior edge
+        BEFORE the product; transposed ones ("JT", "lhsT") need none, but each slab's rows also contribute to the
+        neighbour's boundary cells: those contributions are left in the ghost rows of `out`, sent over and ADDED there --
+        the transpose of the operand exchange (one more exchange of two block rows)."""
         eq = self.eq
-        b = torch.zeros(self.n, dtype=torch.float64, device=self.device)
-        eq.vec_from_rhs(b.data_ptr())
-        eq.precond_setup(matrix, precond)
-
-        def apply_op(x, out):
+        if matrix in ("JT", "lhsT"):
+            eq.op_apply(matrix, x.data_ptr(), out.data_ptr())
+            self.halo.exchange(lambda side, t: eq.vec_halo_pack_ghost(out.data_ptr(), side, t.data_ptr()),
+                               lambda side, t: eq.vec_halo_add(out.data_ptr(), side, t.data_ptr()))
+        else:
             self.halo.exchange(lambda side, t: eq.vec_halo_pack(x.data_ptr(), side, t.data_ptr()),
                                lambda side, t: eq.vec_halo_unpack(x.data_ptr(), side, t.data_ptr()))
             eq.op_apply(matrix, x.data_ptr(), out.data_ptr())
 
+    def solve(self, matrix: str = "lhs", precond: str = "line_j", restart: int = 30, max_iter: int = 500, rtol: float = 1e-10,
+              b=None, setup: bool = True):
+        """A x = b; b = None: the device rhs of the last residual (what linearsolver->set_rhs receives).  Uses the Jacobian
+        of the last jacobian_device(); returns (x as a device tensor laid out as state planes, info)."""
+        import torch
+        eq = self.eq
+        if b is None:
+            b = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+            eq.vec_from_rhs(b.data_ptr())
+        if setup:
+            eq.precond_setup(matrix, precond)
+
         def apply_pc(r, out):
             eq.precond_apply(matrix, precond, r.data_ptr(), out.data_ptr())
 
-        return distributed_gmres(apply_op, apply_pc, b, restart, max_iter, rtol, self._allreduce if self.world > 1 else None)
+        return distributed_gmres(lambda x, out: self.apply_op(matrix, x, out), apply_pc, b, restart, max_iter, rtol,
+                                 self._allreduce if self.world > 1 else None)
+
+    def adjoint_solve(self, g_host: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
+                      restart: int = 40, max_iter: int = 400, rtol: float = 1e-3):
+        """sgpu_adjoint_solve on a slab partition: J^T psi = -g by pseudo-time continuation, (delta/dt - J^T) dpsi = g + J^T psi
+        per step with transposed-LHS GMRES solves, psi += dpsi (A22; no reference code -- "parity unpinned").
+        g_host: GLOBAL [nic][njc][nv] objective gradient (every rank passes the same array, only its rows are read).
+        Returns (psi as a device tensor of this slab, info)."""
+        import math
+
+        import torch
+        eq = self.eq
+        g = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+        eq.vec_from_host(g_host, g.data_ptr())
+        psi = torch.zeros_like(g); r = torch.zeros_like(g)
+        eq.calc_dt(cfl)
+
+        def gnorm(a):
+            t = torch.dot(a, a).reshape(1)
+            self._allreduce(t)
+            return math.sqrt(float(t[0]))
+        g0 = gnorm(g)
+        info = {"steps": 0, "iterations": 0, "rel_residual": 0.0, "converged": True}
+        if g0 == 0.0:
+            return psi, info
+        steps = 0
+        while True:
+            self.apply_op("JT", psi, r)
+            r.add_(g)
+            rel = gnorm(r) / g0
+            info["rel_residual"] = rel
+            if rel <= tol or steps >= max_steps:
+                break
+            dpsi, gi = self.solve("lhsT", precond, restart, max_iter, rtol, b=r, setup=(steps == 0))
+            info["iterations"] += gi["iterations"]
+            psi.add_(dpsi)
+            steps += 1
+        info["steps"] = steps
+        info["converged"] = info["rel_residual"] <= tol
+        return psi, info
 
     def implicit_step(self, cfl: float, under_relaxation: float = 1.0, exchange_state: Callable = None, **kw):
         """The implicit branch of Solver::step on a slab partition: dt, residual, Jacobian, distributed GMRES, update.

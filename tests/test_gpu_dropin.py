@@ -120,3 +120,50 @@ def test_device_resident_implicit_dropin_matches_the_eigen_lu_dropin(tmp_path):
     err = field_rel_err(qs[1], qs[0])
     err[2] = np.abs(qs[1][..., 2] - qs[0][..., 2]).max() / np.abs(qs[0][..., 1]).max()
     assert err.max() <= 1e-8, err
+
+
+BIN_EXPLICIT_SA = os.path.join(ROOT, "integration", "structured_gpu_explicit")
+
+
+@pytest.mark.skipif(not (os.path.exists(BIN_IMPLICIT_DEVICE) and os.path.exists(BIN_EXPLICIT_SA)),
+                    reason="integration binaries not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("mode", ["implicit_device", "explicit"])
+def test_sa_flat_plate_through_the_cpp_dropin_equals_the_python_api(tmp_path, mode):
+    """SA + beta(x) + computed wall distance through the reference's own main.cpp / Config / Mesh: the optional
+    `[turbulence]` table (integration/solver_gpu.cpp) switches the five-variable state on; the run must reproduce the
+    Python API driving the same C ABI calls (SA has no reference code: this pins the drop-in plumbing, not the physics)."""
+    from structured_b200.api import GpuEulerEquation
+    from structured_b200.cases import flat_plate_case, write_case
+    case = flat_plate_case(48, 32, reynolds=1e5)
+    n_it = 4
+    case.iteration_max, case.cfl = n_it, (5.0 if mode == "implicit_device" else 0.3)
+    case.scheme = "rk4_jameson"
+    inp = write_case(case, str(tmp_path), "plate")
+    text = open(inp).read()
+    assert "[turbulence]" in text and 'wall_distance = "compute"' in text
+    binary = BIN_IMPLICIT_DEVICE if mode == "implicit_device" else BIN_EXPLICIT_SA
+    res = subprocess.run([binary, "-c", "plate.inp"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    q5 = np.fromfile(tmp_path / "plate.sa.out").reshape(case.nic, case.njc, 5)
+    npz = np.load(tmp_path / "plate.npz")
+    assert np.array_equal(npz["q"], q5[..., :4])                  # the reference's writer got the mean-flow variables
+    eq = GpuEulerEquation(case)
+    eq.initialize()
+    for _ in range(n_it + 1):                                     # Solver::solve: steps 0 .. iteration_max update, the next one only evaluates
+        if mode == "implicit_device":
+            eq.implicit_step(case.cfl, 1.0, precond="line_j", restart=60, max_iter=2000, rtol=1e-13)
+        else:
+            eq.explicit_step(case.cfl, "rk4_jameson")
+    want = eq.get_state()
+    eq.close()
+    assert np.isfinite(q5).all() and np.abs(q5[..., 4] - 3.0 * case.mu_inf).max() > 0     # the transport equation moved
+    err = field_rel_err(q5, want)
+    assert err.max() <= 1e-12, err
+
+
+def test_stock_configs_have_no_turbulence_table_and_parse_as_before():
+    """the new optional table must not change how stock reference files are read (Config ignores unknown tables,
+    src/utils/config.cpp:91-109; case_from_toml defaults ntrans = 0)"""
+    for name in ("channel", "naca0012"):
+        case, z = golden(name)
+        assert "[turbulence]" not in str(z["inp"]) and case.ntrans == 0 and case.nv == 4

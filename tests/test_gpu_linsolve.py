@@ -270,3 +270,47 @@ def test_slab_partitioned_solve_equals_single_slab_solve(ntrans, precond):
     assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
     for s in slabs + [one]:
         s.close()
+
+
+@pytest.mark.parametrize("ntrans,split", [(0, 30), (1, 17), (1, 2)])
+def test_transposed_products_across_slabs_equal_single_slab(ntrans, split):
+    """J^T x and (delta/dt - J^T) x on two j-slabs: no operand halo, but every slab's rows also feed the neighbour's two
+    boundary rows -- left in the ghost rows of y, sent over and added (sgpu_vec_halo_pack_ghost / sgpu_vec_halo_add).
+    Must equal the one-context product; the dot-product identity psi.(J v) = (J^T psi).v must hold across the slabs."""
+    import torch
+    from structured_b200.slab import HIGH, LOW
+    nic, njc = 70, 48
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4, periodic=(ntrans == 0))
+    q = case.perturbed_q(0.02)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(q.shape)
+    one = gpu_eq(case)
+    one.set_state(q); one.calc_dt(6.0); one.jacobian_device()
+    n1 = one.vec_size()
+    xd = torch.zeros(n1, dtype=torch.float64, device="cuda"); yd = torch.zeros_like(xd)
+    one.vec_from_host(x, xd.data_ptr())
+    want = {}
+    for mat in ("JT", "lhsT", "J"):
+        one.op_apply(mat, xd.data_ptr(), yd.data_ptr())
+        want[mat] = one.vec_to_host(yd.data_ptr())
+    assert np.abs(want["JT"] - one.jacobian_apply(x, transpose=True)).max() <= 1e-12 * np.abs(want["JT"]).max()
+    slabs = [gpu_eq(case, j_begin=0, j_end=split), gpu_eq(case, j_begin=split, j_end=njc)]
+    xs, ys = [], []
+    for s in slabs:
+        s.set_state(q); s.calc_dt(6.0); s.jacobian_device()
+        xs.append(torch.zeros(s.vec_size(), dtype=torch.float64, device="cuda")); ys.append(torch.zeros_like(xs[-1]))
+        s.vec_from_host(x, xs[-1].data_ptr())
+    buf = torch.empty(slabs[0].halo_count(), dtype=torch.float64, device="cuda")
+    for mat in ("JT", "lhsT"):
+        for s, xv, yv in zip(slabs, xs, ys):
+            s.op_apply(mat, xv.data_ptr(), yv.data_ptr())
+        slabs[0].vec_halo_pack_ghost(ys[0].data_ptr(), HIGH, buf.data_ptr()); slabs[1].vec_halo_add(ys[1].data_ptr(), LOW, buf.data_ptr())
+        slabs[1].vec_halo_pack_ghost(ys[1].data_ptr(), LOW, buf.data_ptr()); slabs[0].vec_halo_add(ys[0].data_ptr(), HIGH, buf.data_ptr())
+        got = np.zeros_like(q)
+        for s, yv in zip(slabs, ys):
+            s.vec_to_host(yv.data_ptr(), got)
+        assert np.abs(got - want[mat]).max() <= 1e-12 * np.abs(want[mat]).max(), mat
+        # ghost rows were cleared by the pack: the flat dot products of the Krylov iteration see owned cells only
+        assert float(torch.dot(ys[0], ys[0]) + torch.dot(ys[1], ys[1])) == pytest.approx(float((got * got).sum()), rel=1e-12)
+    for s in slabs + [one]:
+        s.close()

@@ -114,3 +114,63 @@ def test_two_gpu_implicit_step_over_nccl_equals_one_gpu(ntrans):
         assert np.abs(l2 - l2_one).max() <= 1e-10 * np.abs(l2_one).max()
     dq = want - q
     assert np.abs(got - want).max() <= 1e-8 * np.abs(dq).max(), np.abs(got - want).max() / np.abs(dq).max()
+
+
+def _adjoint_worker(rank, world, port, nic, njc, ntrans, g, out):
+    import os
+
+    import torch
+    import torch.distributed as dist
+    from structured_b200.api import GpuEulerEquation
+    from structured_b200.slab import SlabLinearSolver, partition_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4, periodic=False)
+        q = case.perturbed_q(0.02)
+        j0, j1 = partition_rows(njc, world)[rank]
+        eq = GpuEulerEquation(case, device=rank, j_begin=j0, j_end=j1)
+        eq.set_state(q)
+        eq.jacobian_device()
+        solver = SlabLinearSolver(eq, rank, world, dist, torch.device("cuda", rank))
+        psi, info = solver.adjoint_solve(g, cfl=1e4, max_steps=12, tol=1e-9, precond="line_j", restart=60, max_iter=600, rtol=1e-6)
+        rows = eq.vec_to_host(psi.data_ptr())[:, j0:j1, :]
+        out.put((rank, j0, j1, rows, info))
+        eq.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs two GPUs")
+def test_two_gpu_adjoint_solve_equals_one_gpu():
+    """J^T psi = -g on two j-slabs over NCCL (transposed products: each slab's share of the neighbour's rows is exchanged
+    and added; inner products all-reduced) against sgpu_adjoint_solve on one GPU.  Laminar: the well-posed case."""
+    import socket
+
+    import torch.multiprocessing as mp
+    from structured_b200.api import GpuEulerEquation
+    nic, njc, ntrans = 96, 64, 0
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4, periodic=False)
+    q = case.perturbed_q(0.02)
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal(q.shape)
+    one = GpuEulerEquation(case, device=0)
+    one.set_state(q); one.jacobian_device()
+    want, winfo = one.adjoint_solve(g, cfl=1e4, max_steps=12, tol=1e-9, precond="line_j", restart=60, max_iter=600, rtol=1e-6)
+    assert winfo["rel_residual"] <= 1e-9, winfo
+    one.close()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_adjoint_worker, args=(r, 2, port, nic, njc, ntrans, g, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    got = np.zeros_like(want)
+    for rank, j0, j1, rows, info in res:
+        assert info["rel_residual"] <= 1e-9, info
+        got[:, j0:j1, :] = rows
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()

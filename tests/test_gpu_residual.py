@@ -296,3 +296,34 @@ def test_solution_files_roundtrip_through_device(tmp_path):
     assert np.array_equal(z["q"], q) and np.array_equal(z["p"], p) and np.array_equal(z["T"], T)
     assert z["xc"].shape == (case.nic, case.njc)
     eq.close()
+
+
+def test_grid_from_binary_file_equals_host_arrays(tmp_path):
+    """sgpu_set_grid_file (N3): vertex rows straight from the binary file into the device planes -- whole grid and a slab
+    that reads only its window -- must give the metrics and the residual of sgpu_set_grid bit for bit"""
+    from structured_b200.api import SgpuError
+    from structured_b200.cases import write_grid_bin
+    case = turbulent_channel_case(150, 64, ntrans=1, reynolds=1e5)
+    path = str(tmp_path / "grid.bin")
+    write_grid_bin(path, case.xv, case.yv)
+    q = case.perturbed_q()
+    ref = gpu_eq(case)
+    want_m, want_r = ref.metrics(), ref.calc_residual(q)
+    ref.close()
+    for (j0, j1) in ((0, 0), (0, 30), (30, 64)):
+        eq = gpu_eq(case, j_begin=j0, j_end=j1)
+        eq.set_grid_file(path)
+        a, b = (0, case.njc) if j1 == 0 else (j0, j1)
+        got = eq.metrics()
+        assert np.array_equal(got[0][:, a:b], want_m[0][:, a:b]) and np.array_equal(got[1][:, a:b + 1], want_m[1][:, a:b + 1])
+        assert np.array_equal(got[2][:, a:b], want_m[2][:, a:b])
+        eq.set_state(q)
+        eq.residual_device(0)
+        out = np.zeros_like(want_r); eq.get_rhs(out=out)
+        assert np.array_equal(out[:, a:b], want_r[:, a:b])
+        eq.close()
+    eq = gpu_eq(case)
+    (tmp_path / "bad.bin").write_bytes(b"garbage!" + bytes(64))
+    with pytest.raises(SgpuError, match="file format not found"):
+        eq.set_grid_file(str(tmp_path / "bad.bin"))
+    eq.close()
