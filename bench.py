@@ -531,6 +531,36 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             laminar = {"unavailable": str(ex)[:160]}
 
+    # ---- BASELINE.json config 2: SA flat plate, ~1 M cells (slipwall -> wall junction, freestream / outflow, wall distance
+    #      computed on the device): residual kernel and Jacobian build on one GPU
+    plate = None
+    if world == 1 and args.ntrans == 1 and not args.no_jacobian:
+        try:
+            from structured_b200.cases import flat_plate_case
+            pcase = flat_plate_case(1024, 1024)
+            t0w = time.time()
+            peq = GpuEulerEquation(pcase, device=local)            # includes sgpu_wall_distance_from_bcs (820 wall edges x 1 M cells)
+            peq.synchronize()
+            setup_s = time.time() - t0w
+            peq.set_state(pcase.perturbed_q())
+            for _ in range(3):
+                peq.residual_device(0)
+            peq.enable_kernel_timing(True)
+            for _ in range(20):
+                peq.residual_device(0)
+            pk = float(np.mean(peq.kernel_times()))
+            peq.jacobian_device()
+            _, pj = peq.jacobian_device()
+            peq.close()
+            pc = 1024 * 1024
+            plate = {"workload": "SA flat plate 1024x1024 cells (BASELINE.json config 2), MUSCL+Roe+viscous, nv=5, fp64",
+                     "residual_kernel_ms": round(pk, 4), "residual_Mcell_per_s": round(pc / (pk * 1e-3) / 1e6, 1),
+                     "residual_roofline_frac": round(pc * B_PER_CELL[5] / (pk * 1e-3) / 1e9 / measured_peak()[0], 4),
+                     "jacobian_build_ms": round(pj, 4), "jacobian_roofline_frac": round(pc * JAC_B_PER_CELL[5] / (pj * 1e-3) / 1e9 / measured_peak()[0], 4),
+                     "context_setup_s_incl_wall_distance": round(setup_s, 3)}
+        except Exception as ex:  # noqa: BLE001
+            plate = {"unavailable": str(ex)[:160]}
+
     peak, peak_src = measured_peak()
     kt = float(np.mean(ktimes)) if len(ktimes) else None
     achieved = cells_local * B_PER_CELL[nv] / (kt * 1e-3) / 1e9 if kt else None
@@ -593,7 +623,7 @@ def run_ours(args):
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "halo_check": halo_check,
+               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check,
                "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()

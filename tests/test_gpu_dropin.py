@@ -149,7 +149,9 @@ def test_sa_flat_plate_through_the_cpp_dropin_equals_the_python_api(tmp_path, mo
     assert np.array_equal(npz["q"], q5[..., :4])                  # the reference's writer got the mean-flow variables
     eq = GpuEulerEquation(case)
     eq.initialize()
-    for _ in range(n_it + 1):                                     # Solver::solve: steps 0 .. iteration_max update, the next one only evaluates
+    # Solver::solve calls step for counter = 0 .. iteration_max + 1: the implicit branch skips the update in the last call
+    # (src/solver/solver.cpp:154), the explicit branch updates in every call (:103-116)
+    for _ in range(n_it + 1 if mode == "implicit_device" else n_it + 2):
         if mode == "implicit_device":
             eq.implicit_step(case.cfl, 1.0, precond="line_j", restart=60, max_iter=2000, rtol=1e-13)
         else:
