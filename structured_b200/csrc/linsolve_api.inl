@@ -144,7 +144,7 @@ static int lin_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, int 
 // w -= V h (h = L->hdev[0 .. cnt)) and L->hdev[cnt] = |w|^2 of the result, one pass
 static int lin_gs_update(sgpu_ctx* c, double* w, const double* V, int cnt) {
     LinWork* L = c->lin;
-    gs_update_kernel<<<L->blocks, 256, 0, c->stream>>>(w, V, L->n, cnt, L->hdev, L->partial, L->ldp, cnt, L->hdev, L->ticket);
+    gs_update_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V, L->n, cnt, L->hdev, L->partial, L->ldp, cnt, L->hdev, L->ticket);
     CKL(c); c->launches++;
     return SGPU_OK;
 }

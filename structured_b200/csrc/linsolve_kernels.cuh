@@ -637,17 +637,33 @@ __device__ __forceinline__ void last_block_reduce(double* __restrict__ partial, 
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// Both Gram-Schmidt kernels walk the vectors TILE-major: a block holds GS_PER consecutive elements per thread of w in
+// registers and visits the basis vectors one after the other, so at any moment it streams ONE 16 KB-contiguous run of
+// one vector (an element-major loop reads k + 2 vectors at once per warp: ~20 concurrently open DRAM pages per block,
+// measured 3.5 TB/s; tile-major restores long sequential bursts).
+constexpr int GS_PER = 8;                                          // elements per thread and tile
+constexpr int GS_TILE = DOT_THREADS*GS_PER;
+
 // out[j0 .. j0+cnt) = w . V_j  (cnt <= DOT_GROUP basis vectors per pass over w)
 __global__ void __launch_bounds__(DOT_THREADS) dots_kernel(const double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt,
                                                            double* __restrict__ partial, int ldp, int j0, double* __restrict__ out, unsigned* ticket) {
     double acc[DOT_GROUP];
 #pragma unroll
     for (int j = 0; j < DOT_GROUP; j++) acc[j] = 0.0;
-    const size_t stride = (size_t)gridDim.x*blockDim.x;
-    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
-        const double we = w[e];
+    for (size_t t0 = (size_t)blockIdx.x*GS_TILE; t0 < n; t0 += (size_t)gridDim.x*GS_TILE) {
+        double we[GS_PER];
 #pragma unroll
-        for (int j = 0; j < DOT_GROUP; j++) if (j < cnt) acc[j] += we*V[(size_t)j*n + e];
+        for (int p = 0; p < GS_PER; p++) { const size_t e = t0 + (size_t)p*DOT_THREADS + threadIdx.x; we[p] = e < n ? w[e] : 0.0; }
+#pragma unroll
+        for (int j = 0; j < DOT_GROUP; j++) {
+            if (j < cnt) {
+                const double* Vj = V + (size_t)j*n;
+                double a = 0.0;
+#pragma unroll
+                for (int p = 0; p < GS_PER; p++) { const size_t e = t0 + (size_t)p*DOT_THREADS + threadIdx.x; a += we[p]*(e < n ? Vj[e] : 0.0); }
+                acc[j] += a;
+            }
+        }
     }
     __shared__ double ws[DOT_GROUP][DOT_THREADS/32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -668,24 +684,30 @@ __global__ void __launch_bounds__(DOT_THREADS) dots_kernel(const double* __restr
 
 // w -= sum_j h[j] V_j  and, in the same pass, out[ncol] = |w_new|^2  (h on the device: no host round trip between the
 // projection and the update, and no extra pass over w for the norm of the next basis vector)
-__global__ void __launch_bounds__(256) gs_update_kernel(double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ h,
-                                                        double* __restrict__ partial, int ldp, int ncol, double* __restrict__ out, unsigned* ticket) {
-    const size_t stride = (size_t)gridDim.x*blockDim.x;
+__global__ void __launch_bounds__(DOT_THREADS) gs_update_kernel(double* __restrict__ w, const double* __restrict__ V, size_t n, int cnt, const double* __restrict__ h,
+                                                                double* __restrict__ partial, int ldp, int ncol, double* __restrict__ out, unsigned* ticket) {
     double acc = 0.0;
-    for (size_t e = (size_t)blockIdx.x*blockDim.x + threadIdx.x; e < n; e += stride) {
-        double s = w[e];
-        for (int j = 0; j < cnt; j++) s -= h[j]*V[(size_t)j*n + e];
-        w[e] = s;
-        acc += s*s;
+    for (size_t t0 = (size_t)blockIdx.x*GS_TILE; t0 < n; t0 += (size_t)gridDim.x*GS_TILE) {
+        double s[GS_PER];
+#pragma unroll
+        for (int p = 0; p < GS_PER; p++) { const size_t e = t0 + (size_t)p*DOT_THREADS + threadIdx.x; s[p] = e < n ? w[e] : 0.0; }
+        for (int j = 0; j < cnt; j++) {
+            const double hj = h[j];
+            const double* Vj = V + (size_t)j*n;
+#pragma unroll
+            for (int p = 0; p < GS_PER; p++) { const size_t e = t0 + (size_t)p*DOT_THREADS + threadIdx.x; s[p] -= hj*(e < n ? Vj[e] : 0.0); }
+        }
+#pragma unroll
+        for (int p = 0; p < GS_PER; p++) { const size_t e = t0 + (size_t)p*DOT_THREADS + threadIdx.x; if (e < n) { w[e] = s[p]; acc += s[p]*s[p]; } }
     }
-    __shared__ double ws[8];
+    __shared__ double ws[DOT_THREADS/32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
     if (lane == 0) ws[wid] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int k = 0; k < 8; k++) s += ws[k];
+        for (int k = 0; k < DOT_THREADS/32; k++) s += ws[k];
         partial[(size_t)blockIdx.x*ldp + ncol] = s;
     }
     last_block_reduce(partial, ldp, ncol, 1, out, ticket);
