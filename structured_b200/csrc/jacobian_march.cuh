@@ -407,6 +407,46 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
             return;
         }
         const double Vi = M8.Vi;
+        if (!inner) {
+            // radius-2 arm: ONE face, the cell is its LL or RR line cell -- only the reconstruction chain of (rho, u, v, p), so
+            // the block is d(-F)/d(ql or qr) . diag(limiter derivative) . dW/dq with an empty q4 column (3.1 k -> cycles of the
+            // generic path spent mostly on its bookkeeping)
+            const unsigned ent = (unsigned)(desc >> 16) & 255u;
+            const int f = (int)(ent & 3u), lr = (int)((ent >> 2) & 7u) - 1;
+            const double* core = (f < 2) ? sC + lane + f : sE + ((jl + f) & 1)*Cfg::C_DBL + lane;
+            const double sc = (f & 1) ? Vi : -Vi;
+            const double* Fd = core + (Cfg::C_FD + (lr == 0 ? 0 : 4))*32;          // LL: d/d ql, RR: d/d qr
+            const double* dp = core + (lr == 0 ? Cfg::C_DL : Cfg::C_DR + 2)*32;    // LL: dl[k][0], RR: dr[k][2]
+            double nut_up = 0.0;
+            if (SA) {
+                const bool upL = core[Cfg::C_F0*32] >= 0.0;
+                const int st = upL ? 0 : 1;
+                const int udx = (f < 2) ? (f == JF_C0 ? -1 : 0) + st : 0, udy = (f < 2) ? 0 : (f == JF_E0 ? -1 : 0) + st;
+                const double* W = wrow(jl + udy);
+                nut_up = W[JW_RN*JM_RC + cc0 + udx]*W[JW_RI*JM_RC + cc0 + udx];
+            }
+            const double* W = wrow(jl + DY); const int cc = cc0 + DX;
+            const double u = W[JW_U*JM_RC + cc], vv = W[JW_V*JM_RC + cc], ri = W[JW_RI*JM_RC + cc];
+            const double ke = 0.5*(u*u + vv*vv);
+            double dk[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) dk[k] = ORDER == 2 ? -sc*dp[k*3*32] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double cwr[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) cwr[k] = Fd[((r < 4 ? r : 0)*8 + k)*32]*dk[k]*(r < 4 ? 1.0 : nut_up);
+                // chain_W (jacobian_kernel.cuh): d(rho, u, v, p)/dq of the arm cell
+                const double o0 = cwr[0] - (cwr[1]*u + cwr[2]*vv)*ri + cwr[3]*GM1*ke;
+                const double o1 = cwr[1]*ri - cwr[3]*GM1*u, o2 = cwr[2]*ri - cwr[3]*GM1*vv, o3 = cwr[3]*GM1;
+                if (cell_ok) {
+                    double* Jr = Jp + (size_t)(r*NV)*pl;
+                    __stcs(Jr, o0); __stcs(Jr + pl, o1); __stcs(Jr + 2*pl, o2); __stcs(Jr + 3*pl, o3);
+                    if (NV > 4) __stcs(Jr + 4*pl, 0.0);
+                }
+            }
+            return;
+        }
         double cw[5][4], cu[4], cv[4], cT3 = 0.0, cmu[5], cmut[4], cnut4 = 0.0, ex0 = 0.0, ex4 = 0.0;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -540,6 +580,8 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
     // core of face ra and the SA sensitivities of row ra -- through the SAME call sites as every other row (one inlined
     // copy of each routine: smaller code, and chunk seams cannot change a bit of the result).
 #ifdef JM_TIMING
+    __shared__ unsigned long long s_ttask[16];
+    if (threadIdx.x < 16) s_ttask[threadIdx.x] = 0;
     long long tA = 0, tB = 0, tW = 0, t0, t1;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
 #define JM_T(acc) { asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) :: "memory"); acc += t1 - t0; t0 = t1; }
@@ -574,12 +616,19 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
                 n = __shfl_sync(0xffffffffu, n, 0);
                 if (n >= JM_NTASK) break;
                 const int task = (int)((JM_TASKS >> (4*n)) & 15ull);
+#ifdef JM_TIMING
+                long long tt0, tt1; asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt0) :: "memory");
+#endif
                 if (task < 13) { if (task < NS) assemble_slot(task, jl, M8); }
                 else if (more) {
                     if (task == 13) sa_prep(jl + 1);
                     else if (task == 14) convert_w_row(jl + 3);
                     else convert_z_row(jl + 2);
                 }
+#ifdef JM_TIMING
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(tt1) :: "memory");
+                if (lane == 0) atomicAdd((unsigned long long*)&s_ttask[task], (unsigned long long)(tt1 - tt0));
+#endif
             }
         } else if (warp == 3 && JM_WARPS == 4) sa_prep(jl + 1);
         JM_T(tB)
@@ -591,6 +640,11 @@ __global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParam
     }
 #ifdef JM_TIMING
     if (lane == 0 && blockIdx.x % 997 == 5) printf("cta %d warp %d: phase A %lld  phase B %lld  barrier wait %lld cycles over %d rows\n", blockIdx.x, warp, tA, tB, tW, rb - ra);
+    if (threadIdx.x == 0 && blockIdx.x % 997 == 5) {
+        printf("cta %d task cycles per row:", blockIdx.x);
+        for (int k = 0; k < 16; k++) printf(" t%d=%lld", k, (long long)(s_ttask[k]/(unsigned long long)(rb - ra)));
+        printf("\n");
+    }
 #endif
 #undef JM_T
 }
