@@ -149,7 +149,10 @@ __global__ void jac_geom_kernel(View v, Metrics m, double* __restrict__ gchi, do
 }
 
 template <int NV, int ORDER, int FLUX, bool VISC>
-__global__ void __launch_bounds__(32*JM_WARPS, 3) jac_march_kernel(const JmParams prm) {
+#ifndef JM_MINB
+#define JM_MINB 3
+#endif
+__global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const JmParams prm) {
     using Cfg = JmCfg<NV, ORDER, VISC>;
     constexpr bool SA = Cfg::SA;
     constexpr int NWV = Cfg::NWV, NZV = Cfg::NZV;
