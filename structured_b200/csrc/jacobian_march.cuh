@@ -31,6 +31,19 @@ constexpr int JM_CELLS = 31;            // cells per strip; lane 31 only owns th
 constexpr int JM_WARPS = JM_NWARPS;     // 4 face-core warps; 5 = one more that prepares the rings / SA sensitivities during phase A (measured slower: 128 registers, 33.9 vs 24.5 ms)
 constexpr int JM_RC = 36;               // ring columns: cells i0-2 .. i0+33
 
+// viscous part of a core.  JM_RICH: the face-only products of the viscous-flux coefficients and the geometry weights of the four
+// cell classes are formed ONCE per face in phase A (26 values) instead of per (slot, face) pair in phase B (11 raw values + 4 plane
+// loads): 83 doubles per core, 2 CTAs per SM (measured equal to 3 for this kernel).
+#ifndef JM_RICH
+#define JM_RICH 1
+#endif
+#if JM_RICH
+enum { JV_UB = 0, JV_VB, JV_GMU1, JV_GMU2, JV_GMU3, JV_WX0, JV_WY0, JV_WX1, JV_WY1, JV_WXP, JV_WYP, JV_WXM, JV_WYM,           // half 0
+       JV_MU, JV_A1, JV_A2, JV_A3, JV_A4, JV_A5, JV_A6, JV_K1, JV_K2, JV_GK3, JV_GN, JV_MSX, JV_MSY, JV_COUNT };              // half 1
+#else
+enum { JV_MU = 0, JV_KK, JV_UB, JV_VB, JV_TXX, JV_TYY, JV_TXY, JV_TX, JV_TY, JV_GN, JV_MUSA, JV_COUNT };
+#endif
+
 template <int V> struct IC { static constexpr int value = V; };   // compile-time int passed through generic lambdas
 
 template <int NV, int ORDER, bool VISC> struct JmCfg {
@@ -38,13 +51,13 @@ template <int NV, int ORDER, bool VISC> struct JmCfg {
     static constexpr int NWV = 6;                                   // ring W: rho, u, v, p, 1/rho, rho nu~
     static constexpr int NZV = VISC ? (SA ? 6 : 3) : 1;             // ring Z: T, mu, dmu/dT [, mu_t, c_mt, dmu_t/dq4]
     static constexpr int C_FD = 0, C_F0 = 32, C_DL = 33, C_DR = C_DL + (ORDER == 2 ? 12 : 0), C_V = C_DR + (ORDER == 2 ? 12 : 0);
-    static constexpr int CORE = C_V + (VISC ? 11 : 0);
+    static constexpr int CORE = C_V + (VISC ? JV_COUNT : 0);
     static constexpr int W_DBL = 6*NWV*JM_RC, Z_DBL = 4*NZV*JM_RC, C_DBL = CORE*32, S_DBL = SA ? 2*7*32 : 0;
     static constexpr size_t smem_bytes = sizeof(double)*(size_t)(W_DBL + Z_DBL + 3*C_DBL + S_DBL + 2);
 };
 enum { JW_R = 0, JW_U, JW_V, JW_P, JW_RI, JW_RN };
 enum { JZ_T = 0, JZ_MU, JZ_DMUDT, JZ_MUT, JZ_CMT, JZ_DMUT4 };
-enum { JV_MU = 0, JV_KK, JV_UB, JV_VB, JV_TXX, JV_TYY, JV_TXY, JV_TX, JV_TY, JV_GN, JV_MUSA };
+
 enum { JF_C0 = 0, JF_C1 = 1, JF_E0 = 2, JF_E1 = 3 };   // chi face i (-), chi face i+1 (+), eta face j (-), eta face j+1 (+)
 enum { JC_NONE = -1, JC_D0 = 0, JC_D1 = 1, JC_P = 2, JC_M = 3 };
 
@@ -150,7 +163,7 @@ __global__ void jac_geom_kernel(View v, Metrics m, double* __restrict__ gchi, do
 
 template <int NV, int ORDER, int FLUX, bool VISC>
 #ifndef JM_MINB
-#define JM_MINB 3
+#define JM_MINB (JM_RICH ? 2 : 3)
 #endif
 __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const JmParams prm) {
     using Cfg = JmCfg<NV, ORDER, VISC>;
@@ -334,6 +347,31 @@ __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const J
             auto gx = [&](int k) { return xD0*sD0[k] + xD1*sD1[k] + xP*sP[k] + xM*sM[k]; };
             auto gy = [&](int k) { return yD0*sD0[k] + yD1*sD1[k] + yP*sP[k] + yM*sM[k]; };
             auto bar = [&](int k) { return 0.375*(sD0[k] + sD1[k]) + 0.0625*(sP[k] + sM[k]); };
+#if JM_RICH
+            if (half == 0) {
+                const double ux = gx(0), uy = gy(0), vx = gx(1), vy = gy(1);
+                const double div = ux + vy;
+                const double ub = bar(0), vb = bar(1);
+                const double txx_h = 2.0*ux - (2.0/3.0)*div, tyy_h = 2.0*vy - (2.0/3.0)*div, txy_h = uy + vx;   // tau / mu (flux.cpp:36-45)
+                core[(Cfg::C_V + JV_UB)*32] = ub; core[(Cfg::C_V + JV_VB)*32] = vb;
+                core[(Cfg::C_V + JV_GMU1)*32] = txx_h*nx + txy_h*ny; core[(Cfg::C_V + JV_GMU2)*32] = txy_h*nx + tyy_h*ny;
+                core[(Cfg::C_V + JV_GMU3)*32] = nx*(ub*txx_h + vb*txy_h) + ny*(ub*txy_h + vb*tyy_h);
+                core[(Cfg::C_V + JV_WX0)*32] = xD0; core[(Cfg::C_V + JV_WY0)*32] = yD0; core[(Cfg::C_V + JV_WX1)*32] = xD1; core[(Cfg::C_V + JV_WY1)*32] = yD1;
+                core[(Cfg::C_V + JV_WXP)*32] = xP; core[(Cfg::C_V + JV_WYP)*32] = yP; core[(Cfg::C_V + JV_WXM)*32] = xM; core[(Cfg::C_V + JV_WYM)*32] = yM;
+            } else {
+                const double mub = bar(1), mutb = SA ? bar(2) : 0.0;
+                const double mu = mub + mutb, kk = SA ? (mub*g.cp_over_pr + mutb*g.cp_over_prt) : mub*g.cp_over_pr;
+                const double c43 = 4.0/3.0*mu, c23 = 2.0/3.0*mu;
+                core[(Cfg::C_V + JV_MU)*32] = mu;
+                core[(Cfg::C_V + JV_A1)*32] = c43*nx; core[(Cfg::C_V + JV_A2)*32] = mu*ny; core[(Cfg::C_V + JV_A3)*32] = -c23*nx;
+                core[(Cfg::C_V + JV_A4)*32] = -c23*ny; core[(Cfg::C_V + JV_A5)*32] = mu*nx; core[(Cfg::C_V + JV_A6)*32] = c43*ny;
+                core[(Cfg::C_V + JV_K1)*32] = kk*nx; core[(Cfg::C_V + JV_K2)*32] = kk*ny;
+                core[(Cfg::C_V + JV_GK3)*32] = nx*gx(0) + ny*gy(0);
+                const double musa_s = SA ? (mub + bar(4))*(1.0/SA_SIGMA) : 0.0;
+                core[(Cfg::C_V + JV_GN)*32] = SA ? (gx(3)*nx + gy(3)*ny)*(1.0/SA_SIGMA) : 0.0;
+                core[(Cfg::C_V + JV_MSX)*32] = musa_s*nx; core[(Cfg::C_V + JV_MSY)*32] = musa_s*ny;
+            }
+#else
             if (half == 0) {
                 const double ux = gx(0), uy = gy(0), vx = gx(1), vy = gy(1);
                 const double div = ux + vy;
@@ -348,6 +386,7 @@ __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const J
                 core[(Cfg::C_V + JV_GN)*32] = SA ? (gx(3)*nx + gy(3)*ny)*(1.0/SA_SIGMA) : 0.0;
                 core[(Cfg::C_V + JV_MUSA)*32] = SA ? (mub + bar(4))*(1.0/SA_SIGMA) : 0.0;
             }
+#endif
         }
     };
 
@@ -475,13 +514,13 @@ __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const J
             n_wx = __ldg(G + (JG_XD0 + 2*dcf)*pl); n_wy = __ldg(G + (JG_YD0 + 2*dcf)*pl);
         };
         unsigned ents = (unsigned)(desc >> 16);
-        if (VISC) geom_req(ents & 255u);
+        if (VISC && !JM_RICH) geom_req(ents & 255u);
 #pragma unroll 1
         for (int e = 0; e < nface; e++) {
             const unsigned ent = ents & 255u; ents >>= 8;
             const int f = (int)(ent & 3u), lr = (int)((ent >> 2) & 7u) - 1, dc = (int)((ent >> 5) & 7u) - 1;
             const double g_nx = n_nx, g_ny = n_ny, g_wx = n_wx, g_wy = n_wy;
-            if (VISC && e + 1 < nface) geom_req(ents & 255u);
+            if (VISC && !JM_RICH && e + 1 < nface) geom_req(ents & 255u);
             const double* core = (f < 2) ? sC + lane + f : sE + ((jl + f) & 1)*Cfg::C_DBL + lane;      // C0, C1 | E0 (face row jl), E1 (jl + 1)
             const double sc = (f & 1) ? Vi : -Vi;
             if (lr >= 0) {                                             // D = -F: reconstruction chain, line cells LL L | R RR
@@ -515,6 +554,27 @@ __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const J
                     }
                 }
             }
+#if JM_RICH
+            if (dc != JC_NONE) {                                       // viscous flux: the dual cell's six cells (flux.cpp:12-48 through mesh.cpp:10-131)
+                const double* cv_ = core + Cfg::C_V*32;
+                const double wx = sc*cv_[(JV_WX0 + 2*dc)*32], wy = sc*cv_[(JV_WY0 + 2*dc)*32], wb = sc*(dc <= JC_D1 ? 0.375 : 0.0625);
+                const double mu = cv_[JV_MU*32], ub = cv_[JV_UB*32], vb = cv_[JV_VB*32];
+                const double A1 = cv_[JV_A1*32], A2 = cv_[JV_A2*32], A3 = cv_[JV_A3*32], A4 = cv_[JV_A4*32], A5 = cv_[JV_A5*32], A6 = cv_[JV_A6*32];
+                const double gmu1 = cv_[JV_GMU1*32], gmu2 = cv_[JV_GMU2*32], gmu3 = cv_[JV_GMU3*32], gk3 = cv_[JV_GK3*32];
+                cu[1] += A1*wx + A2*wy;                    cv[1] += A2*wx + A3*wy;
+                cu[2] += A4*wx + A5*wy;                    cv[2] += A5*wx + A6*wy;
+                const double b2 = A5*vb + A2*ub;                       // mu (nx vb + ny ub)
+                cu[3] += (A1*ub + A4*vb)*wx + b2*wy + (mu*gmu1)*wb;
+                cv[3] += b2*wx + (A3*ub + A6*vb)*wy + (mu*gmu2)*wb;
+                cT3 += cv_[JV_K1*32]*wx + cv_[JV_K2*32]*wy;
+                cmu[1] += gmu1*wb; cmu[2] += gmu2*wb; cmu[3] += (gmu3 + gk3*g.cp_over_pr)*wb;
+                if (SA) {
+                    cmut[1] += gmu1*wb; cmut[2] += gmu2*wb; cmut[3] += (gmu3 + gk3*g.cp_over_prt)*wb;
+                    cmu[4] += cv_[JV_GN*32]*wb;                        // G4 = (mub + rnb)/sigma (grad nut . n): d/d mu and d/d rn share gn wb
+                    cnut4 += cv_[JV_MSX*32]*wx + cv_[JV_MSY*32]*wy;
+                }
+            }
+#else
             if (dc != JC_NONE) {                                       // viscous flux: the dual cell's six cells (flux.cpp:12-48 through mesh.cpp:10-131)
                 const double nxf = g_nx, nyf = g_ny;
                 const double wx = sc*g_wx, wy = sc*g_wy, wb = sc*(dc <= JC_D1 ? 0.375 : 0.0625);
@@ -541,6 +601,7 @@ __global__ void __launch_bounds__(32*JM_WARPS, JM_MINB) jac_march_kernel(const J
                     cnut4 += musa_s*(wx*nxf + wy*nyf);
                 }
             }
+#endif
         }
         // SA source row (rhs[4] += S V then / V): weights of this cell in the cell-centred gradients
         double s_cu = 0.0, s_cv = 0.0, s_cn = 0.0, s_rho = 0.0, s_mu = 0.0;
