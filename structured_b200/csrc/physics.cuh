@@ -1,6 +1,11 @@
-// Device-side physics of the residual path, written from the reference's formulas (cited per
-// function, paths relative to the reference tree).  Templated on the scalar type S so that the same
-// statements run on `double` (residual kernel) and on small forward-mode dual numbers (Jacobian kernel).
+// Device-side physics of the residual path (cited per function, paths relative to the reference tree).  Templated on
+// the scalar type S so that the same statements run on `double` (residual kernel) and on small forward-mode dual numbers
+// (Jacobian kernel).
+// roe_flux and ausm_flux below FOLLOW THE REFERENCE'S OPERATION SEQUENCE (src/model/flux.cpp:51-146,150-224) statement by
+// statement and keep its identifiers (rlft, uav, b1..b7, aq1..aq4, plar, eplft): the 1e-12 parity bar on a flux whose terms
+// cancel leaves no freedom in the order of the dissipation sums.  What differs is the reciprocal / square-root structure (one
+// rsqrt of rho_L rho_R serves both 1/rho and the Roe weight, one rsqrt gives c and 1/c^2, MUFU seeds + third-order steps
+// instead of IEEE divisions) -- see the notes at each site.  Everything else in this file is written from the formulas.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -200,3 +200,23 @@ def test_field_inversion_size_2048x1024_properties():
     r1 = eq.calc_residual(q)
     assert np.abs(dRdb - (r1[..., 4] - r0[..., 4])).max() <= 1e-10 * np.abs(dRdb).max()
     eq.close()
+
+
+def test_row_window_export_equals_rows_of_the_full_export():
+    """sgpu_jacobian_coo_rows: the COO rows of a window of cell rows from the resident Jacobian = the same rows of
+    sgpu_jacobian_coo (global numbering, sorted, LHS transform included)"""
+    case = turbulent_channel_case(45, 28, ntrans=1, reynolds=2e4)
+    eq = gpu_eq(case)
+    q = case.perturbed_q(0.02)
+    eq.set_state(q); eq.calc_dt(4.0)
+    for lhs in (False, True):
+        ri, ci, va = eq.jacobian_coo(apply_lhs_transform=lhs)
+        for (j0, n) in ((0, 3), (11, 9), (25, 3), (0, 28)):
+            r2, c2, v2 = eq.jacobian_coo(apply_lhs_transform=lhs, rows=(j0, n))
+            cell_j = (ri // 5) % case.njc
+            keep = (cell_j >= j0) & (cell_j < j0 + n)
+            assert np.array_equal(r2, ri[keep]) and np.array_equal(c2, ci[keep]) and np.array_equal(v2, va[keep])
+    from structured_b200.api import SgpuError
+    with pytest.raises(SgpuError, match="do not intersect"):
+        eq.jacobian_coo(rows=(40, 5))
+    eq.close()

@@ -327,3 +327,17 @@ def test_grid_from_binary_file_equals_host_arrays(tmp_path):
     with pytest.raises(SgpuError, match="file format not found"):
         eq.set_grid_file(str(tmp_path / "bad.bin"))
     eq.close()
+
+
+def test_halo_exchange_refuses_a_missing_peer_instead_of_hanging():
+    """advisor finding: a slab with a neighbour but no registered peer buffer used to leave the neighbour's wait kernel
+    spinning forever; push / pull now fail loudly (and the device-side wait is bounded)"""
+    from structured_b200.api import SgpuError
+    case = turbulent_channel_case(64, 32, ntrans=0, reynolds=1e5)
+    lo = gpu_eq(case, j_begin=0, j_end=16)
+    lo.set_state(case.perturbed_q())
+    with pytest.raises(SgpuError, match="no peer receive buffer"):
+        lo.halo_push(0)
+    with pytest.raises(SgpuError, match="before the first halo push"):
+        lo.halo_pull(0)
+    lo.close()
