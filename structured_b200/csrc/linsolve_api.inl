@@ -92,10 +92,17 @@ static int lin_factor(sgpu_ctx* c, int matrix, int precond) {
     const int op = mat_op(matrix);
     CK(c, cudaMemsetAsync(L->err, 0, sizeof(int), c->stream));
     if (precond == SGPU_PC_LINE_J) {
-        const int nb = (v.nic + 31)/32;
+        const char* lf = getenv("SGPU_LINE_FACTOR");
+        const bool serial = lf && !strcmp(lf, "serial");            // the round-1 kernel (one lane per line), kept for A/B runs
 #define LINE_FACTOR(NV_) do { \
-        CK(c, cudaFuncSetAttribute(line_factor_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_ring_bytes<NV_>())); \
-        line_factor_kernel<NV_><<<nb, 32, fact_ring_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); } while (0)
+        if (serial) { \
+            CK(c, cudaFuncSetAttribute(line_factor_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_ring_bytes<NV_>())); \
+            line_factor_kernel<NV_><<<(v.nic + 31)/32, 32, fact_ring_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); \
+        } else { \
+            const int lpw = factr_lines<NV_>(); \
+            CK(c, cudaFuncSetAttribute(line_factor_rows_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factr_ring_bytes<NV_>())); \
+            line_factor_rows_kernel<NV_><<<(v.nic + lpw - 1)/lpw, 32, factr_ring_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); \
+        } } while (0)
         if (v.nv == 5) LINE_FACTOR(5); else LINE_FACTOR(4);
 #undef LINE_FACTOR
     } else {

@@ -430,6 +430,161 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-parallel form of line_factor_kernel (round 2).  The recurrence is sequential in j and the kernel above gives the
+// whole GPU nic/32 warps (128 at 4096^2: less than one per SM), each executing ~1 500 dependent instructions per row.
+// Here a line is worked on by NV lanes -- lane (l, r) holds ROW r of every block of line l -- so a warp covers 32/NV lines,
+// the machine gets NV x the warps, and the per-row dependency chain shrinks to a row's share:
+//   products   T = A B      : lane r forms row r of T; the rows of B come from the line's other lanes by shuffle
+//   inversion  Gauss-Jordan : per column the pivot lane (largest |entry| among the rows not yet used, the choice partial
+//                             pivoting makes) scales and broadcasts its row, all other lanes eliminate; no row swaps --
+//                             the lane that pivoted on column k ends up holding row k of the inverse, one final gather
+// Same arithmetic per row as invert_block / matmul_block.  Rows ahead are streamed through a cp.async ring exactly like
+// above, each lane copying the words of ITS row of the five blocks (+ 1/dt).
+// ------------------------------------------------------------------------------------------------
+constexpr int FACTR_STAGES = 6;
+template <int NV> constexpr int factr_lines() { return 32/NV; }
+template <int NV> constexpr int factr_words() { return 5*NV + 1; }                 // per lane and stage
+template <int NV> constexpr size_t factr_ring_bytes() { return (size_t)FACTR_STAGES*factr_words<NV>()*32*sizeof(double); }
+
+template <int NV>
+__global__ void __launch_bounds__(32) line_factor_rows_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, int nslots,
+                                                              double* __restrict__ F, int* __restrict__ err) {
+    extern __shared__ double fring[];
+    constexpr int B = NV*NV, LPW = 32/NV, NW = 5*NV + 1, S = FACTR_STAGES;
+    const int lane = threadIdx.x;
+    const int l = lane/NV, r = lane - l*NV;                        // line within the warp, block row
+    const bool lane_ok = l < LPW;
+    const int i = blockIdx.x*LPW + l;
+    const bool live = lane_ok && i < v.nic;
+    const int ic = (lane_ok && i < v.nic) ? i : v.nic - 1;          // idle lanes shadow the last line and never store
+    const int base = (lane_ok ? l : 0)*NV;                          // first lane of this line's group (idle lanes mirror group 0)
+    const unsigned full = 0xffffffffu;
+    const size_t pl = v.plane;
+    double* __restrict__ Dinv = F;
+    double* __restrict__ DA = F + (size_t)NV*NV*pl;
+    double* __restrict__ DC = F + (size_t)2*NV*NV*pl;
+    const bool arms = nslots > 9;
+    auto word = [&](int st, int w) -> double* { return fring + ((size_t)st*NW + w)*32 + lane; };
+    auto issue = [&](int jl) {                                     // ring group g = 0..4 <- Jacobian slots 0, 3, 11, 4, 12 (row r of each)
+        if (jl < v.njl) {
+            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            const int st = jl % S;
+#pragma unroll
+            for (int g = 0; g < 5; g++) {
+                const int sl = g == 0 ? 0 : (g == 1 ? 3 : (g == 2 ? 11 : (g == 3 ? 4 : 12)));
+                if ((g == 2 || g == 4) && !arms) continue;
+#pragma unroll
+                for (int c = 0; c < NV; c++) fact_cp_async8(word(st, g*NV + c), J + ((size_t)sl*B + r*NV + c)*pl + o);
+            }
+            if (op == OP_LHS) fact_cp_async8(word(st, 5*NV), dt + o);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto ring_row = [&](int st, int g, double idt, bool diag, double (&a)[NV]) {   // A = -J + I/dt for OP_LHS, J otherwise
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            const double vj = *word(st, g*NV + c);
+            a[c] = op == OP_LHS ? ((diag && r == c) ? idt - vj : -vj) : vj;
+        }
+    };
+    // row r of X Y, the rows of Y held by the line's lanes
+    auto rowmul = [&](const double (&x)[NV], const double (&y)[NV], double (&t)[NV]) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) t[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) t[c] += x[k]*__shfl_sync(full, y[c], base + k);
+    };
+    for (int jl = 0; jl < S - 1; jl++) issue(jl);
+    double DCp[NV];                                                // row r of DC_{j-1}
+#pragma unroll
+    for (int c = 0; c < NV; c++) DCp[c] = 0.0;
+    for (int jl = 0; jl < v.njl; jl++) {
+        issue(jl + S - 1);
+        asm volatile("cp.async.wait_group %0;" :: "n"(S - 1) : "memory");
+        const int st = jl % S;
+        const int gj = v.j0 + jl;
+        const size_t o = v.at(jl + JOFF, ic + IOFF);
+        double D[NV], A[NV], T[NV], I[NV];
+        ring_row(st, 0, op == OP_LHS ? 1.0/(*word(st, 5*NV)) : 0.0, true, D);
+        const bool lo = jl > 0, hi = jl + 1 < v.njl;
+        if (lo) {
+            ring_row(st, 1, 0.0, false, A);
+            if (arms && gj - 2 >= 0) {
+                ring_row(st, 2, 0.0, false, T);
+#pragma unroll
+                for (int c = 0; c < NV; c++) A[c] += T[c];
+            }
+            rowmul(A, DCp, T);
+#pragma unroll
+            for (int c = 0; c < NV; c++) D[c] -= T[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < NV; c++) A[c] = 0.0;
+        }
+        // ---- Gauss-Jordan across the NV lanes of the line
+#pragma unroll
+        for (int c = 0; c < NV; c++) I[c] = r == c ? 1.0 : 0.0;
+        bool used = false; int pcol = -1;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double mine = used ? -1.0 : fabs(D[k]);
+            double big = -1.0; int p = 0;
+#pragma unroll
+            for (int q = 0; q < NV; q++) {                         // first maximum in lane order = the row partial pivoting swaps in
+                const double t = __shfl_sync(full, mine, base + q);
+                if (t > big) { big = t; p = q; }
+            }
+            const double piv = __shfl_sync(full, D[k], base + p);
+            if (piv == 0.0 && lane_ok) atomicExch(err, 1);
+            const double ip = 1.0/(piv == 0.0 ? 1.0 : piv);
+            const bool me = r == p;
+            if (me) {
+#pragma unroll
+                for (int c = 0; c < NV; c++) { D[c] *= ip; I[c] *= ip; }
+                used = true; pcol = k;
+            }
+            const double f = me ? 0.0 : D[k];
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                const double pd = __shfl_sync(full, D[c], base + p), pi = __shfl_sync(full, I[c], base + p);
+                if (!me) { D[c] -= f*pd; I[c] -= f*pi; }
+            }
+        }
+        {   // the lane that pivoted on column k holds row k of the inverse: bring row r to lane r
+            int src = 0;
+#pragma unroll
+            for (int q = 0; q < NV; q++) { const int pc = __shfl_sync(full, pcol, base + q); if (pc == r) src = q; }
+#pragma unroll
+            for (int c = 0; c < NV; c++) I[c] = __shfl_sync(full, I[c], base + src);
+        }
+        rowmul(I, A, T);                                           // DA = D'^-1 A'
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[c]; DA[(size_t)(r*NV + c)*pl + o] = T[c]; }
+        }
+        if (hi) {
+            ring_row(st, 3, 0.0, false, A);
+            if (arms && gj + 2 <= v.njc - 1) {
+                ring_row(st, 4, 0.0, false, T);
+#pragma unroll
+                for (int c = 0; c < NV; c++) A[c] += T[c];
+            }
+            rowmul(I, A, DCp);                                     // DC = D'^-1 C'
+        } else {
+#pragma unroll
+            for (int c = 0; c < NV; c++) DCp[c] = 0.0;
+        }
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) DC[(size_t)(r*NV + c)*pl + o] = DCp[c];
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // z = M^-1 r:  forward  t_j = Dinv_j r_j - DA_j t_{j-1},  backward  z_j = t_j - DC_j z_{j+1}.
 // transpose (M = L U with L = blockdiag(D') + lower(A'), U = I + upper(DC), so M^T = U^T L^T):
 //           forward  y_j = r_j - DC_{j-1}^T y_{j-1},  backward  w_j = y_j - DA_{j+1}^T w_{j+1},  z_j = Dinv_j^T w_j.
