@@ -92,8 +92,10 @@ static int lin_factor(sgpu_ctx* c, int matrix, int precond) {
     const int op = mat_op(matrix);
     CK(c, cudaMemsetAsync(L->err, 0, sizeof(int), c->stream));
     if (precond == SGPU_PC_LINE_J) {
+        // one lane per line (default) or NV lanes per line (SGPU_LINE_FACTOR=rows: 5x the warps and a shorter chain per lane, but the
+        // Gauss-Jordan pivot search / row broadcasts become dependent shuffles -- measured 29.2 vs 22.7 ms at 4096^2, identical factors)
         const char* lf = getenv("SGPU_LINE_FACTOR");
-        const bool serial = lf && !strcmp(lf, "serial");            // the round-1 kernel (one lane per line), kept for A/B runs
+        const bool serial = !(lf && !strcmp(lf, "rows"));
 #define LINE_FACTOR(NV_) do { \
         if (serial) { \
             CK(c, cudaFuncSetAttribute(line_factor_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_ring_bytes<NV_>())); \
