@@ -226,6 +226,24 @@ def test_full_size_4096_matches_oracle_and_properties():
     err = field_rel_err(rhs, want_rhs)
     assert err.max() <= TOL, err
     del want_rhs, port
+    # the Jacobian of the same 16.8 M-cell state (43.6 GB on the device): rows of ~2 600 cells -- bottom wall, top wall, interior --
+    # against the oracle evaluated on crops of the grid (tests/helpers.py::crop_case)
+    from helpers import TOL_SA_COUPLING, jac_rel_err_split, jac_worst, oracle_on_crop, rows_of_cells
+    from test_gpu_jacobian import check_pattern
+    slots, ms = eq.jacobian_device()
+    assert slots == 13 and ms > 0
+    ncells = 0
+    for box in ((2000, 2034, 0, 28), (777, 811, n - 28, n), (3000, 3034, 2040, 2074)):
+        _, (i0, i1, j0, j1), ref = oracle_on_crop(case, q, box)
+        ri, ci, va = eq.jacobian_coo(rows=(j0, j1 - j0))
+        cells = [(i, j) for i in range(i0, i1) for j in range(j0, j1)]
+        keep = np.isin(ri, rows_of_cells(n, 5, cells))
+        ours = (ri[keep], ci[keep], va[keep])
+        e1, e2 = jac_rel_err_split(q.size, ours, ref, 5)
+        assert e1 <= TOL and e2 <= TOL_SA_COUPLING, (box, e1, e2, jac_worst(q.size, ours, ref, 5, n))
+        check_pattern(q.size, ours, ref)
+        ncells += len(cells)
+    assert ncells >= 2000
     want = np.einsum("ijk,ijk->k", rhs, rhs)
     assert np.abs(l2 - want).max() <= 1e-12 * want.max()
     col_sum = rhs.sum(axis=0)                                  # [njc][nv] checksum per row
