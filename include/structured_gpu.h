@@ -245,6 +245,10 @@ int sgpu_linear_solve(sgpu_ctx* ctx, int matrix, const double* b, double* x, sgp
  * d objective / d beta = psi[..., 4] * sgpu_dres_dbeta (+ the explicit part). */
 int sgpu_adjoint_solve(sgpu_ctx* ctx, const double* g, double* psi, double cfl, int max_steps, double tol, sgpu_linsolve* io,
                        int* steps, double* rel_residual);
+/* The same with the pseudo-time step ramped like the forward solver's CFL ramp (Solver::solve, src/solver/solver.cpp:211-214):
+ * step k uses CFL_k = min(cfl0 * cfl_growth^k, cfl_max); dt and the preconditioner are rebuilt when the CFL changes. */
+int sgpu_adjoint_solve_ramp(sgpu_ctx* ctx, const double* g, double* psi, double cfl0, double cfl_growth, double cfl_max, int max_steps,
+                            double tol, sgpu_linsolve* io, int* steps, double* rel_residual);
 /* The whole ENABLE_ADOLC branch of Solver::step on the device (src/solver/solver.cpp:66-101,154-175):
  * calc_dt(cfl); rhs = residual(q) with solver.order; J = d residual(lhs_order)/dq; solve (-J + 1/dt) dq = rhs;
  * q += under_relaxation * dq (ls_eigen.cpp:66-70).  l2sq as in sgpu_residual. */

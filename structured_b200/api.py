@@ -26,7 +26,7 @@ SYMBOLS = [
     "sgpu_get_rhs", "sgpu_get_rhs_window", "sgpu_get_dt", "sgpu_calc_dt", "sgpu_residual", "sgpu_residual_host", "sgpu_residual_host_window", "sgpu_rk_stage",
     "sgpu_forward_euler", "sgpu_explicit_step", "sgpu_jacobian_coo", "sgpu_jacobian_coo_rows", "sgpu_jacobian_device", "sgpu_jacobian_apply", "sgpu_dres_dbeta",
     "sgpu_wall_data", "sgpu_track_wall", "sgpu_surface", "sgpu_surface_gradient",
-    "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve",
+    "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve", "sgpu_adjoint_solve_ramp",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_vec_halo_pack_ghost", "sgpu_vec_halo_add",
     "sgpu_vec_from_host", "sgpu_vec_to_host", "sgpu_op_apply",
     "sgpu_precond_setup", "sgpu_precond_apply",
@@ -402,15 +402,18 @@ class GpuEulerEquation:
         self._ck(self.L.sgpu_precond_apply(self.h, MATRICES[matrix], PRECONDS[precond], ctypes.c_void_p(r_ptr), ctypes.c_void_p(z_ptr)))
 
     def adjoint_solve(self, g: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
-                      restart: int = 40, max_iter: int = 400, rtol: float = 1e-3, reorthogonalize: bool = False):
+                      restart: int = 40, max_iter: int = 400, rtol: float = 1e-3, reorthogonalize: bool = False,
+                      cfl_growth: float = 1.0, cfl_max: Optional[float] = None):
         """Steady adjoint J^T psi = -g (g = d objective / d q) by pseudo-time continuation with transposed-LHS GMRES solves;
-        needs jacobian_device() at the converged state.  Returns (psi, info)."""
+        needs jacobian_device() at the converged state.  cfl_growth > 1 ramps the pseudo-time step like the forward solver's
+        CFL ramp (CFL_k = min(cfl * growth^k, cfl_max)).  Returns (psi, info)."""
         io = self._linsolve(precond, restart, max_iter, rtol, reorthogonalize)
         gg = np.ascontiguousarray(g, dtype=np.float64)
         psi = self._state_array()
         steps = ctypes.c_int(); rel = ctypes.c_double()
-        self._ck(self.L.sgpu_adjoint_solve(self.h, _dp(gg), _dp(psi), ctypes.c_double(cfl), max_steps, ctypes.c_double(tol), ctypes.byref(io),
-                                           ctypes.byref(steps), ctypes.byref(rel)))
+        self._ck(self.L.sgpu_adjoint_solve_ramp(self.h, _dp(gg), _dp(psi), ctypes.c_double(cfl), ctypes.c_double(cfl_growth),
+                                                ctypes.c_double(cfl if cfl_max is None else cfl_max), max_steps, ctypes.c_double(tol),
+                                                ctypes.byref(io), ctypes.byref(steps), ctypes.byref(rel)))
         info = self._linsolve_info(io)
         info.update({"steps": steps.value, "rel_residual": rel.value})
         return psi, info

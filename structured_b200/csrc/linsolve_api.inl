@@ -309,7 +309,16 @@ int sgpu_linear_solve(sgpu_ctx* c, int matrix, const double* b, double* x, sgpu_
 
 int sgpu_adjoint_solve(sgpu_ctx* c, const double* g, double* psi, double cfl, int max_steps, double tol, sgpu_linsolve* io,
                        int* steps_out, double* rel_out) {
-    if (!c || !g || !psi || !io) return SGPU_ERR_ARG;
+    return sgpu_adjoint_solve_ramp(c, g, psi, cfl, 1.0, cfl, max_steps, tol, io, steps_out, rel_out);
+}
+
+// The same continuation with the pseudo-time step RAMPED like the forward solver's CFL ramp (Solver::solve,
+// src/solver/solver.cpp:211-214): step k uses CFL_k = min(cfl0 * growth^k, cfl_max) -- dt and the line factors are rebuilt
+// when the CFL changes.  The SA adjoint operator is strongly non-normal: at a fixed moderate CFL the transient dominates for
+// tens of steps; the ramp damps it first and then approaches Newton on J^T psi = -g.
+int sgpu_adjoint_solve_ramp(sgpu_ctx* c, const double* g, double* psi, double cfl, double cfl_growth, double cfl_max, int max_steps, double tol,
+                            sgpu_linsolve* io, int* steps_out, double* rel_out) {
+    if (!c || !g || !psi || !io || !(cfl > 0.0) || !(cfl_growth >= 1.0)) return SGPU_ERR_ARG;
     CK(c, cudaSetDevice(c->device));
     if (int rc = sgpu_calc_dt(c, cfl)) return rc;
     if (int rc = lin_check(c, SGPU_MAT_LHS_T, io)) return rc;
@@ -337,7 +346,13 @@ int sgpu_adjoint_solve(sgpu_ctx* c, const double* g, double* psi, double cfl, in
         }
         if (rel <= stop || steps >= nmax) break;
         // (delta/dt - J^T) dpsi = rho, psi += dpsi: backward Euler on d psi/d tau = J^T psi + g
-        if (int rc = lin_gmres(c, SGPU_MAT_LHS_T, io, steps == 0)) return rc;
+        bool refactor = steps == 0;
+        if (steps > 0 && cfl_growth > 1.0 && cfl < cfl_max) {
+            cfl = std::min(cfl*cfl_growth, cfl_max);
+            if (int rc = sgpu_calc_dt(c, cfl)) return rc;
+            refactor = true;
+        }
+        if (int rc = lin_gmres(c, SGPU_MAT_LHS_T, io, refactor)) return rc;
         total_iters += io->iterations; setup += io->setup_ms; solve += io->solve_ms;
         axpby_kernel<<<L->blocks, 256, 0, c->stream>>>(L->psi, L->x, n, 1.0, 1.0); CKL(c); c->launches++;
         steps++;

@@ -41,6 +41,7 @@ struct ResParams {
     const double* wdist; const double* beta;
     double* partial;                    // [items][nv] sums of rhs^2, or nullptr
     double eps_chi, eps_eta, dpdx, dpdy;
+    double eps12_chi, epsh_chi, eps12_eta, epsh_eta;      // eps/12, eps/2 of the halved limiter form (muscl_cell2)
     int nstrips, nchunks, rpc;
     int row0, row1;                     // local cell rows [row0, row1) this launch covers (whole slab: 0, njl)
     int strip0;                         // first strip of this launch (column-chunked host pipeline), normally 0
@@ -87,21 +88,33 @@ __device__ __forceinline__ void face_net_flux(const Gas& g, const FaceGeom& fg, 
     D[0] = -F[0]; D[1] = -F[1]; D[2] = -F[2]; D[3] = -F[3];
     if (SA) D[4] = -((F[0] >= 0.0) ? F[0]*nutL : F[0]*nutR);      // first-order upwind on the face mass flux
     if (VISC) {
-        auto gradx = [&](int k) { return (fg.tx*qt[k] - fg.bx*qb[k] + fg.rx*qrr[k] - fg.lx*qll[k])*fg.ivol2; };   // mesh.cpp:83,127
-        auto grady = [&](int k) { return (fg.ty*qt[k] - fg.by*qb[k] + fg.ry*qrr[k] - fg.ly*qll[k])*fg.ivol2; };   // mesh.cpp:84,128
-        auto bar = [&](int k) { return 0.25*(qll[k] + qrr[k] + qt[k] + qb[k]); };                                 // mesh.cpp:18,29
-        const double ubar = bar(VU), vbar = bar(VV);
-        const double mub = bar(VM);
-        double mu = mub, kk;
-        if (SA) { const double mut = bar(VMT); kk = mub*g.cp_over_pr + mut*g.cp_over_prt; mu = mub + mut; }
-        else kk = mub*g.cp_over_pr;
-        double G[4];
-        viscous_flux<double>(fg.nx, fg.ny, gradx(VU), grady(VU), gradx(VV), grady(VV), gradx(VT), grady(VT), ubar, vbar, mu, kk, G);
-        D[1] += G[1]; D[2] += G[2]; D[3] += G[3];
+        // Green-Gauss sums and face averages stay UN-NORMALISED: G(k) = 2 V_dual grad q_k (mesh.cpp:83-84,127-128) and
+        // S(k) = 4 bar q_k (mesh.cpp:18,29); the factors 1/(2 V_dual) and 1/4 go into the viscosities once per face (every
+        // gradient enters the flux multiplied by mu, k or mu_sa), the 1/4 of ubar, vbar into one fma of the work term, and
+        // the SA source's face averages leave as 4 bar (phase 3 folds the 1/4 into 1/V).  Same formulas as viscous_flux<>
+        // (flux.cpp:12-48); differs by rounding only.  -10 fp64 instructions per face.
+        auto Gx = [&](int k) { return fg.tx*qt[k] - fg.bx*qb[k] + fg.rx*qrr[k] - fg.lx*qll[k]; };
+        auto Gy = [&](int k) { return fg.ty*qt[k] - fg.by*qb[k] + fg.ry*qrr[k] - fg.ly*qll[k]; };
+        auto S4 = [&](int k) { return (qll[k] + qrr[k]) + (qt[k] + qb[k]); };
+        const double Su = S4(VU), Sv = S4(VV), Sm = S4(VM);
+        const double iv4 = 0.25*fg.ivol2;
+        double mu, kk;
+        if (SA) { const double Smt = S4(VMT); kk = (Sm*g.cp_over_pr + Smt*g.cp_over_prt)*iv4; mu = (Sm + Smt)*iv4; }
+        else { kk = Sm*g.cp_over_pr*iv4; mu = Sm*iv4; }
+        const double dudx = Gx(VU), dudy = Gy(VU), dvdx = Gx(VV), dvdy = Gy(VV);
+        const double div = dudx + dvdy;
+        const double tau_xy = mu*(dudy + dvdx);
+        const double tau_xx = mu*(2.0*dudx - K23*div);
+        const double tau_yy = mu*(2.0*dvdy - K23*div);
+        const double ex = fma(0.25, Su*tau_xx + Sv*tau_xy, kk*Gx(VT));      // ubar tau_xx + vbar tau_xy - q_x
+        const double ey = fma(0.25, Su*tau_xy + Sv*tau_yy, kk*Gy(VT));
+        D[1] += tau_xx*fg.nx + tau_xy*fg.ny;
+        D[2] += tau_xy*fg.nx + tau_yy*fg.ny;
+        D[3] += ex*fg.nx + ey*fg.ny;
         if (SA) {
-            const double musa = mub + bar(VRN);
-            D[4] += musa*(1.0/SA_SIGMA)*(gradx(VN)*fg.nx + grady(VN)*fg.ny);
-            bars[0] = ubar; bars[1] = vbar; bars[2] = bar(VN);
+            const double musa = (Sm + S4(VRN))*(iv4*(1.0/SA_SIGMA));
+            D[4] += musa*(Gx(VN)*fg.nx + Gy(VN)*fg.ny);
+            bars[0] = Su; bars[1] = Sv; bars[2] = S4(VN);                  // 4 x the face averages
         }
     } else if (SA) { bars[0] = bars[1] = bars[2] = 0.0; }
 }
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         for (int k = 0; k < 4; k++) { q0_[k] = A[k*RW + t]; qm_[k] = A[k*RW + tm]; qp_[k] = A[k*RW + tp]; hi_[k] = lo_[k] = q0_[k]; }   // ghost / first order: the cell value (reconstruction.cpp:29-35)
         if (ORDER == 2) {
             double h2[4], l2[4];
-            muscl_cell2(qm_, q0_, qp_, prm.eps_chi, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps_chi, h2 + 2, l2 + 2);
+            muscl_cell2(qm_, q0_, qp_, prm.eps12_chi, prm.epsh_chi, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps12_chi, prm.epsh_chi, h2 + 2, l2 + 2);
 #pragma unroll
             for (int k = 0; k < 4; k++) { hi_[k] = col_int ? h2[k] : q0_[k]; lo_[k] = col_int ? l2[k] : q0_[k]; }
         }
@@ -230,7 +243,7 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         for (int k = 0; k < 4; k++) { q0_[k] = A0[k*RW + t]; qm_[k] = Am[k*RW + t]; qp_[k] = qp_reg ? qp_reg[k] : Ap[k*RW + t]; to_high[k] = to_low[k] = q0_[k]; }
         if (ORDER == 2) {
             double h2[4], l2[4];
-            muscl_cell2(qm_, q0_, qp_, prm.eps_eta, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps_eta, h2 + 2, l2 + 2);
+            muscl_cell2(qm_, q0_, qp_, prm.eps12_eta, prm.epsh_eta, h2, l2); muscl_cell2(qm_ + 2, q0_ + 2, qp_ + 2, prm.eps12_eta, prm.epsh_eta, h2 + 2, l2 + 2);
 #pragma unroll
             for (int k = 0; k < 4; k++) { to_high[k] = row_int ? h2[k] : q0_[k]; to_low[k] = row_int ? l2[k] : q0_[k]; }
         }
@@ -367,10 +380,11 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
                     const double cxr = M0[MCX*RW + t + 1], cyr = M0[MCY*RW + t + 1], cxl = M0[MCX*RW + t], cyl = M0[MCY*RW + t];
                     const double ext = M1[MEX*RW + t], eyt = M1[MEY*RW + t], exb = M0[MEX*RW + t], eyb = M0[MEY*RW + t];
                     const double ur = sFC[(NV + 0)*RW + t + 1], vr = sFC[(NV + 1)*RW + t + 1], nr = sFC[(NV + 2)*RW + t + 1];
-                    const double dvdx = (vr*cxr - bchi[1]*cxl + btop[1]*ext - bbot[1]*exb)*Vi;
-                    const double dudy = (ur*cyr - bchi[0]*cyl + btop[0]*eyt - bbot[0]*eyb)*Vi;
-                    dndx = (nr*cxr - bchi[2]*cxl + btop[2]*ext - bbot[2]*exb)*Vi;
-                    dndy = (nr*cyr - bchi[2]*cyl + btop[2]*eyt - bbot[2]*eyb)*Vi;
+                    const double Vi4 = 0.25*Vi;             // the faces hand over 4 x their averages
+                    const double dvdx = (vr*cxr - bchi[1]*cxl + btop[1]*ext - bbot[1]*exb)*Vi4;
+                    const double dudy = (ur*cyr - bchi[0]*cyl + btop[0]*eyt - bbot[0]*eyb)*Vi4;
+                    dndx = (nr*cxr - bchi[2]*cxl + btop[2]*ext - bbot[2]*exb)*Vi4;
+                    dndy = (nr*cyr - bchi[2]*cyl + btop[2]*eyt - bbot[2]*eyb)*Vi4;
                     om = fabs(dvdx - dudy);
                 }
                 const double mul = VISC ? Brow(jl)[BM*RW + t] : g.mu_ref;

@@ -547,6 +547,7 @@ static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms, int
     p.v = v; p.g = c->g; p.m = metrics_of(c);
     p.q = c->q[which]; p.rhs = c->rhs; p.wdist = c->wdist; p.beta = c->beta;
     p.eps_chi = c->eps_chi; p.eps_eta = c->eps_eta; p.dpdx = c->d.dpdx; p.dpdy = c->d.dpdy;
+    p.eps12_chi = c->eps_chi/12.0; p.epsh_chi = 0.5*c->eps_chi; p.eps12_eta = c->eps_eta/12.0; p.epsh_eta = 0.5*c->eps_eta;
     p.partial = want_norms ? (double*)1 : nullptr;              // placeholder: sized once the grid is known
     int grid = 0;
     const int order = lhs ? c->d.lhs_order : c->d.order;           // eulerequation.cpp:203-208

@@ -26,14 +26,20 @@ while i < len(L):
             i += 2
             continue
     i += 1
-best = None                                     # the row loop = the largest backward branch
+loops = []                                      # backward branches = loops
 for a, op, st, l in ins:
     if op.startswith('BRA'):
         t = re.search(r'BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)', l)
         if t:
             tgt = int(t.group(1), 16)
-            if tgt < a and (best is None or a - tgt > best[1] - best[0]):
-                best = (tgt, a)
+            if tgt < a: loops.append((tgt, a))
+loops.sort(key=lambda x: x[0] - x[1])           # largest first
+best = loops[0]                                 # the row loop = the largest loop that is not a wrapper around another big loop
+for cand in loops:                              # (the segment loop of the balanced partition contains the row loop)
+    inner = [x for x in loops if x != cand and cand[0] <= x[0] and x[1] <= cand[1] and (x[1] - x[0]) > 0.4*(cand[1] - cand[0])]
+    if not inner:
+        best = cand
+        break
 loop = [x for x in ins if best[0] <= x[0] <= best[1]]
 c = collections.Counter(x[1].split('.')[0] for x in loop)
 fp64 = sum(v for k, v in c.items() if k in ('DFMA', 'DMUL', 'DADD', 'DSETP', 'DMNMX'))
