@@ -53,8 +53,8 @@ struct sgpu_ctx {
     LinWork* lin = nullptr;              // device linear solve workspace (linsolve_api.inl)
     // pipelined host path
     bool pipe_init = false;
-    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_up[64] = {}, pipe_cmp[64] = {}, pipe_start = nullptr;
+    cudaStream_t pipe_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // transpose-in, compute, transpose-out, H2D copies, D2H copies
+    cudaEvent_t pipe_up[64] = {}, pipe_cmp[64] = {}, pipe_h2d[64] = {}, pipe_tout[64] = {}, pipe_d2h[64] = {}, pipe_start = nullptr;
     double* pipe_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pipe_stage_cap = 0;
     double* jac_scratch = nullptr; size_t jac_scratch_cap = 0; bool jac_two_stage = false;
     double* jgeo = nullptr; bool jgeo_valid = false;   // static face-geometry weight planes of the Jacobian build (jac_geom_kernel)
@@ -199,8 +199,8 @@ int sgpu_destroy(sgpu_ctx* c) {
     if (c->jgeo) cudaFree(c->jgeo);
     for (int k = 0; k < 4; k++) if (c->pipe_stage[k]) cudaFree(c->pipe_stage[k]);
     if (c->pipe_init) {
-        for (int k = 0; k < 3; k++) cudaStreamDestroy(c->pipe_stream[k]);
-        for (int k = 0; k < 64; k++) { cudaEventDestroy(c->pipe_up[k]); cudaEventDestroy(c->pipe_cmp[k]); }
+        for (int k = 0; k < 5; k++) cudaStreamDestroy(c->pipe_stream[k]);
+        for (int k = 0; k < 64; k++) { cudaEventDestroy(c->pipe_up[k]); cudaEventDestroy(c->pipe_cmp[k]); cudaEventDestroy(c->pipe_h2d[k]); cudaEventDestroy(c->pipe_tout[k]); cudaEventDestroy(c->pipe_d2h[k]); }
         cudaEventDestroy(c->pipe_start);
     }
     if (c->ghost_tab) cudaFree(c->ghost_tab);
@@ -596,27 +596,51 @@ int sgpu_residual(sgpu_ctx* c, int which, int lhs, double* l2sq) {
 
 } // extern "C"
 
+// streams and events of the pipelined host paths (created on first use)
+static int pipe_setup(sgpu_ctx* c) {
+    if (c->pipe_init) return SGPU_OK;
+    for (int k = 0; k < 5; k++) CK(c, cudaStreamCreateWithFlags(&c->pipe_stream[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 64; k++)
+        for (cudaEvent_t* e : {&c->pipe_up[k], &c->pipe_cmp[k], &c->pipe_h2d[k], &c->pipe_tout[k], &c->pipe_d2h[k]}) CK(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
+    c->pipe_init = true;
+    return SGPU_OK;
+}
+
 // Column-chunk pipeline (preferred): the host arrays are [i][j][k], so a range of i is ONE contiguous block -- the
 // H2D and D2H copies are plain 1-D transfers (measured 98 GB/s aggregate full duplex on this box vs 75 GB/s for the
 // strided 2-D copies a row-chunk pipeline needs).  Chunks are whole strips of the residual kernel.
 static int residual_host_pipelined_cols(sgpu_ctx* c, const double* q, int qj0, int qjn, double* rhs, int rj0, int rjn, int lhs) {
     const View& v = c->v;
     const int nstrips_all = (v.nic + RCELLS - 1)/RCELLS;
-    int nch = std::min(18, nstrips_all/2);                      // measured at 4096^2 (69 strips): 12 chunks 962, 18 1040, 23 1032, 35 1005 Mcell/s
+    int nch = std::min(14, nstrips_all/2);                      // measured at 4096^2 (69 strips), ramped sizes, copy streams of their own: 10 chunks 1120, 14 1128, 18 1121 Mcell/s
     if (const char* e = getenv("SGPU_PIPE_CHUNKS")) nch = std::max(1, std::min(atoi(e), nstrips_all));
-    nch = std::min(nch, 64);                                    // pipe_up / pipe_cmp hold 64 events
+    nch = std::min(nch, 62);                                    // the event arrays hold 64 entries (one is the wrap pre-upload's)
     const int jlo = std::max(std::max(v.j0 - 2, 0), qj0), jhi = std::min(std::min(v.j1 + 2, v.njc), qj0 + qjn);   // rows uploaded
     const int nrows_up = jhi - jlo, r0_up = jlo - v.j0 + JOFF;
     bool vert_periodic = false;
     for (const sgpu_bc& b : c->bcs) if (b.type == SGPU_BC_PERIODIC && (b.face == SGPU_FACE_LEFT || b.face == SGPU_FACE_RIGHT)) vert_periodic = true;
-    if (!c->pipe_init) {
-        for (int k = 0; k < 3; k++) CK(c, cudaStreamCreateWithFlags(&c->pipe_stream[k], cudaStreamNonBlocking));
-        for (int k = 0; k < 64; k++) { CK(c, cudaEventCreateWithFlags(&c->pipe_up[k], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->pipe_cmp[k], cudaEventDisableTiming)); }
-        CK(c, cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
-        c->pipe_init = true;
-    }
+    if (int rc = pipe_setup(c)) return rc;
     const int strips_per = (nstrips_all + nch - 1)/nch;
     nch = (nstrips_all + strips_per - 1)/strips_per;
+    // chunk boundaries in strips.  Uniform chunks leave the link half idle while the pipeline fills (only H2D runs until the
+    // first chunk is up) and drains (only D2H after the last kernel): the chunk sizes RAMP 1, 2, .. strips_per at the head and
+    // back down at the tail, so fill and drain cost one strip's copy each instead of a full chunk's (SGPU_PIPE_RAMP=0: uniform)
+    std::vector<int> bound(1, 0);
+    {
+        const char* e = getenv("SGPU_PIPE_RAMP");
+        const int ramp = strips_per*(strips_per - 1);                   // strips in the two ramps
+        if ((e && atoi(e) == 0) || ramp + strips_per > nstrips_all || nch + 2*(strips_per - 1) > 62) {
+            for (int ch = 0; ch < nch; ch++) bound.push_back(std::min((ch + 1)*strips_per, nstrips_all));
+        } else {
+            for (int k = 1; k < strips_per; k++) bound.push_back(bound.back() + k);
+            int mid = nstrips_all - ramp;
+            if (mid % strips_per) { bound.push_back(bound.back() + mid % strips_per); mid -= mid % strips_per; }
+            for (; mid > 0; mid -= strips_per) bound.push_back(bound.back() + strips_per);
+            for (int k = strips_per - 1; k >= 1; k--) bound.push_back(bound.back() + k);
+        }
+        nch = (int)bound.size() - 1;
+    }
     const size_t cols_max = (size_t)strips_per*RCELLS + 4;
     const size_t stage_dbl = cols_max*(size_t)std::max(nrows_up, v.njl)*v.nv;
     if (stage_dbl > c->pipe_stage_cap) {
@@ -624,29 +648,37 @@ static int residual_host_pipelined_cols(sgpu_ctx* c, const double* q, int qj0, i
         for (int k = 0; k < 4; k++) CK(c, cudaMalloc(&c->pipe_stage[k], stage_dbl*sizeof(double)));
         c->pipe_stage_cap = stage_dbl;
     }
-    cudaStream_t s_in = c->pipe_stream[0], s_cmp = c->pipe_stream[1], s_out = c->pipe_stream[2];
+    // five streams: the two copy engines get streams of their OWN (s_h2d, s_d2h) so that the next chunk's copy runs while the
+    // previous chunk's transpose kernel does (on one stream the link idled for every transpose); events order them per chunk and
+    // guard the two staging buffers of each direction
+    cudaStream_t s_in = c->pipe_stream[0], s_cmp = c->pipe_stream[1], s_out = c->pipe_stream[2], s_h2d = c->pipe_stream[3], s_d2h = c->pipe_stream[4];
     cudaStream_t user = c->stream;
     CK(c, cudaEventRecord(c->pipe_start, user));
-    for (int k = 0; k < 3; k++) CK(c, cudaStreamWaitEvent(c->pipe_stream[k], c->pipe_start, 0));
+    for (int k = 0; k < 5; k++) CK(c, cudaStreamWaitEvent(c->pipe_stream[k], c->pipe_start, 0));
     const size_t Mq = (size_t)nrows_up*v.nv;                       // doubles per column in the upload staging
     const bool q_contig = (jlo == qj0 && nrows_up == qjn);         // the window IS the uploaded row range: 1-D copies
-    auto upload_cols = [&](int ia, int ib, double* st) -> int {    // columns [ia, ib)
+    auto upload_cols = [&](int ia, int ib, double* st, cudaEvent_t copied) -> int {    // columns [ia, ib)
         if (ib <= ia) return SGPU_OK;
         const int ni = ib - ia;
-        if (q_contig) CK(c, cudaMemcpyAsync(st, q + (size_t)ia*qjn*v.nv, sizeof(double)*Mq*ni, cudaMemcpyHostToDevice, s_in));
-        else CK(c, cudaMemcpy2DAsync(st, sizeof(double)*Mq, q + ((size_t)ia*qjn + (jlo - qj0))*v.nv, sizeof(double)*qjn*v.nv, sizeof(double)*Mq, ni, cudaMemcpyHostToDevice, s_in));
+        if (q_contig) CK(c, cudaMemcpyAsync(st, q + (size_t)ia*qjn*v.nv, sizeof(double)*Mq*ni, cudaMemcpyHostToDevice, s_h2d));
+        else CK(c, cudaMemcpy2DAsync(st, sizeof(double)*Mq, q + ((size_t)ia*qjn + (jlo - qj0))*v.nv, sizeof(double)*qjn*v.nv, sizeof(double)*Mq, ni, cudaMemcpyHostToDevice, s_h2d));
+        CK(c, cudaEventRecord(copied, s_h2d));
+        CK(c, cudaStreamWaitEvent(s_in, copied, 0));
         aos_to_planes_kernel<<<dim3((unsigned)((Mq + 31)/32), (ni + 31)/32), dim3(32, 8), 0, s_in>>>(v, st, c->q[0], r0_up, nrows_up, ia, ni);
         CKL(c); c->launches++;
         return SGPU_OK;
     };
     int rc = SGPU_OK;
-    if (vert_periodic) rc = upload_cols(std::max(v.nic - 2, 0), v.nic, c->pipe_stage[0]);   // wrap-around ghost source of chunk 0
+    if (vert_periodic) {                                                               // wrap-around ghost source of chunk 0
+        rc = upload_cols(std::max(v.nic - 2, 0), v.nic, c->pipe_stage[0], c->pipe_h2d[63]);
+        CK(c, cudaStreamSynchronize(s_in));                                            // staging buffer 0 is reused right away (tiny copy)
+    }
     for (int ch = 0; ch < nch && rc == SGPU_OK; ch++) {
-        const int s0 = ch*strips_per, s1 = std::min(s0 + strips_per, nstrips_all);
+        const int s0 = bound[ch], s1 = bound[ch + 1];
         const int a = s0*RCELLS, b = std::min(s1*RCELLS, v.nic);                       // cell columns of this chunk
         const int ul = ch == 0 ? 0 : std::min(a + 2, v.nic), uh = ch == nch - 1 ? v.nic : std::min(b + 2, v.nic);
-        if (vert_periodic && ch == 0) CK(c, cudaStreamSynchronize(s_in));              // staging buffer 0 is reused right away (tiny copy)
-        rc = upload_cols(ul, uh, c->pipe_stage[ch & 1]);
+        if (ch >= 2) CK(c, cudaStreamWaitEvent(s_h2d, c->pipe_up[ch - 2], 0));         // staging buffer ch & 1 has been transposed
+        rc = upload_cols(ul, uh, c->pipe_stage[ch & 1], c->pipe_h2d[ch]);
         if (rc != SGPU_OK) break;
         CK(c, cudaEventRecord(c->pipe_up[ch], s_in));
         CK(c, cudaStreamWaitEvent(s_cmp, c->pipe_up[ch], 0));
@@ -660,18 +692,22 @@ static int residual_host_pipelined_cols(sgpu_ctx* c, const double* q, int qj0, i
         if (rc != SGPU_OK) break;
         CK(c, cudaEventRecord(c->pipe_cmp[ch], s_cmp));
         CK(c, cudaStreamWaitEvent(s_out, c->pipe_cmp[ch], 0));
+        if (ch >= 2) CK(c, cudaStreamWaitEvent(s_out, c->pipe_d2h[ch - 2], 0));        // staging buffer 2 + (ch & 1) has been downloaded
         {
             const int ni = b - a; const size_t M = (size_t)v.njl*v.nv;
             double* st = c->pipe_stage[2 + (ch & 1)];
             planes_to_aos_kernel<<<dim3((unsigned)((M + 31)/32), (ni + 31)/32), dim3(32, 8), 0, s_out>>>(v, st, c->rhs, JOFF, v.njl, v.nv, a, ni);
             CKL(c); c->launches++;
-            if (rj0 == v.j0 && rjn == v.njl) CK(c, cudaMemcpyAsync(rhs + (size_t)a*rjn*v.nv, st, sizeof(double)*M*ni, cudaMemcpyDeviceToHost, s_out));
-            else CK(c, cudaMemcpy2DAsync(rhs + ((size_t)a*rjn + (v.j0 - rj0))*v.nv, sizeof(double)*rjn*v.nv, st, sizeof(double)*M, sizeof(double)*M, ni, cudaMemcpyDeviceToHost, s_out));
+            CK(c, cudaEventRecord(c->pipe_tout[ch], s_out));
+            CK(c, cudaStreamWaitEvent(s_d2h, c->pipe_tout[ch], 0));
+            if (rj0 == v.j0 && rjn == v.njl) CK(c, cudaMemcpyAsync(rhs + (size_t)a*rjn*v.nv, st, sizeof(double)*M*ni, cudaMemcpyDeviceToHost, s_d2h));
+            else CK(c, cudaMemcpy2DAsync(rhs + ((size_t)a*rjn + (v.j0 - rj0))*v.nv, sizeof(double)*rjn*v.nv, st, sizeof(double)*M, sizeof(double)*M, ni, cudaMemcpyDeviceToHost, s_d2h));
+            CK(c, cudaEventRecord(c->pipe_d2h[ch], s_d2h));
         }
     }
-    cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_in);
+    cudaError_t e1 = cudaStreamSynchronize(s_d2h), e2 = cudaStreamSynchronize(s_out), e3 = cudaStreamSynchronize(s_cmp), e4 = cudaStreamSynchronize(s_in), e5 = cudaStreamSynchronize(s_h2d);
     if (rc != SGPU_OK) return rc;
-    CK(c, e1); CK(c, e2); CK(c, e3);
+    CK(c, e1); CK(c, e2); CK(c, e3); CK(c, e4); CK(c, e5);
     return SGPU_OK;
 }
 
@@ -693,12 +729,7 @@ static int residual_host_pipelined(sgpu_ctx* c, const double* q, int qj0, int qj
         if (int rc = sgpu_residual(c, SGPU_STATE_Q, lhs, nullptr)) return rc;
         return download_planes(c, c->rhs, v.nv, rhs, !(rj0 == 0 && rjn == v.njc));
     }
-    if (!c->pipe_init) {
-        for (int k = 0; k < 3; k++) CK(c, cudaStreamCreateWithFlags(&c->pipe_stream[k], cudaStreamNonBlocking));
-        for (int k = 0; k < 64; k++) { CK(c, cudaEventCreateWithFlags(&c->pipe_up[k], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->pipe_cmp[k], cudaEventDisableTiming)); }
-        CK(c, cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
-        c->pipe_init = true;
-    }
+    if (int rc = pipe_setup(c)) return rc;
     const int rows_per = (v.njl + nch - 1)/nch;
     const size_t stage_rows = (size_t)rows_per + 4;
     const size_t stage_dbl = (size_t)v.nic*stage_rows*v.nv;
