@@ -62,6 +62,12 @@ class HaloExchanger:
         self.dist = dist_module
         self.send = {s: torch.empty(halo_count, dtype=torch.float64, device=device) for s in self.nb}
         self.recv = {s: torch.empty(halo_count, dtype=torch.float64, device=device) for s in self.nb}
+        # gloo moves host memory only: device buffers are staged through pinned host tensors (two ranks sharing ONE GPU in
+        # the single-GPU form of the multi-process tests; NCCL refuses two ranks on one device)
+        self.stage = None
+        if dist_module is not None and torch.device(device).type == "cuda" and dist_module.is_initialized() and dist_module.get_backend() == "gloo":
+            self.stage = {s: (torch.empty(halo_count, dtype=torch.float64).pin_memory(), torch.empty(halo_count, dtype=torch.float64).pin_memory())
+                          for s in self.nb}
 
     def exchange(self, pack: Callable, unpack: Callable) -> None:
         if not self.nb:
@@ -70,11 +76,19 @@ class HaloExchanger:
         ops = []
         for side, nbr in self.nb.items():
             pack(side, self.send[side])
-            ops.append(dist.P2POp(dist.isend, self.send[side], nbr))
-            ops.append(dist.P2POp(dist.irecv, self.recv[side], nbr))
+            if self.stage is None:
+                ops.append(dist.P2POp(dist.isend, self.send[side], nbr))
+                ops.append(dist.P2POp(dist.irecv, self.recv[side], nbr))
+            else:
+                hs, hr = self.stage[side]
+                hs.copy_(self.send[side])                  # synchronous D2H on the current stream
+                ops.append(dist.P2POp(dist.isend, hs, nbr))
+                ops.append(dist.P2POp(dist.irecv, hr, nbr))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         for side in self.nb:
+            if self.stage is not None:
+                self.recv[side].copy_(self.stage[side][1])
             unpack(side, self.recv[side])
 
     def allreduce_sum(self, values: np.ndarray, device) -> np.ndarray:
@@ -184,7 +198,12 @@ class SlabLinearSolver:
 
     def _allreduce(self, t):
         if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            if self.halo.stage is not None:                # gloo with device tensors: reduce a host copy
+                h = t.cpu()
+                self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM)
+                t.copy_(h)
+            else:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
     def apply_op(self, matrix: str, x, out) -> None:
         """out = A x on this slab's rows.  Forward matrices ("lhs", "J") need the operand's two ghost rows per interior edge

@@ -1,6 +1,8 @@
-"""Multi-GPU (needs >= 2 devices; run with `gpurun --gpus 2`): two j-slabs on two B200s exchanging their ghost rows
-through NVLink peer memory (stores straight into the neighbour's buffer + device-side sequence flags) reproduce the
-single-GPU residual bit for bit."""
+"""Multi-GPU: two j-slabs on two B200s exchanging their ghost rows through NVLink peer memory (stores straight into the
+neighbour's buffer + device-side sequence flags) reproduce the single-GPU residual bit for bit (needs >= 2 devices:
+`gpurun --gpus 2`).  The two-PROCESS tests (implicit step, adjoint solve over torch.distributed) also run on a box with ONE
+GPU: both ranks then share cuda:0 and talk over gloo with host-staged buffers (NCCL refuses two ranks on one device) --
+same slab contexts, same kernels, same host logic, only the transport differs."""
 import numpy as np
 import pytest
 
@@ -49,6 +51,20 @@ def test_two_gpus_peer_memory_halo_bit_for_bit(ntrans):
         s.close()
 
 
+def _init_rank(rank, world):
+    """one rank per GPU over NCCL when the box has enough devices, else all ranks on cuda:0 over gloo"""
+    import torch
+    import torch.distributed as dist
+    ndev = torch.cuda.device_count()
+    idev = rank if ndev >= world else 0
+    torch.cuda.set_device(idev)
+    if ndev >= world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", idev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    return idev
+
+
 def _implicit_worker(rank, world, port, nic, njc, ntrans, cfl, out):
     import os
 
@@ -57,15 +73,14 @@ def _implicit_worker(rank, world, port, nic, njc, ntrans, cfl, out):
     from structured_b200.api import GpuEulerEquation
     from structured_b200.slab import HaloExchanger, SlabLinearSolver, partition_rows
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    idev = _init_rank(rank, world)
     try:
         case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4)
         q = case.perturbed_q(0.02)
         j0, j1 = partition_rows(njc, world)[rank]
-        eq = GpuEulerEquation(case, device=rank, j_begin=j0, j_end=j1)
+        eq = GpuEulerEquation(case, device=idev, j_begin=j0, j_end=j1)
         eq.set_state_window(np.ascontiguousarray(q[:, j0:j1, :]), j0)        # own rows only: ghosts must come from the exchange
-        dev = torch.device("cuda", rank)
+        dev = torch.device("cuda", idev)
         qhalo = HaloExchanger(rank, world, eq.halo_count(), dev, dist)
         solver = SlabLinearSolver(eq, rank, world, dist, dev)
 
@@ -80,10 +95,10 @@ def _implicit_worker(rank, world, port, nic, njc, ntrans, cfl, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ndev() < 2, reason="needs two GPUs")
+@pytest.mark.skipif(_ndev() < 1, reason="needs a GPU")
 @pytest.mark.parametrize("ntrans", [0, 1])
 def test_two_gpu_implicit_step_over_nccl_equals_one_gpu(ntrans):
-    """one implicit Solver::step on two j-slabs, two processes, NCCL: ghost rows of q and of every Krylov operand
+    """one implicit Solver::step on two j-slabs, two processes, NCCL (one GPU: both ranks on cuda:0 over gloo): ghost rows of q and of every Krylov operand
     exchanged, inner products all-reduced -- same new state as sgpu_implicit_step on one GPU"""
     import socket
 
@@ -124,16 +139,15 @@ def _adjoint_worker(rank, world, port, nic, njc, ntrans, g, out):
     from structured_b200.api import GpuEulerEquation
     from structured_b200.slab import SlabLinearSolver, partition_rows
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    idev = _init_rank(rank, world)
     try:
         case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=2e4, periodic=False)
         q = case.perturbed_q(0.02)
         j0, j1 = partition_rows(njc, world)[rank]
-        eq = GpuEulerEquation(case, device=rank, j_begin=j0, j_end=j1)
+        eq = GpuEulerEquation(case, device=idev, j_begin=j0, j_end=j1)
         eq.set_state(q)
         eq.jacobian_device()
-        solver = SlabLinearSolver(eq, rank, world, dist, torch.device("cuda", rank))
+        solver = SlabLinearSolver(eq, rank, world, dist, torch.device("cuda", idev))
         psi, info = solver.adjoint_solve(g, cfl=1e4, max_steps=12, tol=1e-9, precond="line_j", restart=60, max_iter=600, rtol=1e-6)
         rows = eq.vec_to_host(psi.data_ptr())[:, j0:j1, :]
         out.put((rank, j0, j1, rows, info))
@@ -142,7 +156,7 @@ def _adjoint_worker(rank, world, port, nic, njc, ntrans, g, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ndev() < 2, reason="needs two GPUs")
+@pytest.mark.skipif(_ndev() < 1, reason="needs a GPU")
 def test_two_gpu_adjoint_solve_equals_one_gpu():
     """J^T psi = -g on two j-slabs over NCCL (transposed products: each slab's share of the neighbour's rows is exchanged
     and added; inner products all-reduced) against sgpu_adjoint_solve on one GPU.  Laminar: the well-posed case."""
