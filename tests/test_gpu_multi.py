@@ -188,3 +188,76 @@ def test_two_gpu_adjoint_solve_equals_one_gpu():
         assert info["rel_residual"] <= 1e-9, info
         got[:, j0:j1, :] = rows
     assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+
+
+def _ipc_halo_worker(rank, world, port, nic, njc, ntrans, out):
+    import os
+
+    import torch
+    import torch.distributed as dist
+    from structured_b200.api import GpuEulerEquation
+    from structured_b200.slab import partition_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    idev = rank if ndev >= world else 0
+    torch.cuda.set_device(idev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # handles only; the rows travel through peer memory
+    try:
+        case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=1e5)
+        j0, j1 = partition_rows(njc, world)[rank]
+        eq = GpuEulerEquation(case, device=idev, j_begin=j0, j_end=j1)
+        mine = (eq.halo_ipc_handle(LOW), eq.halo_ipc_handle(HIGH))
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        if rank > 0:
+            eq.halo_open_peer(LOW, allh[rank - 1][HIGH])
+        if rank < world - 1:
+            eq.halo_open_peer(HIGH, allh[rank + 1][LOW])
+        got = []
+        for rep in range(3):                                         # several exchanges: both receive slots and the flags cycle
+            q = case.perturbed_q() * (1.0 + 0.001 * rep)
+            eq.set_state_window(np.ascontiguousarray(q[:, j0:j1, :]), j0)   # own rows only
+            dist.barrier()
+            eq.halo_push(0)
+            eq.halo_pull(0)
+            eq.residual_device(0)
+            rows = np.zeros((nic, j1 - j0, case.nv))
+            eq.get_rhs_window(rows)
+            got.append(rows)
+            eq.synchronize()
+            dist.barrier()
+        out.put((rank, j0, j1, got))
+        dist.barrier()
+        eq.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ndev() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("ntrans", [0, 1])
+def test_three_processes_cuda_ipc_halo_bit_for_bit(ntrans):
+    """the transport bench.py uses at N > 1: one process per slab, receive buffers opened through CUDA IPC handles, boundary rows
+    stored straight into the neighbour's memory, device-side sequence flags (sgpu_halo_ipc_handle / open_peer / push / pull).
+    Three slabs (one has two neighbours) must reproduce the one-context residual bit for bit; with fewer than three GPUs the
+    ranks share cuda:0 -- the same IPC path, the stores then stay on one device."""
+    import socket
+
+    import torch.multiprocessing as mp
+    from structured_b200.api import GpuEulerEquation
+    nic, njc, world = 200, 90, 3
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=1e5)
+    one = GpuEulerEquation(case, device=0)
+    want = [one.calc_residual(case.perturbed_q() * (1.0 + 0.001 * rep)) for rep in range(3)]
+    one.close()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_halo_worker, args=(r, world, port, nic, njc, ntrans, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, j0, j1, got in res:
+        for rep in range(3):
+            assert np.array_equal(got[rep], want[rep][:, j0:j1, :]), (rank, rep)
