@@ -235,6 +235,45 @@ __device__ __forceinline__ bool invert_block(double (&a)[NV][NV], double (&b)[NV
     return ok;
 }
 
+// The same Gauss-Jordan elimination for the line factorisation's dependent chain: the pivot row is swapped in with SELECTS
+// (32 lanes = 32 lines pivot differently: the branchy swaps above diverge into up to ten serial blocks per inversion) and the
+// pivot reciprocal is a MUFU seed + one third-order step (rcp_fast, 1 ulp) instead of an IEEE division.
+template <int NV>
+__device__ __forceinline__ bool invert_block_fast(double (&a)[NV][NV], double (&b)[NV][NV]) {
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) b[r][c] = r == c ? 1.0 : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        int p = k; double big = fabs(a[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < NV; r++) { const double t = fabs(a[r][k]); const bool g = t > big; big = g ? t : big; p = g ? r : p; }
+#pragma unroll
+        for (int r = k + 1; r < NV; r++) {
+            const bool sw = r == p;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                const double x = a[k][c], y = a[r][c]; a[k][c] = sw ? y : x; a[r][c] = sw ? x : y;
+                const double u = b[k][c], w = b[r][c]; b[k][c] = sw ? w : u; b[r][c] = sw ? u : w;
+            }
+        }
+        if (a[k][k] == 0.0) { ok = false; a[k][k] = 1.0; }
+        const double ip = rcp_fast(a[k][k]);
+#pragma unroll
+        for (int c = 0; c < NV; c++) { a[k][c] *= ip; b[k][c] *= ip; }
+#pragma unroll
+        for (int r = 0; r < NV; r++) {
+            if (r == k) continue;
+            const double f = a[r][k];
+#pragma unroll
+            for (int c = 0; c < NV; c++) { a[r][c] = fma(-f, a[k][c], a[r][c]); b[r][c] = fma(-f, b[k][c], b[r][c]); }
+        }
+    }
+    return ok;
+}
+
 template <int NV>
 __device__ __forceinline__ void load_block(const double* __restrict__ J, size_t pl, size_t o, int s, int op, double idt, bool diag, double (&a)[NV][NV]) {
 #pragma unroll
@@ -337,7 +376,7 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
     const int ic = live ? i : v.nic - 1;                           // idle lanes shadow the last line and never store
     const size_t pl = v.plane;
     double* __restrict__ Dinv = F;
-    double* __restrict__ DA = F + (size_t)NV*NV*pl;
+    double* __restrict__ DAo = F + (size_t)NV*NV*pl;
     double* __restrict__ DC = F + (size_t)2*NV*NV*pl;
     const bool arms = nslots > 9;
     auto slot = [&](int st, int p) -> double* { return fring + ((size_t)st*NP + p)*32 + lane; };
@@ -366,60 +405,78 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
                 a[r][c] = op == OP_LHS ? ((diag && r == c) ? idt - vj : -vj) : vj;
             }
     };
+    // one row of a ring block (lumped with the radius-2 arm's block when `arm`), transformed like load_block
+    auto ring_row = [&](int st, int g, int ga, bool arm, int r, double (&a)[NV]) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            double vj = *slot(st, g*B + r*NV + c);
+            if (arm) vj += *slot(st, ga*B + r*NV + c);
+            a[c] = op == OP_LHS ? -vj : vj;
+        }
+    };
     for (int jl = 0; jl < S - 1; jl++) issue(jl);
     double DCp[NV][NV];                                            // DC_{j-1}
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) DCp[r][c] = 0.0;
     for (int jl = 0; jl < v.njl; jl++) {
         issue(jl + S - 1);
         asm volatile("cp.async.wait_group %0;" :: "n"(S - 1) : "memory");
         const int st = jl % S;
         const int gj = v.j0 + jl;
         const size_t o = v.at(jl + JOFF, ic + IOFF);
-        double D[NV][NV], A[NV][NV], T[NV][NV], I[NV][NV];
-        ring_block(st, 0, op == OP_LHS ? 1.0/(*slot(st, 5*B)) : 0.0, true, D);
         const bool lo = jl > 0, hi = jl + 1 < v.njl;
+        const bool arm_lo = arms && gj - 2 >= 0, arm_hi = arms && gj + 2 <= v.njc - 1;
+        // D' = D - A' DC_{j-1}, formed row by row: the blocks are re-read from the ring where they are needed instead of being
+        // held (five nv x nv blocks in registers put part of them into local memory: 232 registers + a 400-byte stack frame)
+        double D[NV][NV], I[NV][NV];
+        ring_block(st, 0, op == OP_LHS ? rcp_fast(*slot(st, 5*B)) : 0.0, true, D);
         if (lo) {
-            ring_block(st, 1, 0.0, false, A);
-            if (arms && gj - 2 >= 0) {
-                ring_block(st, 2, 0.0, false, T);
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double a[NV];
+                ring_row(st, 1, 2, arm_lo, r, a);
+#pragma unroll
+                for (int k = 0; k < NV; k++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) D[r][c] = fma(-a[k], DCp[k][c], D[r][c]);
+            }
+        }
+        if (!invert_block_fast<NV>(D, I)) atomicExch(err, 1);
+        // DA = D'^-1 A' and DC = D'^-1 C': accumulated over the rows k of A' / C' as they come out of the ring
+        double DA[NV][NV];
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) { DA[r][c] = 0.0; DCp[r][c] = 0.0; }
+        if (lo) {
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                double a[NV];
+                ring_row(st, 1, 2, arm_lo, k, a);
 #pragma unroll
                 for (int r = 0; r < NV; r++)
 #pragma unroll
-                    for (int c = 0; c < NV; c++) A[r][c] += T[r][c];
+                    for (int c = 0; c < NV; c++) DA[r][c] = fma(I[r][k], a[c], DA[r][c]);
             }
-            matmul_block<NV>(A, DCp, T);
-#pragma unroll
-            for (int r = 0; r < NV; r++)
-#pragma unroll
-                for (int c = 0; c < NV; c++) D[r][c] -= T[r][c];
-        } else {
-#pragma unroll
-            for (int r = 0; r < NV; r++)
-#pragma unroll
-                for (int c = 0; c < NV; c++) A[r][c] = 0.0;
         }
-        if (!invert_block<NV>(D, I)) atomicExch(err, 1);
-        matmul_block<NV>(I, A, T);
         if (live) {
 #pragma unroll
             for (int r = 0; r < NV; r++)
 #pragma unroll
-                for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DA[(size_t)(r*NV + c)*pl + o] = T[r][c]; }
+                for (int c = 0; c < NV; c++) { Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DAo[(size_t)(r*NV + c)*pl + o] = DA[r][c]; }
         }
         if (hi) {
-            ring_block(st, 3, 0.0, false, A);
-            if (arms && gj + 2 <= v.njc - 1) {
-                ring_block(st, 4, 0.0, false, T);
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                double a[NV];
+                ring_row(st, 3, 4, arm_hi, k, a);
 #pragma unroll
                 for (int r = 0; r < NV; r++)
 #pragma unroll
-                    for (int c = 0; c < NV; c++) A[r][c] += T[r][c];
+                    for (int c = 0; c < NV; c++) DCp[r][c] = fma(I[r][k], a[c], DCp[r][c]);
             }
-            matmul_block<NV>(I, A, DCp);
-        } else {
-#pragma unroll
-            for (int r = 0; r < NV; r++)
-#pragma unroll
-                for (int c = 0; c < NV; c++) DCp[r][c] = 0.0;
         }
         if (live) {
 #pragma unroll
@@ -603,22 +660,59 @@ __device__ __forceinline__ void cp_async8(double* smem, const double* g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int NV> constexpr int line_ring_planes() { return 2*NV*NV + NV; }
+template <int NV> constexpr int line_ring_planes() { return 2*(NV*NV + (NV*NV & 1)) + NV + (NV & 1); }   // each group padded to an even plane count
 template <int NV> constexpr size_t line_ring_bytes() { return (size_t)LINE_STAGES*line_ring_planes<NV>()*32*sizeof(double); }
+__device__ __forceinline__ void cp_async16(double* smem, const double* g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+}
 
+// One warp owns 32 adjacent lines (a CTA is one warp) and walks them row by row; the sweep is sequential in j, i.e. pure latency,
+// and only nic/32 warps exist, so what bounds it is the warp's own INSTRUCTION count per row -- and of the ~300 instructions per
+// row and sweep, 55 were eight-byte cp.async (LDGSTS costs ~8 cycles of the load/store unit each, whatever its size).  Round 2b:
+// the ring is filled with SIXTEEN-byte copies: one instruction moves the 256-byte row segments of TWO planes (lanes 0-15 the
+// first, lanes 16-31 the second), 28 instead of 55 per row; the lanes then read words other lanes copied, so the wait is
+// followed by a __syncwarp.  Same arithmetic in the same order (results bit-identical).  Measured and rejected: one TMA bulk copy
+// (cp.async.bulk + mbarrier) per plane and row -- 256-byte bulk copies complete at ~1 per 50 cycles and SM: 3.1 -> 11.9 ms.
+// Lanes past the last line compute on padding and never store.
 template <int NV, bool TR>
 __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __restrict__ F, const double* __restrict__ rv, double* __restrict__ z) {
-    extern __shared__ double ring[];
-    constexpr int B = NV*NV, NP = 2*NV*NV + NV, S = LINE_STAGES;
+    extern __shared__ __align__(128) double ring[];
+    // ring planes of a stage: [0, B) first block, [BP, BP + B) second block, [2 BP, 2 BP + NV) the operand; BP = B rounded up to even,
+    // so that every sixteen-byte copy instruction serves two planes of the SAME source array (no per-lane source selection)
+    constexpr int B = NV*NV, BP = B + (B & 1), NP = 2*BP + NV + (NV & 1), S = LINE_STAGES;
     const int lane = threadIdx.x;
     const int i = blockIdx.x*32 + lane;
     const bool live = i < v.nic;
-    const int ic = live ? i : v.nic - 1;                           // idle lanes shadow the last line and never store
+    const int c0 = blockIdx.x*32 + IOFF;                           // first plane column of the warp's segment (16-byte aligned)
     const size_t pl = v.plane;
     const double* __restrict__ Dinv = F;
     const double* __restrict__ DA = F + (size_t)B*pl;
     const double* __restrict__ DC = F + (size_t)2*B*pl;
     auto slot = [&](int st, int p) -> double* { return ring + ((size_t)st*NP + p)*32 + lane; };
+    const int half = lane >> 4, word = (lane & 15)*2;               // this lane copies words word, word+1 of plane 2h + half
+    const bool in_row = c0 + word < v.pitch;                        // the last warp's segment ends with the row
+    const size_t lane_src = (size_t)half*pl + word;                 // this lane's offset inside a plane pair
+    const unsigned lane_dst = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)((half*32 + word)*sizeof(double));
+    for (int k = lane; k < S*NP*32; k += 32) ring[k] = 0.0;        // words past a short last segment are never written by the copies
+    __syncwarp();
+    // one commit group per row: blocks P0 (and P1 unless null) and the operand's nv planes, two planes per instruction
+    auto issue_row = [&](int st, int jl, bool valid, const double* P0, const double* P1, const double* vec) {
+        if (valid && in_row) {
+            const size_t o = v.at(jl + JOFF, c0) + lane_src;
+            const unsigned d = lane_dst + (unsigned)(st*NP*32*sizeof(double));
+            auto group = [&](const double* src, int first, int count) {
+#pragma unroll
+                for (int h = 0; h < (count + 1)/2; h++)
+                    if (2*h + 1 < count || half == 0)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)((first + 2*h)*32*sizeof(double))), "l"(src + o + (size_t)(2*h)*pl) : "memory");
+            };
+            group(P0, 0, B);
+            if (P1) group(P1, BP, B);
+            group(vec, 2*BP, NV);
+        }
+        cp_async_commit();
+    };
     double t[NV];
 #pragma unroll
     for (int r = 0; r < NV; r++) t[r] = 0.0;
@@ -626,32 +720,20 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
     // ---- sweep 1: rows ascending
     {
         const double* __restrict__ P0 = TR ? DC : Dinv;            // first nv*nv planes of a stage
-        auto issue = [&](int jl) {
-            if (jl < v.njl) {
-                const size_t o = v.at(jl + JOFF, ic + IOFF);
-                const int st = jl % S;
-#pragma unroll
-                for (int e = 0; e < B; e++) cp_async8(slot(st, e), P0 + (size_t)e*pl + o);
-                if (!TR) {
-#pragma unroll
-                    for (int e = 0; e < B; e++) cp_async8(slot(st, B + e), DA + (size_t)e*pl + o);
-                }
-#pragma unroll
-                for (int k = 0; k < NV; k++) cp_async8(slot(st, 2*B + k), rv + (size_t)k*pl + o);
-            }
-            cp_async_commit();
-        };
-        for (int jl = 0; jl < S - 1; jl++) issue(jl);
+        const double* __restrict__ P1 = TR ? nullptr : DA;
+        for (int jl = 0; jl < S - 1; jl++) issue_row(jl % S, jl, jl < v.njl, P0, P1, rv);
         for (int jl = 0; jl < v.njl; jl++) {
-            issue(jl + S - 1);
-            cp_async_wait<S - 1>();
+            __syncwarp();                                          // every lane is done with the stage row jl + S - 1 overwrites
+            issue_row((jl + S - 1) % S, jl + S - 1, jl + S - 1 < v.njl, P0, P1, rv);
             const int st = jl % S;
-            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            cp_async_wait<S - 1>();                                // this lane's copies of row jl have landed ...
+            __syncwarp();                                          // ... and so have the other lanes'
+            const size_t o = v.at(jl + JOFF, c0 + lane);
             double g[NV];
             if (!TR) {
                 double rr[NV];
 #pragma unroll
-                for (int r = 0; r < NV; r++) rr[r] = *slot(st, 2*B + r);
+                for (int r = 0; r < NV; r++) rr[r] = *slot(st, 2*BP + r);
 #pragma unroll
                 for (int r = 0; r < NV; r++) {
                     double s = 0.0;
@@ -663,7 +745,7 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
                 for (int r = 0; r < NV; r++) {
                     double s = g[r];
 #pragma unroll
-                    for (int c = 0; c < NV; c++) s -= *slot(st, B + r*NV + c)*t[c];
+                    for (int c = 0; c < NV; c++) s -= *slot(st, BP + r*NV + c)*t[c];
                     g[r] = s;
                 }
 #pragma unroll
@@ -674,7 +756,7 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < NV; r++) g[r] = *slot(st, 2*B + r) - t[r];
+                for (int r = 0; r < NV; r++) g[r] = *slot(st, 2*BP + r) - t[r];
                 if (live) {
 #pragma unroll
                     for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
@@ -688,46 +770,35 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
                 }
             }
         }
-        cp_async_wait<0>();
     }
-    __syncwarp();                                                  // z rows written above are re-read below by the same lane only
+    cp_async_wait<0>();
+    __threadfence();                                               // the z rows written above are copied in below by OTHER lanes
+    __syncwarp();
 
     // ---- sweep 2: rows descending
     {
         const double* __restrict__ P0 = TR ? DA : DC;
+        const double* __restrict__ P1 = TR ? Dinv : nullptr;
         const int jtop = TR ? v.njl - 1 : v.njl - 2;               // the untransposed last row is already final (t holds it)
         if (TR) {
 #pragma unroll
             for (int r = 0; r < NV; r++) t[r] = 0.0;
         }
-        auto issue = [&](int n) {                                  // n-th row of this sweep = row jtop - n
-            const int jl = jtop - n;
-            if (jl >= 0) {
-                const size_t o = v.at(jl + JOFF, ic + IOFF);
-                const int st = n % S;
-#pragma unroll
-                for (int e = 0; e < B; e++) cp_async8(slot(st, e), P0 + (size_t)e*pl + o);
-                if (TR) {
-#pragma unroll
-                    for (int e = 0; e < B; e++) cp_async8(slot(st, B + e), Dinv + (size_t)e*pl + o);
-                }
-#pragma unroll
-                for (int k = 0; k < NV; k++) cp_async8(slot(st, 2*B + k), z + (size_t)k*pl + o);
-            }
-            cp_async_commit();
-        };
-        for (int n = 0; n < S - 1; n++) issue(n);
+        // n-th row of this sweep = row jtop - n
+        for (int n = 0; n < S - 1; n++) issue_row(n % S, jtop - n, n <= jtop, P0, P1, z);
         for (int n = 0; n <= jtop; n++) {
-            issue(n + S - 1);
-            cp_async_wait<S - 1>();
+            __syncwarp();
+            issue_row((n + S - 1) % S, jtop - (n + S - 1), n + S - 1 <= jtop, P0, P1, z);
             const int st = n % S;
+            cp_async_wait<S - 1>();
+            __syncwarp();
             const int jl = jtop - n;
-            const size_t o = v.at(jl + JOFF, ic + IOFF);
+            const size_t o = v.at(jl + JOFF, c0 + lane);
             double g[NV];
             if (!TR) {
 #pragma unroll
                 for (int r = 0; r < NV; r++) {
-                    double s = *slot(st, 2*B + r);
+                    double s = *slot(st, 2*BP + r);
 #pragma unroll
                     for (int c = 0; c < NV; c++) s -= *slot(st, r*NV + c)*t[c];
                     g[r] = s;
@@ -741,7 +812,7 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
             } else {
                 double w[NV];
 #pragma unroll
-                for (int r = 0; r < NV; r++) w[r] = *slot(st, 2*B + r) - t[r];
+                for (int r = 0; r < NV; r++) w[r] = *slot(st, 2*BP + r) - t[r];
 #pragma unroll
                 for (int c = 0; c < NV; c++) {
                     double s = 0.0;
@@ -753,7 +824,7 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
                 for (int c = 0; c < NV; c++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int r = 0; r < NV; r++) s += *slot(st, B + r*NV + c)*w[r];
+                    for (int r = 0; r < NV; r++) s += *slot(st, BP + r*NV + c)*w[r];
                     g[c] = s;
                 }
                 if (live) {
