@@ -40,19 +40,42 @@ __global__ void __launch_bounds__(128) op_apply_kernel(View v, GhostTable gt, in
     for (int r = 0; r < NV; r++) yr[r] = 0.0;
     const bool inner = i >= 2 && i < v.nic - 2 && gj >= 2 && gj < v.njc - 2;
     if (inner) {
-#pragma unroll 1
-        for (int s = 0; s < nslots; s++) {
-            if (!viscous && s >= 5 && s <= 8) continue;
-            if (!order2 && s >= 9) continue;
+        // Software pipelined over the slots: the 25 block entries and 5 operand values of the NEXT slot are loaded while the
+        // current slot's products run (ncu on the plain loop: latency bound -- long_scoreboard 62 stall cycles per issue at 37
+        // warps per SM -- because the compiler sinks every load to its first use and a warp issues in order, so the first
+        // dependent DFMA blocks the loads behind it: ~6 loads in flight per warp.  Here a warp keeps 30.)
+        auto slot_on = [&](int s) { return !((!viscous && s >= 5 && s <= 8) || (!order2 && s >= 9)); };
+        auto fetch = [&](int s, double (&a)[NV*NV], double (&xs)[NV]) {
             const size_t oc = o + (long long)c_slot_dy[s]*v.pitch + c_slot_dx[s];
-            double xs[NV];
+            const double* Js = J + (size_t)s*NV*NV*pl + o;
+            // the 45 of 325 entries that are STRUCTURALLY zero (entry_present: mass row x corner cells, q4 column of the mass row
+            // and of the radius-2 arms) are not read: these planes hold exact zeros for inner cells (no ghost folding there)
+            const bool corner = s >= 5 && s <= 8, arm = s >= 9;
+#pragma unroll
+            for (int e = 0; e < NV*NV; e++) {
+                const int r = e/NV, c2 = e - r*NV;
+                const bool zero = (r == 0 && corner) || (NV > 4 && c2 == 4 && (r == 0 || arm));
+                a[e] = zero ? 0.0 : ld_stream(Js + (size_t)e*pl);
+            }
 #pragma unroll
             for (int c2 = 0; c2 < NV; c2++) xs[c2] = x[c2*pl + oc];
-            const double* Js = J + (size_t)s*NV*NV*pl + o;
+        };
+        double a[NV*NV], xs[NV], an[NV*NV], xn[NV];
+        int s = 0;
+        fetch(0, a, xs);                                           // slot 0 (the cell itself) is always present
+        while (s < nslots) {
+            int sn = s + 1;
+            while (sn < nslots && !slot_on(sn)) sn++;
+            if (sn < nslots) fetch(sn, an, xn);
 #pragma unroll
             for (int r = 0; r < NV; r++)
 #pragma unroll
-                for (int c2 = 0; c2 < NV; c2++) yr[r] += ld_stream(Js + (size_t)(r*NV + c2)*pl)*xs[c2];
+                for (int c2 = 0; c2 < NV; c2++) yr[r] += a[r*NV + c2]*xs[c2];
+#pragma unroll
+            for (int e = 0; e < NV*NV; e++) a[e] = an[e];
+#pragma unroll
+            for (int c2 = 0; c2 < NV; c2++) xs[c2] = xn[c2];
+            s = sn;
         }
     } else {
         SlotCols sc; resolve_slots(gt, nslots, i, gj, viscous, order2, sc);
