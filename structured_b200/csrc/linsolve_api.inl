@@ -18,7 +18,8 @@ struct LinWork {
     double* hhost = nullptr;       // pinned, ldp doubles
     int* err = nullptr;
     unsigned* ticket = nullptr;    // arrival counter of the in-kernel final reductions
-    int blocks = 0, ldp = 0;
+    int blocks = 0, ldp = 0;       // blocks: grid of the flat vector kernels (and the capacity of `partial`)
+    int blocks_dots = 0, blocks_upd = 0;   // grids of the two Gram-Schmidt kernels = exactly ONE resident wave each
 };
 
 static void lin_free(LinWork*& L) {
@@ -39,7 +40,14 @@ static int lin_prepare(sgpu_ctx* c, int m) {
     L = new LinWork();
     L->n = n; L->m = m; L->ldp = m + 2;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    L->blocks = 4*sms;
+    // Grids = what is RESIDENT at once.  The Gram-Schmidt kernels are grid-stride loops that end in a last-block reduction: with
+    // 4 x SMs blocks and 76 registers only 3 blocks fit an SM, so a quarter of the tiles ran in a second wave of one block per SM
+    // at a third of the bandwidth (ncu launch list: 0.38 ms of every dots launch).  The flat kernels get 8 x SMs blocks.
+    int occ_d = 1, occ_u = 1;
+    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, dots_kernel, DOT_THREADS, 0));
+    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, gs_update_kernel, DOT_THREADS, 0));
+    L->blocks_dots = std::max(1, occ_d)*sms; L->blocks_upd = std::max(1, occ_u)*sms;
+    L->blocks = std::max(8*sms, std::max(L->blocks_dots, L->blocks_upd));
     const size_t vb = n*sizeof(double);
     CK(c, cudaMalloc(&L->V, vb*(m + 1)));
     CK(c, cudaMalloc(&L->w, vb)); CK(c, cudaMalloc(&L->z, vb)); CK(c, cudaMalloc(&L->x, vb)); CK(c, cudaMalloc(&L->b, vb)); CK(c, cudaMalloc(&L->u, vb));
@@ -145,7 +153,7 @@ static int lin_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, int 
     LinWork* L = c->lin;
     for (int g = 0; g < cnt; g += DOT_GROUP) {
         const int k = std::min(DOT_GROUP, cnt - g);
-        dots_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, j0 + g, L->hdev, L->ticket);
+        dots_kernel<<<L->blocks_dots, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, j0 + g, L->hdev, L->ticket);
         CKL(c); c->launches++;
     }
     return SGPU_OK;
@@ -153,7 +161,7 @@ static int lin_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, int 
 // w -= V h (h = L->hdev[0 .. cnt)) and L->hdev[cnt] = |w|^2 of the result, one pass
 static int lin_gs_update(sgpu_ctx* c, double* w, const double* V, int cnt) {
     LinWork* L = c->lin;
-    gs_update_kernel<<<L->blocks, DOT_THREADS, 0, c->stream>>>(w, V, L->n, cnt, L->hdev, L->partial, L->ldp, cnt, L->hdev, L->ticket);
+    gs_update_kernel<<<L->blocks_upd, DOT_THREADS, 0, c->stream>>>(w, V, L->n, cnt, L->hdev, L->partial, L->ldp, cnt, L->hdev, L->ticket);
     CKL(c); c->launches++;
     return SGPU_OK;
 }
