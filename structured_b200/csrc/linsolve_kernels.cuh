@@ -125,23 +125,47 @@ __global__ void __launch_bounds__(128) op_apply_t_kernel(View v, int nslots, boo
     double yr[NV];
 #pragma unroll
     for (int r = 0; r < NV; r++) yr[r] = 0.0;
-#pragma unroll 1
-    for (int s = 0; s < nslots; s++) {
-        if (!viscous && s >= 5 && s <= 8) continue;
-        if (!order2 && s >= 9) continue;
-        const int ri = i - c_slot_dx[s], rj = gj - c_slot_dy[s];          // the row cell whose slot s points at this cell
-        if (!(ri >= 2 && ri < v.nic - 2 && rj >= 2 && rj < v.njc - 2)) continue;   // band rows: scattered separately
+    // software pipelined like op_apply_kernel: the next contributing slot's loads are in flight under this slot's products, and
+    // the structurally-zero entries (exact zeros in inner row cells) are not read
+    auto slot_row = [&](int s, size_t& orow) -> bool {              // the row cell whose slot s points at this cell, if it contributes here
+        if ((!viscous && s >= 5 && s <= 8) || (!order2 && s >= 9)) return false;
+        const int ri = i - c_slot_dx[s], rj = gj - c_slot_dy[s];
+        if (!(ri >= 2 && ri < v.nic - 2 && rj >= 2 && rj < v.njc - 2)) return false;    // band rows: scattered separately
         const int rl = rj - v.j0;
-        if (rl < 0 || rl >= v.njl) continue;                       // row cell owned by another slab
-        const size_t orow = v.at(rl + JOFF, ri + IOFF);
-        double xs[NV];
+        if (rl < 0 || rl >= v.njl) return false;                   // row cell owned by another slab
+        orow = v.at(rl + JOFF, ri + IOFF);
+        return true;
+    };
+    auto fetch = [&](int s, size_t orow, double (&a)[NV*NV], double (&xs)[NV]) {
+        const double* Js = J + (size_t)s*NV*NV*pl + orow;
+        const bool corner = s >= 5 && s <= 8, arm = s >= 9;
+#pragma unroll
+        for (int e = 0; e < NV*NV; e++) {
+            const int r = e/NV, c2 = e - r*NV;
+            const bool zero = (r == 0 && corner) || (NV > 4 && c2 == 4 && (r == 0 || arm));
+            a[e] = zero ? 0.0 : ld_stream(Js + (size_t)e*pl);
+        }
 #pragma unroll
         for (int r = 0; r < NV; r++) xs[r] = x[r*pl + orow];
-        const double* Js = J + (size_t)s*NV*NV*pl + orow;
+    };
+    double a[NV*NV], xs[NV], an[NV*NV], xn[NV];
+    size_t orow = 0, onext = 0;
+    int s = 0;
+    while (s < nslots && !slot_row(s, orow)) s++;
+    if (s < nslots) fetch(s, orow, a, xs);
+    while (s < nslots) {
+        int sn = s + 1;
+        while (sn < nslots && !slot_row(sn, onext)) sn++;
+        if (sn < nslots) fetch(sn, onext, an, xn);
 #pragma unroll
         for (int r = 0; r < NV; r++)
 #pragma unroll
-            for (int c2 = 0; c2 < NV; c2++) yr[c2] += ld_stream(Js + (size_t)(r*NV + c2)*pl)*xs[r];
+            for (int c2 = 0; c2 < NV; c2++) yr[c2] += a[r*NV + c2]*xs[r];
+#pragma unroll
+        for (int e = 0; e < NV*NV; e++) a[e] = an[e];
+#pragma unroll
+        for (int r = 0; r < NV; r++) xs[r] = xn[r];
+        s = sn;
     }
 #pragma unroll
     for (int r = 0; r < NV; r++) y[r*pl + o] = yr[r];
