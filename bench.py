@@ -284,13 +284,18 @@ def run_ours(args):
     j0, j1 = partition_rows(njc_total, world)[rank]
     # each rank generates only the grid rows its slab needs (own rows + 2 ghost rows per interior side)
     win = (max(j0 - 2, 0), min(j1 + 2, njc_total)) if world > 1 else None
+    t_setup = time.time()
     case = build_case(nic, njc_total, args.ntrans, cell_rows=win)
+    t_case = time.time() - t_setup
     eq = GpuEulerEquation(case, device=local, j_begin=j0 if world > 1 else 0, j_end=j1 if world > 1 else 0, window=case.window)
     # each rank generates only its own rows (+2 ghost rows each side) of the synthetic state
     jw0, jw1 = (max(j0 - 2, 0), min(j1 + 2, njc_total)) if world > 1 else (0, njc_total)
     q = case.perturbed_q(j_first=jw0, j_count=jw1 - jw0)
     eq.set_state_window(q, jw0, 0)
     eq.synchronize()
+    # setup per rank = grid window + context (vertices, metrics, wall distance, beta) + state upload
+    setup = {"total_s": round(time.time() - t_setup, 2), "grid_window_generation_s": round(t_case, 2),
+             "what": "per rank: vertex rows of the slab generated on the host (a binary vertex file is read the same way: sgpu_set_grid_file), context + metrics on the device, state upload"}
     cells_local = nic * njc_per
     cells_total = nic * njc_total
 
@@ -627,7 +632,7 @@ def run_ours(args):
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check,
+               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check, "setup": setup,
                "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()
