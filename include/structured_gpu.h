@@ -275,6 +275,14 @@ int sgpu_vec_from_host(sgpu_ctx* ctx, const double* host, double* vec_dev);
 int sgpu_vec_to_host(sgpu_ctx* ctx, const double* vec_dev, double* host);
 int sgpu_precond_setup(sgpu_ctx* ctx, int matrix, int precond);                         /* slab-local factors */
 int sgpu_precond_apply(sgpu_ctx* ctx, int matrix, int precond, const double* r_dev, double* z_dev);
+/* Gram-Schmidt building blocks (device pointers throughout; V = cnt basis vectors of sgpu_vec_size doubles, contiguous):
+ *   out[0 .. cnt) = w . V_j            -- all-reduce out across the slabs, then
+ *   w -= sum_j h[j] V_j, *normsq = |w|^2 of this slab's rows -- all-reduce normsq, then
+ *   dst = src / sqrt(*normsq)
+ * The kernels of sgpu_linear_solve (deterministic in-kernel reductions); partition the inner products of ls_petsc.cpp's GMRES. */
+int sgpu_vec_dots(sgpu_ctx* ctx, const double* w_dev, const double* V_dev, int cnt, double* out_dev);
+int sgpu_vec_gs_update(sgpu_ctx* ctx, double* w_dev, const double* V_dev, int cnt, const double* h_dev, double* normsq_dev);
+int sgpu_vec_scale_rsqrt(sgpu_ctx* ctx, double* dst_dev, const double* src_dev, const double* normsq_dev);
 
 /* ---- multi-GPU j-slabs ---------------------------------------------------------------------- */
 /* Two ghost rows of q per interior slab edge.  side: 0 = low-j neighbour, 1 = high-j neighbour.

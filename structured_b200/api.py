@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgpu_linear_solve", "sgpu_implicit_step", "sgpu_adjoint_solve", "sgpu_adjoint_solve_ramp",
     "sgpu_vec_size", "sgpu_vec_from_rhs", "sgpu_vec_add_to_state", "sgpu_vec_halo_pack", "sgpu_vec_halo_unpack", "sgpu_vec_halo_pack_ghost", "sgpu_vec_halo_add",
     "sgpu_vec_from_host", "sgpu_vec_to_host", "sgpu_op_apply",
-    "sgpu_precond_setup", "sgpu_precond_apply",
+    "sgpu_precond_setup", "sgpu_precond_apply", "sgpu_vec_dots", "sgpu_vec_gs_update", "sgpu_vec_scale_rsqrt",
     "sgpu_halo_count", "sgpu_halo_pack", "sgpu_halo_unpack", "sgpu_halo_pack_ghost", "sgpu_halo_recv_buffer", "sgpu_halo_enable_peer", "sgpu_halo_set_peer", "sgpu_halo_ipc_handle", "sgpu_halo_open_peer",
     "sgpu_halo_push", "sgpu_halo_pull", "sgpu_launch_count", "sgpu_kernel_times", "sgpu_enable_kernel_timing",
 ]
@@ -400,6 +400,19 @@ class GpuEulerEquation:
 
     def precond_apply(self, matrix: str, precond: str, r_ptr: int, z_ptr: int):
         self._ck(self.L.sgpu_precond_apply(self.h, MATRICES[matrix], PRECONDS[precond], ctypes.c_void_p(r_ptr), ctypes.c_void_p(z_ptr)))
+
+    def vec_dots(self, w_ptr: int, V_ptr: int, cnt: int, out_ptr: int):
+        """out[0..cnt) = w . V_j on the device (the Gram-Schmidt projection kernel of sgpu_linear_solve)"""
+        self._ck(self.L.sgpu_vec_dots(self.h, ctypes.c_void_p(w_ptr), ctypes.c_void_p(V_ptr), int(cnt), ctypes.c_void_p(out_ptr)))
+
+    def vec_gs_update(self, w_ptr: int, V_ptr: int, cnt: int, h_ptr: int, normsq_ptr: int):
+        """w -= sum_j h[j] V_j and *normsq = |w|^2 (this slab's rows), one pass"""
+        self._ck(self.L.sgpu_vec_gs_update(self.h, ctypes.c_void_p(w_ptr), ctypes.c_void_p(V_ptr), int(cnt), ctypes.c_void_p(h_ptr),
+                                           ctypes.c_void_p(normsq_ptr)))
+
+    def vec_scale_rsqrt(self, dst_ptr: int, src_ptr: int, normsq_ptr: int):
+        """dst = src / sqrt(*normsq)"""
+        self._ck(self.L.sgpu_vec_scale_rsqrt(self.h, ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), ctypes.c_void_p(normsq_ptr)))
 
     def adjoint_solve(self, g: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
                       restart: int = 40, max_iter: int = 400, rtol: float = 1e-3, reorthogonalize: bool = False,

@@ -38,7 +38,7 @@ static int lin_prepare(sgpu_ctx* c, int m) {
     if (L && (L->n != n || L->m < m)) lin_free(L);
     if (L) return SGPU_OK;
     L = new LinWork();
-    L->n = n; L->m = m; L->ldp = m + 2;
+    L->n = n; L->m = m; L->ldp = SGPU_GMRES_MAX + 2;       // reduction scratch sized for the longest basis: the building blocks below never reallocate
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     // Grids = what is RESIDENT at once.  The Gram-Schmidt kernels are grid-stride loops that end in a last-block reduction: with
     // 4 x SMs blocks and 76 registers only 3 blocks fit an SM, so a quarter of the tiles ran in a second wave of one block per SM
@@ -478,6 +478,38 @@ int sgpu_precond_apply(sgpu_ctx* c, int matrix, int precond, const double* r, do
     CK(c, cudaSetDevice(c->device));
     if (!c->lin) FAIL(c, SGPU_ERR_STATE, "sgpu_precond_setup has not been called");
     return lin_apply_pc(c, matrix, precond, r, z);
+}
+
+// Gram-Schmidt building blocks of a slab-partitioned Krylov solve: the SAME kernels sgpu_linear_solve runs, with the results left
+// on the device so that the caller can all-reduce them between the projection and the update.
+int sgpu_vec_dots(sgpu_ctx* c, const double* w, const double* V, int cnt, double* out) {
+    if (!c || !w || !V || !out || cnt < 1 || cnt > SGPU_GMRES_MAX + 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = lin_prepare(c, 1)) return rc;
+    LinWork* L = c->lin;
+    for (int g = 0; g < cnt; g += DOT_GROUP) {
+        const int k = std::min(DOT_GROUP, cnt - g);
+        dots_kernel<<<L->blocks_dots, DOT_THREADS, 0, c->stream>>>(w, V + (size_t)g*L->n, L->n, k, L->partial, L->ldp, g, out, L->ticket);
+        CKL(c); c->launches++;
+    }
+    return SGPU_OK;
+}
+int sgpu_vec_gs_update(sgpu_ctx* c, double* w, const double* V, int cnt, const double* h, double* normsq) {
+    if (!c || !w || !V || !h || !normsq || cnt < 1 || cnt > SGPU_GMRES_MAX + 1) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = lin_prepare(c, 1)) return rc;
+    LinWork* L = c->lin;
+    // the kernel writes its reduction to out[ncol]: column 0 of the caller's scalar
+    gs_update_kernel<<<L->blocks_upd, DOT_THREADS, 0, c->stream>>>(w, V, L->n, cnt, h, L->partial, L->ldp, 0, normsq, L->ticket);
+    CKL(c); c->launches++;
+    return SGPU_OK;
+}
+int sgpu_vec_scale_rsqrt(sgpu_ctx* c, double* dst, const double* src, const double* normsq) {
+    if (!c || !dst || !src || !normsq) return SGPU_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (int rc = lin_prepare(c, 1)) return rc;
+    scale_rsqrt_kernel<<<c->lin->blocks, 256, 0, c->stream>>>(dst, src, c->lin->n, normsq); CKL(c); c->launches++;
+    return SGPU_OK;
 }
 
 int sgpu_implicit_step(sgpu_ctx* c, double cfl, double under_relaxation, sgpu_linsolve* io, double* l2sq) {

@@ -110,11 +110,14 @@ class HaloExchanger:
 # tensors so that the CPU tests run it over gloo with a numpy-defined operator.
 # ---------------------------------------------------------------------------------------------------
 def distributed_gmres(apply_op: Callable, apply_pc: Callable, b, restart: int = 30, max_iter: int = 500, rtol: float = 1e-10,
-                      allreduce: Callable = None):
+                      allreduce: Callable = None, kernels=None):
     """Solve A x = b for the row block this rank owns.
 
     apply_op(x, out) / apply_pc(r, out) act on this rank's block (apply_op may exchange halos inside);
     allreduce(t) sums a small tensor over the ranks in place (None: single rank).
+    kernels: an object with vec_dots / vec_gs_update / vec_scale_rsqrt taking device pointers (GpuEulerEquation): the
+    Gram-Schmidt step then runs on the kernels of sgpu_linear_solve -- projections in one pass, update + |w|^2 in one pass,
+    scaling from the device value -- with the all-reduces in between; None: plain torch operations (the CPU tests).
     Returns (x, info) with info = {iterations, converged, rel_residual}; rel_residual is the TRUE residual.
     """
     import math
@@ -123,6 +126,7 @@ def distributed_gmres(apply_op: Callable, apply_pc: Callable, b, restart: int = 
     n, m = b.numel(), int(restart)
     V = torch.zeros((m + 1, n), dtype=b.dtype, device=b.device)
     x = torch.zeros_like(b); w = torch.zeros_like(b); z = torch.zeros_like(b); u = torch.zeros_like(b)
+    hbuf = torch.zeros(m + 2, dtype=b.dtype, device=b.device)
 
     def gsum(t):
         if allreduce is not None:
@@ -153,12 +157,21 @@ def distributed_gmres(apply_op: Callable, apply_pc: Callable, b, restart: int = 
         while k < m and iters < max_iter and not done:
             apply_pc(V[k], z)
             apply_op(z, w)
-            h = gsum(torch.mv(V[:k + 1], w))                       # classical Gram-Schmidt, one all-reduce
-            w.addmv_(V[:k + 1].t(), h, alpha=-1.0)
-            hk1 = norm(w)
-            hh = np.concatenate([h.cpu().numpy(), [hk1]])
-            if hk1 > 0.0:
-                V[k + 1].copy_(w).div_(hk1)
+            if kernels is not None:
+                kernels.vec_dots(w.data_ptr(), V.data_ptr(), k + 1, hbuf.data_ptr())
+                gsum(hbuf[:k + 1])                                 # classical Gram-Schmidt, one all-reduce
+                kernels.vec_gs_update(w.data_ptr(), V.data_ptr(), k + 1, hbuf.data_ptr(), hbuf[k + 1:].data_ptr())
+                gsum(hbuf[k + 1:k + 2])
+                kernels.vec_scale_rsqrt(V[k + 1].data_ptr(), w.data_ptr(), hbuf[k + 1:].data_ptr())
+                hh = hbuf[:k + 2].cpu().numpy().copy()             # the one host synchronisation of the iteration
+                hk1 = hh[k + 1] = math.sqrt(hh[k + 1])
+            else:
+                h = gsum(torch.mv(V[:k + 1], w))                   # classical Gram-Schmidt, one all-reduce
+                w.addmv_(V[:k + 1].t(), h, alpha=-1.0)
+                hk1 = norm(w)
+                hh = np.concatenate([h.cpu().numpy(), [hk1]])
+                if hk1 > 0.0:
+                    V[k + 1].copy_(w).div_(hk1)
             for j in range(k):                                     # Givens rotations
                 t = cs[j] * hh[j] + sn[j] * hh[j + 1]
                 hh[j + 1] = -sn[j] * hh[j] + cs[j] * hh[j + 1]
@@ -236,7 +249,7 @@ class SlabLinearSolver:
             eq.precond_apply(matrix, precond, r.data_ptr(), out.data_ptr())
 
         return distributed_gmres(lambda x, out: self.apply_op(matrix, x, out), apply_pc, b, restart, max_iter, rtol,
-                                 self._allreduce if self.world > 1 else None)
+                                 self._allreduce if self.world > 1 else None, kernels=eq if b.is_cuda else None)
 
     def adjoint_solve(self, g_host: np.ndarray, cfl: float = 100.0, max_steps: int = 50, tol: float = 1e-8, precond: str = "line_j",
                       restart: int = 40, max_iter: int = 400, rtol: float = 1e-3):
