@@ -519,6 +519,30 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             lin = {"unavailable": str(ex)[:160]}
 
+    # ---- one explicit Solver::step (rk4_jameson, src/solver/solver.cpp:109-114) on the device: dt + 4 x (BCs + residual + stage update)
+    explicit = None
+    if world == 1 and not args.no_jacobian:
+        try:
+            eq.copy_state(1, 0)
+            res = {}
+            for name, env in (("rk4_step_ms", None), ("rk4_step_two_kernel_ms", "0")):
+                if env is None:
+                    os.environ.pop("SGPU_RK_FUSED", None)
+                else:
+                    os.environ["SGPU_RK_FUSED"] = env
+                eq.explicit_step(1e-3, "rk4_jameson")
+                eq.synchronize()
+                t0 = time.time()
+                for _ in range(5):
+                    eq.explicit_step(1e-3, "rk4_jameson")
+                eq.synchronize()
+                res[name] = round((time.time() - t0) / 5 * 1e3, 3)
+            os.environ.pop("SGPU_RK_FUSED", None)
+            res["what"] = "calc_dt + 4 x (boundary conditions + residual with the stage update fused into its epilogue) + q <- q_tmp; two_kernel = residual + separate update pass"
+            explicit = res
+        except Exception as ex:  # noqa: BLE001
+            explicit = {"unavailable": str(ex)[:160]}
+
     # ---- the laminar rows the reference itself has (nv = 4, 104 B/cell): same grid, device resident, beside the COMPILED
     #      REFERENCE (oracle/_ref, kind "reference") on a bounded sample -- the one pairing against the reference's own code
     laminar = None
@@ -632,7 +656,7 @@ def run_ours(args):
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check, "setup": setup,
+               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check, "setup": setup, "explicit_step": explicit,
                "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()

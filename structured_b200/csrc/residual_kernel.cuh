@@ -45,6 +45,9 @@ struct ResParams {
     int nstrips, nchunks, rpc;
     int row0, row1;                     // local cell rows [row0, row1) this launch covers (whole slab: 0, njl)
     int strip0;                         // first strip of this launch (column-chunked host pipeline), normally 0
+    // fused Runge-Kutta stage update (update_rk4, src/solver/solver.cpp:4-13): udst[cell] = uq[cell] + rhs*udt/udiv written from the
+    // epilogue (udst = nullptr: off; udst2: a second destination for the last stage, or nullptr).  udst must not alias q.
+    const double* uq = nullptr; const double* udt = nullptr; double* udst = nullptr; double* udst2 = nullptr; double udiv = 1.0, uzinv = 1.0;
 };
 
 // vertex-average / dual-cell variable set
@@ -119,7 +122,16 @@ __device__ __forceinline__ void face_net_flux(const Gas& g, const FaceGeom& fg, 
     } else if (SA) { bars[0] = bars[1] = bars[2] = 0.0; }
 }
 
-template <int NV, int ORDER, int FLUX, bool VISC>
+// x/d for a divisor d known to the host, correctly rounded like the IEEE division the reference's stage update performs
+// (q + rhs*dt/(4.0 - order), src/solver/solver.cpp:4-13) but without its slow path: q0 = RN(x z), z = RN(1/d); the residual
+// r = x - q0 d is exact in one fma; RN(q0 + r z) is the correctly rounded quotient (d = 1, 2, 4: z exact, r = 0; d = 3: the
+// classical division-by-constant sequence).  The bitwise equality with axpy_dt_div_kernel is what the fused-stage test checks.
+__device__ __forceinline__ double div_const(double x, double d, double z) {
+    const double q0 = x*z;
+    return fma(fma(-d, q0, x), z, q0);
+}
+
+template <int NV, int ORDER, int FLUX, bool VISC, bool UPD = false>
 __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResParams prm) {
     using Cfg = ResCfg<NV, VISC>;
     constexpr bool SA = Cfg::SA;
@@ -367,6 +379,13 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         // ---- phase 3
         if (cell_ok) {
             const size_t o = v.at(jl + JOFF, c);
+            // operands of the fused stage update: requested here, used ~200 instructions later
+            double uq_[NV], udt_ = 0.0;
+            if (UPD) {
+#pragma unroll
+                for (int k = 0; k < NV; k++) uq_[k] = __ldg(prm.uq + k*pl + o);
+                udt_ = __ldg(prm.udt + o);
+            }
             const double* M0 = Mrow(jl); const double* M1 = Mrow(jl + 1);
             const double V = M0[MVOL*RW + t], Vi = rcp_fast(V);
             double res[NV];
@@ -398,6 +417,11 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
                 const double rk = res[k]*Vi;             // eulerequation.cpp:224-230
                 prm.rhs[k*pl + o] = rk;
                 acc[k] += rk*rk;
+                if (UPD) {                               // q + rhs*dt/(4.0 - order): the value axpy_dt_div_kernel computes, bit for bit
+                    const double qn = uq_[k] + div_const(rk*udt_, prm.udiv, prm.uzinv);
+                    prm.udst[k*pl + o] = qn;
+                    if (prm.udst2) prm.udst2[k*pl + o] = qn;
+                }
             }
 #pragma unroll
             for (int k = 0; k < NV; k++) Dbot[k] = Dtop[k];

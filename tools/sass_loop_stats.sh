@@ -7,9 +7,9 @@ cat > $W/rk.cu <<EOC
 #include "$HERE/include/structured_gpu.h"
 #include "common.cuh"
 #include "residual_kernel.cuh"
-template __global__ void sg::residual_kernel<5, 2, SGPU_FLUX_ROE, true>(const sg::ResParams);
+template __global__ void sg::residual_kernel<5, 2, SGPU_FLUX_ROE, true, SG_SASS_UPD>(const sg::ResParams);
 EOC
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I$HERE/structured_b200/csrc "$@" -Xptxas -v -cubin -o $W/rk.cubin $W/rk.cu 2>&1 | grep -E "registers|spill|error"
+nvcc -DSG_SASS_UPD=${SG_SASS_UPD:-false} -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I$HERE/structured_b200/csrc "$@" -Xptxas -v -cubin -o $W/rk.cubin $W/rk.cu 2>&1 | grep -E "registers|spill|error"
 cuobjdump -sass $W/rk.cubin > $W/rk.sass
 python3 - $W/rk.sass <<'PY'
 import re, collections, sys
