@@ -182,6 +182,23 @@ __global__ void axpy_dt_kernel(View v, double* __restrict__ dst, const double* _
         dst[ok] = q[ok] + rhs[ok]*d*inv_div;      // inv_div = 1/(4-order) (exact for 1, 1/2, 1/4; 1/3 differs by <= 1 ulp)
     }
 }
+// ghost frame of a state (the two padded rows below / above the owned rows and the padded columns left / right of the cells) copied
+// from src to dst, all nv planes: the fused Runge-Kutta stages write their result into the OTHER q_tmp buffer, whose ghost cells
+// must look to the next boundary-condition pass exactly as q_tmp's own would have (a BC may read a ghost cell a later table writes)
+__global__ void ghost_frame_copy_kernel(View v, double* __restrict__ dst, const double* __restrict__ src, int cols) {
+    int r, c;
+    if (!cols) {                                   // the 2 JOFF ghost rows, every column: grid (pitch/128, 2 JOFF)
+        c = blockIdx.x*blockDim.x + threadIdx.x;
+        r = (int)blockIdx.y < JOFF ? (int)blockIdx.y : v.njl + (int)blockIdx.y;
+        if (c >= v.pitch) return;
+    } else {                                       // the ghost / padding columns of the owned rows: grid (rows/128, pitch - nic)
+        r = JOFF + blockIdx.x*blockDim.x + threadIdx.x;
+        c = (int)blockIdx.y < IOFF ? (int)blockIdx.y : v.nic + (int)blockIdx.y;
+        if (r >= JOFF + v.njl) return;
+    }
+    const size_t o = v.at(r, c);
+    for (int k = 0; k < v.nv; k++) dst[k*v.plane + o] = src[k*v.plane + o];
+}
 // the reference divides: q + rhs*dt/(4.0-order).  Keep that form for bit-fidelity of the stage update.
 __global__ void axpy_dt_div_kernel(View v, double* __restrict__ dst, const double* __restrict__ q, const double* __restrict__ rhs,
                                    const double* __restrict__ dt, double div) {

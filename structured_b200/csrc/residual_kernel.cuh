@@ -362,6 +362,12 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
         // next row's HBM traffic overlaps this row's flux arithmetic; the metric ring slot is that of row jl-1
         // and the staging row was consumed above: no reader is left after the barrier
         if (jl + 1 < rb) fetch_async(jl + 3, jl + 1);
+        if (UPD && jl + 1 < rb) {                          // the stage update's operands of the NEXT row: into L2, so that phase 3's loads find them there
+            const size_t on = v.at(jl + 1 + JOFF, c);
+#pragma unroll
+            for (int k = 0; k < NV; k++) asm volatile("prefetch.global.L2 [%0];" :: "l"(prm.uq + k*pl + on));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(prm.udt + on));
+        }
         double Dtop[NV], btop[3] = {0, 0, 0}, Dchi[NV], bchi[3] = {0, 0, 0};
         // both faces unconditionally, in one basic block: the halo lanes of a warp execute the face code anyway, and
         // without the two divergent regions the scheduler interleaves the independent eta / chi chains (A/B: 1.365 ->

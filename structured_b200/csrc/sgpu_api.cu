@@ -871,6 +871,9 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
             c->launches++;
             c->wall_valid = true;
         }
+        ghost_frame_copy_kernel<<<dim3((v.pitch + 127)/128, 2*JOFF), 128, 0, c->stream>>>(v, c->q_scratch, c->q[1], 0);
+        ghost_frame_copy_kernel<<<dim3((v.njl + 127)/128, v.pitch - v.nic), 128, 0, c->stream>>>(v, c->q_scratch, c->q[1], 1);
+        c->launches += 2;
         std::swap(c->q[1], c->q_scratch); swaps++;                 // q_tmp now names the buffer just written
     }
     if (swaps & 1) std::swap(c->q[1], c->q_scratch);               // only after an error: keep the pointers where they were
