@@ -542,13 +542,13 @@ static int launch_residual_t(sgpu_ctx* c, ResParams& p, int* grid_out) {
 }
 
 // fused stage update handed to the residual kernel's epilogue: dst = q + rhs*dt/div on the owned cells (dst must not be the state evaluated)
-struct StageUpdate { const double* q; const double* dt; double* dst; double div; };
+struct StageUpdate { const double* q; const double* dt; double* dst; double div; double* dst2 = nullptr; };
 
 static int launch_residual(sgpu_ctx* c, int which, int lhs, bool want_norms, int row0 = 0, int row1 = -1, int strip0 = 0, int nstrips = 0,
                            const StageUpdate* upd = nullptr) {
     const View& v = c->v;
     ResParams p;
-    if (upd) { p.uq = upd->q; p.udt = upd->dt; p.udst = upd->dst; p.udiv = upd->div; p.uzinv = 1.0/upd->div; }
+    if (upd) { p.uq = upd->q; p.udt = upd->dt; p.udst = upd->dst; p.udst2 = upd->dst2; p.udiv = upd->div; p.uzinv = 1.0/upd->div; }
     p.row0 = row0; p.row1 = row1 < 0 ? v.njl : row1;
     p.strip0 = strip0; p.nstrips = nstrips;
     p.v = v; p.g = c->g; p.m = metrics_of(c);
@@ -863,6 +863,9 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
         rc = apply_bcs(c, SGPU_STATE_Q_TMP);
         if (rc != SGPU_OK) break;
         StageUpdate upd{c->q[0], c->dt, c->q_scratch, 4.0 - order};
+        // the last stage also writes q itself (q <- q_tmp, solver.cpp:114: each thread reads its own cell of q before it writes it;
+        // q's ghost cells are re-made by the boundary-condition pass every consumer of them runs first)
+        if (order == 3) upd.dst2 = c->q[0];
         rc = launch_residual(c, SGPU_STATE_Q_TMP, 0, order == 3 && l2sq != nullptr, 0, -1, 0, 0, &upd);
         if (rc != SGPU_OK) break;
         if (c->wall_track && v.j0 == 0 && v.njl >= 2) {            // as in sgpu_residual: the wall rows of this evaluation
@@ -882,7 +885,7 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
         CK(c, cudaMemcpyAsync(l2sq, c->l2sq_dev, sizeof(double)*v.nv, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
     }
-    return sgpu_copy_state(c, SGPU_STATE_Q, SGPU_STATE_Q_TMP);     // solver.cpp:114
+    return SGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- surface output
