@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(RW, SG_RES_MINB) residual_kernel(const ResPara
             double uq_[NV], udt_ = 0.0;
             if (UPD) {
 #pragma unroll
-                for (int k = 0; k < NV; k++) uq_[k] = __ldg(prm.uq + k*pl + o);
+                for (int k = 0; k < NV; k++) uq_[k] = prm.uq[k*pl + o];      // plain loads: the last stage writes these cells of q itself (udst2)
                 udt_ = __ldg(prm.udt + o);
             }
             const double* M0 = Mrow(jl); const double* M1 = Mrow(jl + 1);
