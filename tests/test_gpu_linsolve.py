@@ -351,3 +351,32 @@ def test_transposed_products_across_slabs_equal_single_slab(ntrans, split):
         assert float(torch.dot(ys[0], ys[0]) + torch.dot(ys[1], ys[1])) == pytest.approx(float((got * got).sum()), rel=1e-12)
     for s in slabs + [one]:
         s.close()
+
+
+def test_gram_schmidt_building_blocks_match_numpy():
+    """sgpu_vec_dots / sgpu_vec_gs_update / sgpu_vec_scale_rsqrt (the kernels of the one-GPU GMRES, exported for the slab solver):
+    projections, update + |w|^2 in one pass and the scaling from the device value against numpy on random vectors"""
+    import torch
+    case = turbulent_channel_case(150, 64, ntrans=1, reynolds=1e5)
+    eq = gpu_eq(case)
+    n = eq.vec_size()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for cnt in (1, 5, 17, 33):                               # 17, 33: more than one group of 16 basis vectors per pass
+        V = torch.randn((cnt, n), dtype=torch.float64, device="cuda", generator=g)
+        w = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        w0 = w.clone()
+        h = torch.zeros(cnt + 1, dtype=torch.float64, device="cuda")
+        eq.vec_dots(w.data_ptr(), V.data_ptr(), cnt, h.data_ptr())
+        eq.synchronize()
+        want_h = (V.cpu().numpy() @ w0.cpu().numpy())
+        assert np.abs(h[:cnt].cpu().numpy() - want_h).max() <= 1e-12 * np.abs(want_h).max() * np.sqrt(n)
+        eq.vec_gs_update(w.data_ptr(), V.data_ptr(), cnt, h.data_ptr(), h[cnt:].data_ptr())
+        eq.synchronize()
+        want_w = w0.cpu().numpy() - V.cpu().numpy().T @ h[:cnt].cpu().numpy()
+        assert np.abs(w.cpu().numpy() - want_w).max() <= 1e-12 * np.abs(want_w).max()
+        assert abs(float(h[cnt]) - float(want_w @ want_w)) <= 1e-12 * float(want_w @ want_w)
+        dst = torch.zeros_like(w)
+        eq.vec_scale_rsqrt(dst.data_ptr(), w.data_ptr(), h[cnt:].data_ptr())
+        eq.synchronize()
+        assert np.abs(dst.cpu().numpy() - want_w / np.sqrt(want_w @ want_w)).max() <= 1e-14
+    eq.close()
