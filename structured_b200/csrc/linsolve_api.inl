@@ -20,6 +20,7 @@ struct LinWork {
     unsigned* ticket = nullptr;    // arrival counter of the in-kernel final reductions
     int blocks = 0, ldp = 0;       // blocks: grid of the flat vector kernels (and the capacity of `partial`)
     int blocks_dots = 0, blocks_upd = 0;   // grids of the two Gram-Schmidt kernels = exactly ONE resident wave each
+    bool twisted = false;          // the line factors in Dinv are those of the twisted factorisation (line_apply_twisted_kernel reads them)
 };
 
 static void lin_free(LinWork*& L) {
@@ -104,8 +105,15 @@ static int lin_factor(sgpu_ctx* c, int matrix, int precond) {
         // Gauss-Jordan pivot search / row broadcasts become dependent shuffles -- measured 29.2 vs 22.7 ms at 4096^2, identical factors)
         const char* lf = getenv("SGPU_LINE_FACTOR");
         const bool serial = !(lf && !strcmp(lf, "rows"));
+        // default: the TWISTED factorisation (two warps per 32 lines, eliminating from both ends towards the middle row: half the
+        // sequential rows per warp); SGPU_LINE_TWISTED=0 or SGPU_LINE_FACTOR=rows select the one-directional forms
+        const char* tw = getenv("SGPU_LINE_TWISTED");
+        L->twisted = serial && !(tw && atoi(tw) == 0);
 #define LINE_FACTOR(NV_) do { \
-        if (serial) { \
+        if (L->twisted) { \
+            CK(c, cudaFuncSetAttribute(line_factor_twisted_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_twisted_bytes<NV_>())); \
+            line_factor_twisted_kernel<NV_><<<(v.nic + 31)/32, 64, fact_twisted_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); \
+        } else if (serial) { \
             CK(c, cudaFuncSetAttribute(line_factor_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fact_ring_bytes<NV_>())); \
             line_factor_kernel<NV_><<<(v.nic + 31)/32, 32, fact_ring_bytes<NV_>(), c->stream>>>(v, c->jac.blocks, c->dt, op, c->jac.slots, L->Dinv, L->err); \
         } else { \
@@ -135,8 +143,15 @@ static int lin_apply_pc(sgpu_ctx* c, int matrix, int precond, const double* r, d
 #define LINE_APPLY(NV_, TR_) do { \
         CK(c, cudaFuncSetAttribute(line_apply_kernel<NV_, TR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)line_ring_bytes<NV_>())); \
         line_apply_kernel<NV_, TR_><<<nb, 32, line_ring_bytes<NV_>(), c->stream>>>(v, L->Dinv, r, z); } while (0)
-        if (mat_transposed(matrix)) { if (v.nv == 5) LINE_APPLY(5, true); else LINE_APPLY(4, true); }
+#define LINE_APPLY_TW(NV_, TR_) do { \
+        CK(c, cudaFuncSetAttribute(line_apply_twisted_kernel<NV_, TR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)line_twisted_bytes<NV_>())); \
+        line_apply_twisted_kernel<NV_, TR_><<<nb, 64, line_twisted_bytes<NV_>(), c->stream>>>(v, L->Dinv, r, z); } while (0)
+        if (L->twisted) {
+            if (mat_transposed(matrix)) { if (v.nv == 5) LINE_APPLY_TW(5, true); else LINE_APPLY_TW(4, true); }
+            else { if (v.nv == 5) LINE_APPLY_TW(5, false); else LINE_APPLY_TW(4, false); }
+        } else if (mat_transposed(matrix)) { if (v.nv == 5) LINE_APPLY(5, true); else LINE_APPLY(4, true); }
         else { if (v.nv == 5) LINE_APPLY(5, false); else LINE_APPLY(4, false); }
+#undef LINE_APPLY_TW
 #undef LINE_APPLY
     } else {
         const dim3 grd((v.nic + 127)/128, v.njl);

@@ -535,6 +535,199 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// TWISTED factorisation (round 2b; the solve is line_apply_twisted_kernel): two warps per 32 lines eliminate from both ends of
+// the line towards the middle row m = njl/2.  Below m: D'_j = D_j - A'_j DC_{j-1} as above.  Above m, descending:
+// D''_j = D_j - C'_j DA_{j+1}.  Middle row: D*_m = D_m - A'_m DC_{m-1} - C'_m DA_{m+1}.  Every row stores Dinv = (its eliminated
+// diagonal)^-1, DA = Dinv A', DC = Dinv C' as before -- which of the two the neighbouring row's elimination uses depends on the
+// side.  Half the dependent rows per warp: the setup halves.
+// ------------------------------------------------------------------------------------------------
+constexpr int TWF_STAGES = 3;
+template <int NV> constexpr size_t fact_twisted_bytes() { return (size_t)2*TWF_STAGES*fact_ring_planes<NV>()*32*sizeof(double) + 2*NV*NV*32*sizeof(double); }
+
+template <int NV>
+__global__ void __launch_bounds__(64) line_factor_twisted_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, int nslots,
+                                                                 double* __restrict__ F, int* __restrict__ err) {
+    extern __shared__ double tw_fring[];
+    constexpr int B = NV*NV, NP = 5*NV*NV + 1, S = TWF_STAGES;
+    const int lane = threadIdx.x & 31, up = threadIdx.x >> 5;
+    double* fring = tw_fring + (size_t)up*S*NP*32;
+    double* ex = tw_fring + (size_t)2*S*NP*32;                     // [2][B][32]: the product each half hands to the middle row
+    const int i = blockIdx.x*32 + lane;
+    const bool live = i < v.nic;
+    const int ic = live ? i : v.nic - 1;                           // idle lanes shadow the last line and never store
+    const size_t pl = v.plane;
+    double* __restrict__ Dinv = F;
+    double* __restrict__ DAo = F + (size_t)B*pl;
+    double* __restrict__ DCo = F + (size_t)2*B*pl;
+    const bool arms = nslots > 9;
+    const int n = v.njl, m = n/2;
+    const int row0 = up ? n - 1 : 0, step = up ? -1 : 1, count = up ? n - 1 - m : m;
+    auto slot = [&](int st, int p) -> double* { return fring + ((size_t)st*NP + p)*32 + lane; };
+    auto issue = [&](int k) {                                      // k-th row of this half; ring group g = 0..4 <- Jacobian slots 0, 3, 11, 4, 12
+        if (k < count) {
+            const size_t o = v.at(row0 + k*step + JOFF, ic + IOFF);
+            const int st = k % S;
+#pragma unroll
+            for (int g = 0; g < 5; g++) {
+                const int sl = g == 0 ? 0 : (g == 1 ? 3 : (g == 2 ? 11 : (g == 3 ? 4 : 12)));
+                if ((g == 2 || g == 4) && !arms) continue;
+#pragma unroll
+                for (int e = 0; e < B; e++) fact_cp_async8(slot(st, g*B + e), J + ((size_t)sl*B + e)*pl + o);
+            }
+            if (op == OP_LHS) fact_cp_async8(slot(st, 5*B), dt + o);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto ring_row = [&](int st, int g, int ga, bool arm, int r, double (&a)[NV]) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            double vj = *slot(st, g*B + r*NV + c);
+            if (arm) vj += *slot(st, ga*B + r*NV + c);
+            a[c] = op == OP_LHS ? -vj : vj;
+        }
+    };
+    for (int k = 0; k < S - 1; k++) issue(k);
+    double P[NV][NV];                                              // Dinv x (the block towards the middle) of the previous row of this half
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) P[r][c] = 0.0;
+    // X = the block that couples a row to the previous row of its half (A' below the middle, C' above), Y = the other one
+    const int gx = up ? 3 : 1, gxa = up ? 4 : 2, gy = up ? 1 : 3, gya = up ? 2 : 4;
+    double* __restrict__ DX = up ? DCo : DAo;                      // Dinv X is stored where Dinv A' / Dinv C' belong
+    double* __restrict__ DY = up ? DAo : DCo;
+    for (int k = 0; k < count; k++) {
+        issue(k + S - 1);
+        asm volatile("cp.async.wait_group %0;" :: "n"(S - 1) : "memory");
+        const int st = k % S;
+        const int jl = row0 + k*step, gj = v.j0 + jl;
+        const size_t o = v.at(jl + JOFF, ic + IOFF);
+        const bool has_a = jl > 0, has_c = jl + 1 < n;
+        const bool arm_a = arms && gj - 2 >= 0, arm_c = arms && gj + 2 <= v.njc - 1;
+        const bool has_x = up ? has_c : has_a, has_y = up ? has_a : has_c, arm_x = up ? arm_c : arm_a, arm_y = up ? arm_a : arm_c;
+        double D[NV][NV], I[NV][NV];
+        {
+            const double idt = op == OP_LHS ? rcp_fast(*slot(st, 5*B)) : 0.0;
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    const double vj = *slot(st, r*NV + c);
+                    D[r][c] = op == OP_LHS ? (r == c ? idt - vj : -vj) : vj;
+                }
+        }
+        if (has_x && k > 0) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double a[NV];
+                ring_row(st, gx, gxa, arm_x, r, a);
+#pragma unroll
+                for (int kk = 0; kk < NV; kk++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) D[r][c] = fma(-a[kk], P[kk][c], D[r][c]);
+            }
+        }
+        if (!invert_block_fast<NV>(D, I) && live) atomicExch(err, 1);
+        double DXv[NV][NV];
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) { DXv[r][c] = 0.0; P[r][c] = 0.0; }
+        if (has_x) {
+#pragma unroll
+            for (int kk = 0; kk < NV; kk++) {
+                double a[NV];
+                ring_row(st, gx, gxa, arm_x, kk, a);
+#pragma unroll
+                for (int r = 0; r < NV; r++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) DXv[r][c] = fma(I[r][kk], a[c], DXv[r][c]);
+            }
+        }
+        if (has_y) {
+#pragma unroll
+            for (int kk = 0; kk < NV; kk++) {
+                double a[NV];
+                ring_row(st, gy, gya, arm_y, kk, a);
+#pragma unroll
+                for (int r = 0; r < NV; r++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) P[r][c] = fma(I[r][kk], a[c], P[r][c]);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DX[(size_t)(r*NV + c)*pl + o] = DXv[r][c]; DY[(size_t)(r*NV + c)*pl + o] = P[r][c];
+                }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- the middle row: D* = D - A' DC_{m-1} - C' DA_{m+1}
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+        for (int c = 0; c < NV; c++) ex[((size_t)up*B + r*NV + c)*32 + lane] = P[r][c];
+    __syncthreads();
+    if (up) return;
+    {
+        const int jl = m, gj = v.j0 + jl;
+        const size_t o = v.at(jl + JOFF, ic + IOFF);
+        const bool has_a = jl > 0, has_c = jl + 1 < n;
+        const bool arm_a = arms && gj - 2 >= 0, arm_c = arms && gj + 2 <= v.njc - 1;
+        auto gblock = [&](int sl, int sla, bool arm, bool diag, double (&a)[NV][NV]) {     // straight from the Jacobian planes
+            const double idt = (diag && op == OP_LHS) ? 1.0/dt[o] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    double vj = J[((size_t)sl*B + r*NV + c)*pl + o];
+                    if (arm) vj += J[((size_t)sla*B + r*NV + c)*pl + o];
+                    a[r][c] = op == OP_LHS ? ((diag && r == c) ? idt - vj : -vj) : vj;
+                }
+        };
+        double D[NV][NV], A[NV][NV], C[NV][NV], I[NV][NV];
+        gblock(0, 0, false, true, D);
+#pragma unroll
+        for (int r = 0; r < NV; r++)
+#pragma unroll
+            for (int c = 0; c < NV; c++) { A[r][c] = 0.0; C[r][c] = 0.0; }
+        if (has_a) {
+            gblock(3, 11, arm_a, false, A);
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int kk = 0; kk < NV; kk++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) D[r][c] = fma(-A[r][kk], ex[((size_t)kk*NV + c)*32 + lane], D[r][c]);
+        }
+        if (has_c) {
+            gblock(4, 12, arm_c, false, C);
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int kk = 0; kk < NV; kk++)
+#pragma unroll
+                    for (int c = 0; c < NV; c++) D[r][c] = fma(-C[r][kk], ex[((size_t)B + kk*NV + c)*32 + lane], D[r][c]);
+        }
+        if (!invert_block_fast<NV>(D, I) && live) atomicExch(err, 1);
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < NV; r++)
+#pragma unroll
+                for (int c = 0; c < NV; c++) {
+                    double sa = 0.0, sc = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < NV; kk++) { sa = fma(I[r][kk], A[kk][c], sa); sc = fma(I[r][kk], C[kk][c], sc); }
+                    Dinv[(size_t)(r*NV + c)*pl + o] = I[r][c]; DAo[(size_t)(r*NV + c)*pl + o] = sa; DCo[(size_t)(r*NV + c)*pl + o] = sc;
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row-parallel form of line_factor_kernel (round 2).  The recurrence is sequential in j and the kernel above gives the
 // whole GPU nic/32 warps (128 at 4096^2: less than one per SM), each executing ~1 500 dependent instructions per row.
 // Here a line is worked on by NV lanes -- lane (l, r) holds ROW r of every block of line l -- so a warp covers 32/NV lines,
@@ -882,6 +1075,199 @@ __global__ void __launch_bounds__(32) line_apply_kernel(View v, const double* __
         }
         cp_async_wait<0>();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TWISTED line solve (round 2b).  The sweeps above are sequential in j and what bounds them is one warp's instruction stream per
+// row, so the lever is the LENGTH of the sequence: the line is eliminated from BOTH ends towards its middle row m = njl/2 by two
+// warps of one CTA -- rows 0 .. m-1 ascending with (Dinv, DA) exactly as before, rows njl-1 .. m+1 descending with the roles of the
+// sub- and super-diagonal blocks exchanged (factors from line_factor_twisted_kernel: D''_j = D_j - C_j DA_{j+1}) -- the two halves
+// meet in the middle row, x_m = Dinv_m r_m - DA_m y_{m-1} - DC_m y_{m+1}, and both substitute back outwards.  The same
+// block-tridiagonal system, hence the same preconditioner up to rounding; half the dependent rows per warp.  The transposed
+// solve is the adjoint of that sequence: inward sweeps with the transposed back-substitution blocks, the middle row, outward
+// sweeps with the transposed elimination blocks.
+//   mode 0  inward,  A x = r :  g = P0 r - P1 t;  t = g;                 z = g      (P0 = Dinv, P1 = DA below / DC above)
+//   mode 1  outward, A x = r :  g = y - P0 t;     t = g;                 z = g      (P0 = DC below / DA above)
+//   mode 2  inward,  A^T     :  g = r - t;        t = P0^T g;            z = g      (P0 = DC below / DA above)
+//   mode 3  outward, A^T     :  w = y - t;        t = P0^T w;            z = P1^T w (P0 = DA below / DC above, P1 = Dinv)
+// ------------------------------------------------------------------------------------------------
+constexpr int TW_STAGES = 6;
+template <int NV> constexpr size_t line_twisted_bytes() { return (size_t)2*TW_STAGES*line_ring_planes<NV>()*32*sizeof(double) + 2*NV*32*sizeof(double); }
+
+template <int NV, int MODE>
+__device__ __forceinline__ void twisted_sweep(const View& v, double* __restrict__ ring, int lane, int c0, bool live, int row0, int step, int count,
+                                              const double* __restrict__ P0, const double* __restrict__ P1, const double* __restrict__ vec,
+                                              double* __restrict__ z, double (&t)[NV]) {
+    constexpr int B = NV*NV, BP = B + (B & 1), NP = 2*BP + NV + (NV & 1), S = TW_STAGES;
+    const size_t pl = v.plane;
+    const int half = lane >> 4, word = (lane & 15)*2;
+    const bool in_row = c0 + word < v.pitch;
+    const size_t lane_src = (size_t)half*pl + word;
+    const unsigned lane_dst = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)((half*32 + word)*sizeof(double));
+    auto slot = [&](int st, int p) -> double* { return ring + ((size_t)st*NP + p)*32 + lane; };
+    auto issue_row = [&](int n) {                                  // n-th row of this sweep = row row0 + n step
+        if (n < count && in_row) {
+            const size_t o = v.at(row0 + n*step + JOFF, c0) + lane_src;
+            const unsigned d = lane_dst + (unsigned)((n % S)*NP*32*sizeof(double));
+            auto group = [&](const double* src, int first, int cnt) {
+#pragma unroll
+                for (int h = 0; h < (cnt + 1)/2; h++)
+                    if (2*h + 1 < cnt || half == 0)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)((first + 2*h)*32*sizeof(double))), "l"(src + o + (size_t)(2*h)*pl) : "memory");
+            };
+            group(P0, 0, B);
+            if (MODE == 0 || MODE == 3) group(P1, BP, B);
+            group(vec, 2*BP, NV);
+        }
+        cp_async_commit();
+    };
+    for (int n = 0; n < S - 1; n++) issue_row(n);
+    for (int n = 0; n < count; n++) {
+        __syncwarp();                                              // every lane is done with the stage the next copy overwrites
+        issue_row(n + S - 1);
+        const int st = n % S;
+        cp_async_wait<S - 1>();
+        __syncwarp();
+        const size_t o = v.at(row0 + n*step + JOFF, c0 + lane);
+        double g[NV];
+        if (MODE == 0) {
+            double rr[NV];
+#pragma unroll
+            for (int r = 0; r < NV; r++) rr[r] = *slot(st, 2*BP + r);
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < NV; c++) s += *slot(st, r*NV + c)*rr[c];
+                g[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double s = g[r];
+#pragma unroll
+                for (int c = 0; c < NV; c++) s -= *slot(st, BP + r*NV + c)*t[c];
+                g[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < NV; r++) t[r] = g[r];
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double s = *slot(st, 2*BP + r);
+#pragma unroll
+                for (int c = 0; c < NV; c++) s -= *slot(st, r*NV + c)*t[c];
+                g[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < NV; r++) t[r] = g[r];
+        } else if (MODE == 2) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) g[r] = *slot(st, 2*BP + r) - t[r];
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < NV; r++) s += *slot(st, r*NV + c)*g[r];
+                t[c] = s;
+            }
+        } else {
+            double w[NV];
+#pragma unroll
+            for (int r = 0; r < NV; r++) w[r] = *slot(st, 2*BP + r) - t[r];
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < NV; r++) s += *slot(st, r*NV + c)*w[r];
+                t[c] = s;
+            }
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < NV; r++) s += *slot(st, BP + r*NV + c)*w[r];
+                g[c] = s;
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) z[r*pl + o] = g[r];
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <int NV, bool TR>
+__global__ void __launch_bounds__(64) line_apply_twisted_kernel(View v, const double* __restrict__ F, const double* __restrict__ rv, double* __restrict__ z) {
+    extern __shared__ __align__(128) double tw_smem[];
+    constexpr int B = NV*NV, BP = B + (B & 1), NP = 2*BP + NV + (NV & 1), S = TW_STAGES;
+    const int lane = threadIdx.x & 31, up = threadIdx.x >> 5;      // warp 0: the rows below the middle row, warp 1: the rows above it
+    double* ring = tw_smem + (size_t)up*S*NP*32;
+    double* ex = tw_smem + (size_t)2*S*NP*32;                      // [2][NV][32]: what each half hands to the middle row
+    const int i = blockIdx.x*32 + lane;
+    const bool live = i < v.nic;
+    const int c0 = blockIdx.x*32 + IOFF;
+    const size_t pl = v.plane;
+    const double* __restrict__ Dinv = F;
+    const double* __restrict__ DA = F + (size_t)B*pl;
+    const double* __restrict__ DC = F + (size_t)2*B*pl;
+    for (int k = lane; k < S*NP*32; k += 32) ring[k] = 0.0;        // words past a short last segment are never written by the copies
+    __syncwarp();
+    const int n = v.njl, m = n/2;
+    const int row0 = up ? n - 1 : 0, step = up ? -1 : 1, count = up ? n - 1 - m : m;
+    double t[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) t[r] = 0.0;
+    // ---- inward
+    if (!TR) twisted_sweep<NV, 0>(v, ring, lane, c0, live, row0, step, count, Dinv, up ? DC : DA, rv, z, t);
+    else twisted_sweep<NV, 2>(v, ring, lane, c0, live, row0, step, count, up ? DA : DC, nullptr, rv, z, t);
+#pragma unroll
+    for (int r = 0; r < NV; r++) ex[(up*NV + r)*32 + lane] = t[r];
+    __threadfence();                                               // the z rows written above are copied in below by OTHER lanes
+    __syncthreads();
+    // ---- the middle row (both warps evaluate it; warp 0 stores it)
+    {
+        const int ic = imin(c0 + lane, v.pitch - 1);               // lanes past the last line shadow a valid column and never store
+        const size_t o = v.at(m + JOFF, ic);
+        double tl[NV], tu[NV], rm[NV], xm[NV];
+#pragma unroll
+        for (int r = 0; r < NV; r++) { tl[r] = ex[r*32 + lane]; tu[r] = ex[(NV + r)*32 + lane]; rm[r] = rv[r*pl + o]; }
+        if (!TR) {
+#pragma unroll
+            for (int r = 0; r < NV; r++) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < NV; c++) s += Dinv[(size_t)(r*NV + c)*pl + o]*rm[c] - DA[(size_t)(r*NV + c)*pl + o]*tl[c] - DC[(size_t)(r*NV + c)*pl + o]*tu[c];
+                xm[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < NV; r++) t[r] = xm[r];
+            if (live && !up) {
+#pragma unroll
+                for (int r = 0; r < NV; r++) z[r*pl + o] = xm[r];
+            }
+        } else {
+            double w[NV];
+#pragma unroll
+            for (int r = 0; r < NV; r++) w[r] = rm[r] - tl[r] - tu[r];
+            const double* __restrict__ Pt = up ? DC : DA;          // what the outward sweep of this half subtracts first
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double s = 0.0, so = 0.0;
+#pragma unroll
+                for (int r = 0; r < NV; r++) { s += Pt[(size_t)(r*NV + c)*pl + o]*w[r]; so += Dinv[(size_t)(r*NV + c)*pl + o]*w[r]; }
+                t[c] = s; xm[c] = so;
+            }
+            if (live && !up) {
+#pragma unroll
+                for (int r = 0; r < NV; r++) z[r*pl + o] = xm[r];
+            }
+        }
+    }
+    // ---- outward: the rows of this half in the opposite order
+    const int orow0 = up ? m + 1 : m - 1, ostep = -step;
+    if (!TR) twisted_sweep<NV, 1>(v, ring, lane, c0, live, orow0, ostep, count, up ? DA : DC, nullptr, z, z, t);
+    else twisted_sweep<NV, 3>(v, ring, lane, c0, live, orow0, ostep, count, up ? DC : DA, Dinv, z, z, t);
 }
 
 // ------------------------------------------------------------------------------------------------
