@@ -542,13 +542,14 @@ __global__ void __launch_bounds__(32) line_factor_kernel(View v, const double* _
 // side.  Half the dependent rows per warp: the setup halves.
 // ------------------------------------------------------------------------------------------------
 constexpr int TWF_STAGES = 3;
-template <int NV> constexpr size_t fact_twisted_bytes() { return (size_t)2*TWF_STAGES*fact_ring_planes<NV>()*32*sizeof(double) + 2*NV*NV*32*sizeof(double); }
+template <int NV> constexpr int fact_twisted_planes() { return 5*(NV*NV + (NV*NV & 1)) + 2; }      // five block groups padded to even plane counts + the dt pair
+template <int NV> constexpr size_t fact_twisted_bytes() { return (size_t)2*TWF_STAGES*fact_twisted_planes<NV>()*32*sizeof(double) + 2*NV*NV*32*sizeof(double); }
 
 template <int NV>
 __global__ void __launch_bounds__(64) line_factor_twisted_kernel(View v, const double* __restrict__ J, const double* __restrict__ dt, int op, int nslots,
                                                                  double* __restrict__ F, int* __restrict__ err) {
     extern __shared__ double tw_fring[];
-    constexpr int B = NV*NV, NP = 5*NV*NV + 1, S = TWF_STAGES;
+    constexpr int B = NV*NV, BP = B + (B & 1), NP = 5*BP + 2, S = TWF_STAGES;
     const int lane = threadIdx.x & 31, up = threadIdx.x >> 5;
     double* fring = tw_fring + (size_t)up*S*NP*32;
     double* ex = tw_fring + (size_t)2*S*NP*32;                     // [2][B][32]: the product each half hands to the middle row
@@ -563,26 +564,38 @@ __global__ void __launch_bounds__(64) line_factor_twisted_kernel(View v, const d
     const int n = v.njl, m = n/2;
     const int row0 = up ? n - 1 : 0, step = up ? -1 : 1, count = up ? n - 1 - m : m;
     auto slot = [&](int st, int p) -> double* { return fring + ((size_t)st*NP + p)*32 + lane; };
+    // sixteen-byte copies, two planes of one block per instruction (lanes 0-15 the first, 16-31 the second), as in the sweeps
+    const int half = lane >> 4, word = (lane & 15)*2;
+    const int c0 = blockIdx.x*32 + IOFF;
+    const bool in_row = c0 + word < v.pitch;
+    const size_t lane_src = (size_t)half*pl + word;
+    const unsigned lane_dst = (unsigned)__cvta_generic_to_shared(fring) + (unsigned)((half*32 + word)*sizeof(double));
+    for (int k = lane; k < S*NP*32; k += 32) fring[k] = 1.0;      // words past a short last segment are never copied
+    __syncwarp();
     auto issue = [&](int k) {                                      // k-th row of this half; ring group g = 0..4 <- Jacobian slots 0, 3, 11, 4, 12
-        if (k < count) {
-            const size_t o = v.at(row0 + k*step + JOFF, ic + IOFF);
-            const int st = k % S;
+        if (k < count && in_row) {
+            const size_t o = v.at(row0 + k*step + JOFF, c0) + lane_src;
+            const unsigned d = lane_dst + (unsigned)((k % S)*NP*32*sizeof(double));
 #pragma unroll
             for (int g = 0; g < 5; g++) {
                 const int sl = g == 0 ? 0 : (g == 1 ? 3 : (g == 2 ? 11 : (g == 3 ? 4 : 12)));
                 if ((g == 2 || g == 4) && !arms) continue;
+                const double* src = J + (size_t)sl*B*pl + o;
 #pragma unroll
-                for (int e = 0; e < B; e++) fact_cp_async8(slot(st, g*B + e), J + ((size_t)sl*B + e)*pl + o);
+                for (int h = 0; h < (B + 1)/2; h++)
+                    if (2*h + 1 < B || half == 0)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)((g*BP + 2*h)*32*sizeof(double))), "l"(src + (size_t)(2*h)*pl) : "memory");
             }
-            if (op == OP_LHS) fact_cp_async8(slot(st, 5*B), dt + o);
+            if (op == OP_LHS && half == 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)(5*BP*32*sizeof(double))), "l"(dt + v.at(row0 + k*step + JOFF, c0) + word) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto ring_row = [&](int st, int g, int ga, bool arm, int r, double (&a)[NV]) {
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            double vj = *slot(st, g*B + r*NV + c);
-            if (arm) vj += *slot(st, ga*B + r*NV + c);
+            double vj = *slot(st, g*BP + r*NV + c);
+            if (arm) vj += *slot(st, ga*BP + r*NV + c);
             a[c] = op == OP_LHS ? -vj : vj;
         }
     };
@@ -597,8 +610,10 @@ __global__ void __launch_bounds__(64) line_factor_twisted_kernel(View v, const d
     double* __restrict__ DX = up ? DCo : DAo;                      // Dinv X is stored where Dinv A' / Dinv C' belong
     double* __restrict__ DY = up ? DAo : DCo;
     for (int k = 0; k < count; k++) {
+        __syncwarp();                                              // every lane is done with the stage the next copy overwrites
         issue(k + S - 1);
         asm volatile("cp.async.wait_group %0;" :: "n"(S - 1) : "memory");
+        __syncwarp();                                              // the other lanes' copies of this row have landed too
         const int st = k % S;
         const int jl = row0 + k*step, gj = v.j0 + jl;
         const size_t o = v.at(jl + JOFF, ic + IOFF);
@@ -607,7 +622,7 @@ __global__ void __launch_bounds__(64) line_factor_twisted_kernel(View v, const d
         const bool has_x = up ? has_c : has_a, has_y = up ? has_a : has_c, arm_x = up ? arm_c : arm_a, arm_y = up ? arm_a : arm_c;
         double D[NV][NV], I[NV][NV];
         {
-            const double idt = op == OP_LHS ? rcp_fast(*slot(st, 5*B)) : 0.0;
+            const double idt = op == OP_LHS ? rcp_fast(*slot(st, 5*BP)) : 0.0;
 #pragma unroll
             for (int r = 0; r < NV; r++)
 #pragma unroll
