@@ -543,6 +543,21 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             explicit = {"unavailable": str(ex)[:160]}
 
+    # ---- one implicit Solver::step on the device (src/solver/solver.cpp:66-101,154-175): dt, residual, Jacobian, line factors, GMRES, update
+    implicit = None
+    if world == 1 and not args.no_jacobian and not args.no_linsolve:
+        try:
+            eq.set_state_window(q, jw0, 0)
+            eq.synchronize()
+            t0 = time.time()
+            l2i, info = eq.implicit_step(20.0, 1.0, precond="line_j", restart=20, max_iter=40, rtol=1e-2)
+            eq.synchronize()
+            implicit = {"ms": round((time.time() - t0) * 1e3, 1), "gmres_iterations": info["iterations"], "gmres_rel_residual": info["rel_residual"],
+                        "setup_ms": round(info["setup_ms"], 2), "solve_ms": round(info["solve_ms"], 1),
+                        "what": "sgpu_implicit_step at CFL 20: calc_dt + residual + Jacobian build + twisted line factors + GMRES(20) to 1e-2 + update, device resident"}
+        except Exception as ex:  # noqa: BLE001
+            implicit = {"unavailable": str(ex)[:160]}
+
     # ---- the laminar rows the reference itself has (nv = 4, 104 B/cell): same grid, device resident, beside the COMPILED
     #      REFERENCE (oracle/_ref, kind "reference") on a bounded sample -- the one pairing against the reference's own code
     laminar = None
@@ -656,7 +671,7 @@ def run_ours(args):
                           "l2_flush": "inputs (q %.0f MB + rhs %.0f MB per GPU) exceed the 126 MB L2" % (cells_local * nv * 8 / 1e6, cells_local * nv * 8 / 1e6),
                           "step": "ghost-row exchange (N>1) + boundary conditions + fused residual kernel", "halo": halo_mode},
                "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check, "setup": setup, "explicit_step": explicit,
+               "jacobian": jac, "linear_solve": lin, "laminar": laminar, "flat_plate": plate, "halo_check": halo_check, "setup": setup, "explicit_step": explicit, "implicit_step": implicit,
                "l2norm": [float(x) for x in np.sqrt(l2)]}
         print(json.dumps(out), flush=True)
     eq.close()
