@@ -105,7 +105,11 @@ static int launch_jacobian_march_t(sgpu_ctx* c, const JacParams& p) {
     jp.rpc = (v.njl + best - 1)/best; jp.nchunks = (v.njl + jp.rpc - 1)/jp.rpc;
     kern<<<jp.nstrips*jp.nchunks, 32*JM_WARPS, Cfg::smem_bytes, c->stream>>>(jp);
     CKL(c);
-    jac_fold_kernel<NV><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, p.g, p.m, p.gt, p.q, p.J, p.nslots, p.err);
+    if (v.nic < 8 || v.njl < 8) jac_fold_kernel<NV><<<dim3((v.nic + 127)/128, v.njl), 128, 0, c->stream>>>(v, p.g, p.m, p.gt, p.q, p.J, p.nslots, p.err, 0);
+    else {                                                          // the boundary band only: two thin launches
+        jac_fold_kernel<NV><<<dim3((v.nic + 127)/128, 4), 128, 0, c->stream>>>(v, p.g, p.m, p.gt, p.q, p.J, p.nslots, p.err, 1);
+        jac_fold_kernel<NV><<<dim3((v.njl + 127)/128, 4), 128, 0, c->stream>>>(v, p.g, p.m, p.gt, p.q, p.J, p.nslots, p.err, 2);
+    }
     CKL(c);
     c->launches += 1;
     return SGPU_OK;
