@@ -147,7 +147,10 @@ int sgpu_rk_stage(sgpu_ctx* ctx, int order);
 int sgpu_forward_euler(sgpu_ctx* ctx);
 /* The explicit branch of Solver::step (src/solver/solver.cpp:66,103-134) entirely on the device:
  * calc_dt, 1 (forward_euler) or 4 (rk4_jameson) residual evaluations + updates, then l2sq[nv]
- * of the last rhs.  scheme: 0 = forward_euler, 1 = rk4_jameson. */
+ * of the last rhs.  scheme: 0 = forward_euler, 1 = rk4_jameson.  The Runge-Kutta stage update is written from the residual
+ * kernel's epilogue (bit-identical to the residual + sgpu_rk_stage sequence).  On a j-slab (j_begin/j_end) every evaluation is
+ * preceded by the ghost-row exchange over the registered peer buffers (sgpu_halo_set_peer / sgpu_halo_open_peer) and l2sq holds
+ * THIS slab's sums: all ranks call it once per step and add their l2sq. */
 int sgpu_explicit_step(sgpu_ctx* ctx, int scheme, double cfl, double* l2sq);
 
 /* ---- Jacobian ------------------------------------------------------------------------------ */

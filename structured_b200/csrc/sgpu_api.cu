@@ -832,15 +832,24 @@ int sgpu_forward_euler(sgpu_ctx* c) {
 
 int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
     if (!c || (scheme != 0 && scheme != 1)) { if (c) c->err = "scheme not defined."; return SGPU_ERR_ARG; }   // solver.cpp:119
-    if (c->v.j0 != 0 || c->v.j1 != c->v.njc) FAIL(c, SGPU_ERR_STATE, "sgpu_explicit_step drives a whole grid; on a slab partition the caller interleaves halo exchanges");
+    // On a j-slab every residual evaluation is preceded by the ghost-row exchange over peer memory (sgpu_halo_push / pull: the
+    // neighbours' receive buffers must be registered); l2sq then holds THIS slab's sums, which the caller adds over the ranks.
+    const bool slab = c->v.j0 != 0 || c->v.j1 != c->v.njc;
+    auto exchange = [&](int which) -> int {
+        if (!slab) return SGPU_OK;
+        if (int rc = sgpu_halo_push(c, which)) return rc;
+        return sgpu_halo_pull(c, which);
+    };
     if (int rc = sgpu_calc_dt(c, cfl)) return rc;                  // solver.cpp:66
     if (scheme == 0) {                                             // solver.cpp:103-106
+        if (int rc = exchange(SGPU_STATE_Q)) return rc;
         if (int rc = sgpu_residual(c, SGPU_STATE_Q, 0, l2sq)) return rc;
         return sgpu_forward_euler(c);
     }
     const char* fe = getenv("SGPU_RK_FUSED");
     if (fe && atoi(fe) == 0) {                                     // the two-kernel form (A/B, and what a slab-partitioned caller runs)
         for (int order = 0; order < 4; order++) {                  // solver.cpp:109-112
+            if (int rc = exchange(SGPU_STATE_Q_TMP)) return rc;
             if (int rc = sgpu_residual(c, SGPU_STATE_Q_TMP, 0, order == 3 ? l2sq : nullptr)) return rc;
             if (int rc = sgpu_rk_stage(c, order)) return rc;
         }
@@ -860,6 +869,8 @@ int sgpu_explicit_step(sgpu_ctx* c, int scheme, double cfl, double* l2sq) {
     int rc = SGPU_OK;
     int swaps = 0;
     for (int order = 0; order < 4 && rc == SGPU_OK; order++) {
+        rc = exchange(SGPU_STATE_Q_TMP);
+        if (rc != SGPU_OK) break;
         rc = apply_bcs(c, SGPU_STATE_Q_TMP);
         if (rc != SGPU_OK) break;
         StageUpdate upd{c->q[0], c->dt, c->q_scratch, 4.0 - order};

@@ -261,3 +261,76 @@ def test_three_processes_cuda_ipc_halo_bit_for_bit(ntrans):
     for rank, j0, j1, got in res:
         for rep in range(3):
             assert np.array_equal(got[rep], want[rep][:, j0:j1, :]), (rank, rep)
+
+
+def _explicit_slab_worker(rank, world, port, nic, njc, ntrans, nsteps, cfl, out):
+    import os
+
+    import torch
+    import torch.distributed as dist
+    from structured_b200.api import GpuEulerEquation
+    from structured_b200.slab import partition_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    idev = rank if ndev >= world else 0
+    torch.cuda.set_device(idev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # handles and norms only; the rows travel through peer memory
+    try:
+        case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=1e5)
+        j0, j1 = partition_rows(njc, world)[rank]
+        eq = GpuEulerEquation(case, device=idev, j_begin=j0, j_end=j1)
+        mine = (eq.halo_ipc_handle(LOW), eq.halo_ipc_handle(HIGH))
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        if rank > 0:
+            eq.halo_open_peer(LOW, allh[rank - 1][HIGH])
+        if rank < world - 1:
+            eq.halo_open_peer(HIGH, allh[rank + 1][LOW])
+        q = case.perturbed_q(0.01)
+        own = np.ascontiguousarray(q[:, j0:j1, :])
+        eq.set_state_window(own, j0, 0); eq.set_state_window(own, j0, 1)   # own rows only: every ghost row comes from the exchange
+        dist.barrier()
+        l2 = []
+        for _ in range(nsteps):
+            part = eq.explicit_step(cfl, "rk4_jameson") ** 2               # this slab's sums of rhs^2
+            t = torch.as_tensor(part, dtype=torch.float64)
+            dist.all_reduce(t)
+            l2.append(np.sqrt(t.numpy()))
+        rows = eq.get_state(0)[:, j0:j1, :]
+        out.put((rank, j0, j1, rows, np.array(l2)))
+        dist.barrier()
+        eq.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ndev() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("ntrans", [0, 1])
+def test_explicit_steps_on_three_slabs_equal_one_context_bitwise(ntrans):
+    """sgpu_explicit_step on j-slabs: one call per rank and step runs calc_dt and the four fused Runge-Kutta stages, each preceded
+    by the ghost-row exchange over CUDA-IPC peer buffers (device-side flags, no host synchronisation inside the step).  Three
+    processes reproduce the one-context states BIT FOR BIT after several steps; the norms agree to summation order."""
+    import socket
+
+    import torch.multiprocessing as mp
+    from structured_b200.api import GpuEulerEquation
+    nic, njc, world, nsteps, cfl = 150, 60, 3, 3, 0.5
+    case = turbulent_channel_case(nic, njc, ntrans=ntrans, reynolds=1e5)
+    q = case.perturbed_q(0.01)
+    one = GpuEulerEquation(case, device=0)
+    one.set_state(q, 0); one.set_state(q, 1)
+    l2_one = np.array([one.explicit_step(cfl, "rk4_jameson") for _ in range(nsteps)])
+    want = one.get_state(0)
+    one.close()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_explicit_slab_worker, args=(r, world, port, nic, njc, ntrans, nsteps, cfl, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, j0, j1, rows, l2 in res:
+        assert np.array_equal(rows, want[:, j0:j1, :]), rank
+        assert np.abs(l2 - l2_one).max() <= 1e-12 * np.abs(l2_one).max()
